@@ -1,0 +1,401 @@
+// conv_tc.cu -- implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+// GEMM view (stride-1 convs, any dilation / padding):
+//   D[128 output pixels, BLOCK_N couts] += sum over taps (ky,kx) and Cin chunks  A_tap[128, BK] * W_tap[BLOCK_N, BK]^T
+//   * M tile = a TH x TW spatial patch of one image (TH*TW = 128).  For every tap the A operand is ONE 4-D
+//     TMA box load {BK channels, TW, TH, 1} from the NHWC activation at the tap-shifted coordinate; the TMA
+//     unit zero-fills out-of-image elements, which implements the conv padding with no im2col buffer.
+//     The box lands in shared memory as 128 rows x 128 bytes with the 128B swizzle = the canonical K-major
+//     UMMA operand layout (8-row atoms, SBO = 1024 B).
+//   * B operand = weights [Cout][KH*KW*Cin] (K contiguous), 2-D TMA box {BK, BLOCK_N}, same layout.
+//   * Accumulator: 128 lanes x BLOCK_N fp32 columns of TMEM; one elected thread issues tcgen05.mma
+//     (kind::f16 for bf16 operands, kind::tf32 for fp32 operands), tcgen05.commit releases smem stages
+//     and signals the epilogue through mbarriers.
+//   * Epilogue (4 warps, one TMEM lane quarter each): tcgen05.ld -> folded-BN scale/shift (+bias)
+//     -> (+residual) -> ReLU/PReLU -> NHWC store (channel slice of the destination = fused torch.cat).
+//   * Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+//   Non-persistent: one CTA per (m-tile, n-tile); two CTAs co-reside per SM so one CTA's epilogue overlaps
+//   the other's main loop.
+#include "common.cuh"
+#include <cuda.h>
+#include <mutex>
+
+namespace arseg {
+
+constexpr int TC_THREADS = 192;
+constexpr int TC_BM = 128;
+constexpr int TC_ROW_BYTES = 128;           // one swizzle row = BK elements
+constexpr int TC_A_STAGE = TC_BM * TC_ROW_BYTES;  // 16 KB
+
+struct TcParams {
+    const float* scale; const float* shift; const void* res; void* out;
+    int N, Ho, Wo, Cin, Cout, KH, KW, pad, dil, ocs, oco, act;
+    float slope;
+    int TH, TW, tiles_x, tiles_y, n_tiles, kchunks;  // kchunks = Cin / BK
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a mis-programmed descriptor must not hang the GPU box -- trap after ~4e9 cycles.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("arseg conv_tc: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4 | [32,46) stride byte offset >> 4 (8 rows * 128 B = 1024) | [46,48) version = 1
+//   | [61,64) layout type = 2 (SWIZZLE_128B).  LBO is unused for swizzled K-major operands.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) @4, a/b format @7/@10
+// (BF16 = 1, TF32 = 2), K-major A and B, N>>3 @17, M>>4 @24.
+__host__ __device__ constexpr uint32_t umma_idesc(int fmt, int M, int N) {
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+template <bool TF32>
+__device__ __forceinline__ void umma_ss(uint64_t da, uint64_t db, uint32_t tmem_d, uint32_t accumulate, uint32_t idesc) {
+    if (TF32)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------
+template <typename T, int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                             const __grid_constant__ CUtensorMap map_b, TcParams p) {
+    constexpr bool TF32 = sizeof(T) == 4;
+    constexpr int BK = TC_ROW_BYTES / (int)sizeof(T);     // elements per swizzle row: 64 (bf16) / 32 (tf32)
+    constexpr int UMMA_K = 32 / (int)sizeof(T);           // 16 / 8
+    constexpr int B_STAGE = BLOCK_N * TC_ROW_BYTES;
+    constexpr uint32_t STAGE_BYTES = TC_A_STAGE + B_STAGE;
+    constexpr uint32_t IDESC = umma_idesc(TF32 ? 2 : 1, TC_BM, BLOCK_N);
+    constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES * TC_A_STAGE;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // tile coordinates: n-tile fastest so CTAs sharing an A tile are co-scheduled (L2 reuse)
+    int b = blockIdx.x;
+    const int nt = b % p.n_tiles; b /= p.n_tiles;
+    const int txi = b % p.tiles_x; b /= p.tiles_x;
+    const int tyi = b % p.tiles_y;
+    const int img = b / p.tiles_y;
+    const int x0 = txi * p.TW, y0 = tyi * p.TH, n0 = nt * BLOCK_N;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int taps = p.KH * p.KW;
+    const int kiters = taps * p.kchunks;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int it = 0; it < kiters; ++it) {
+                const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
+                const int ky = tap / p.KW, kx = tap - ky * p.KW;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+                tma_load_4d(&map_a, &full_bar[stage], smem_a + stage * TC_A_STAGE, kc * BK, x0 - p.pad + kx * p.dil,
+                            y0 - p.pad + ky * p.dil, img);
+                tma_load_2d(&map_b, &full_bar[stage], smem_b + stage * B_STAGE, tap * p.Cin + kc * BK, n0);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        int stage = 0; uint32_t phase = 0;
+        for (int it = 0; it < kiters; ++it) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint64_t da = umma_desc_sw128(smem_u32(smem_a + stage * TC_A_STAGE));
+                const uint64_t db = umma_desc_sw128(smem_u32(smem_b + stage * B_STAGE));
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k)   // +32 bytes per UMMA_K step inside the swizzle row
+                    umma_ss<TF32>(da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), tmem_base, (it | k) != 0, IDESC);
+                umma_commit(&empty_bar[stage]);                       // frees the smem stage when the MMAs retire
+                if (it == kiters - 1) umma_commit(tmem_full_bar);     // accumulator complete -> epilogue
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else {
+        // epilogue warps 2..5: TMEM lane quarter = warp % 4
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const int gy = y0 + row / p.TW, gx = x0 + row % p.TW;
+        const bool valid = gy < p.Ho && gx < p.Wo;
+        const size_t pix = ((size_t)img * p.Ho + gy) * p.Wo + gx;
+        T* __restrict__ out = reinterpret_cast<T*>(p.out) + pix * p.ocs + p.oco;
+        const T* __restrict__ res = p.res ? reinterpret_cast<const T*>(p.res) + pix * p.Cout : nullptr;
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int cb = 0; cb < BLOCK_N; cb += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)cb, r);
+            tmem_ld_wait();
+            if (!valid) continue;
+            const int co0 = n0 + cb;
+            if (co0 >= p.Cout) continue;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int co = co0 + j;
+                float a = __uint_as_float(r[j]);
+                if (co < p.Cout) {
+                    a = a * (p.scale ? __ldg(p.scale + co) : 1.f) + (p.shift ? __ldg(p.shift + co) : 0.f);
+                    if (res) a += to_f32(res[co]);
+                    if (p.act == ARSEG_ACT_RELU) a = fmaxf(a, 0.f);
+                    else if (p.act == ARSEG_ACT_PRELU) a = a > 0.f ? a : a * p.slope;
+                }
+                v[j] = a;
+            }
+            if (co0 + 32 <= p.Cout && ((p.ocs | p.oco) % (16 / (int)sizeof(T)) == 0)) {
+                if (TF32) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + co0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        uint4 pk;
+                        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                        pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                        pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + co0 + j) = pk;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (co0 + j < p.Cout) out[co0 + j] = from_f32<T>(v[j]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    });
+    return fn;
+}
+
+static bool tf32_tma_round() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("ARSEG_TF32_TMA_ROUND");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+static void pick_tile(int Ho, int Wo, int& TH, int& TW) {
+    long long best = -1;
+    for (int tw = 8; tw <= 128; tw *= 2) {
+        const int th = 128 / tw;
+        const long long tiles = (long long)ceil_div(Ho, th) * ceil_div(Wo, tw);
+        // fewest tiles; tie -> squarer tile (less halo traffic)
+        if (best < 0 || tiles < best || (tiles == best && abs(th - tw) < abs(TH - TW))) { best = tiles; TH = th; TW = tw; }
+    }
+}
+
+bool conv_tc_supported(const arseg_conv_desc* d) {
+    const int es = d->engine == ARSEG_CONV_TC_TF32 ? 4 : 2;
+    const int bk = 128 / es;
+    if (d->engine == ARSEG_CONV_TC_TF32 && d->dtype != ARSEG_F32) return false;
+    if (d->engine == ARSEG_CONV_TC_BF16 && d->dtype != ARSEG_BF16) return false;
+    if (d->stride != 1) return false;
+    if (d->Cin % bk != 0) return false;
+    if (d->Cout < 16) return false;
+    const int Ho = d->Hi + 2 * d->pad - d->dil * (d->KH - 1), Wo = d->Wi + 2 * d->pad - d->dil * (d->KW - 1);
+    if (Ho != d->Hi || Wo != d->Wi) return false;   // "same" convs only (all stride-1 convs on the path)
+    if ((uintptr_t)d->in % 16 || (uintptr_t)d->w % 16) return false;
+    return true;
+}
+
+template <typename T, int BLOCK_N, int STAGES>
+static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st) {
+    constexpr size_t smem = (size_t)STAGES * (TC_A_STAGE + BLOCK_N * TC_ROW_BYTES) + (2 * STAGES + 1) * 8 + 16 + 1024;
+    auto kern = conv_tc_kernel<T, BLOCK_N, STAGES>;
+    static bool configured[64] = {false};
+    int dev = 0;
+    ARSEG_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        ARSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    const long long blocks = (long long)p.N * p.tiles_y * p.tiles_x * p.n_tiles;
+    ARSEG_REQUIRE(blocks > 0 && blocks < 2147483647LL, "conv_tc: grid too large");
+    kern<<<(unsigned)blocks, TC_THREADS, smem, st>>>(ma, mb, p);
+    ARSEG_CHECK_LAUNCH("conv_tc");
+    return ARSEG_OK;
+}
+
+int conv_tc_launch(const arseg_conv_desc* d, cudaStream_t st) {
+    EncodeTiledFn encode = get_encode();
+    if (!encode) { set_error("conv_tc: cuTensorMapEncodeTiled entry point not available"); return ARSEG_E_CUDA; }
+    const bool tf32 = d->engine == ARSEG_CONV_TC_TF32;
+    const int es = tf32 ? 4 : 2, bk = 128 / es;
+    TcParams p;
+    p.scale = d->scale; p.shift = d->shift; p.res = d->residual; p.out = d->out;
+    p.N = d->N; p.Ho = d->Hi; p.Wo = d->Wi; p.Cin = d->Cin; p.Cout = d->Cout; p.KH = d->KH; p.KW = d->KW;
+    p.pad = d->pad; p.dil = d->dil; p.ocs = d->out_cstride; p.oco = d->out_coff; p.act = d->act; p.slope = d->prelu_slope;
+    pick_tile(p.Ho, p.Wo, p.TH, p.TW);
+    p.tiles_x = ceil_div(p.Wo, p.TW); p.tiles_y = ceil_div(p.Ho, p.TH);
+    p.kchunks = d->Cin / bk;
+    const int block_n = d->Cout >= 128 ? 128 : (d->Cout > 32 ? 64 : 32);
+    p.n_tiles = ceil_div(d->Cout, block_n);
+
+    const CUtensorMapDataType dt = tf32 ? (tf32_tma_round() ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32)
+                                        : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    CUtensorMap ma, mb;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->Wi, (cuuint64_t)d->Hi, (cuuint64_t)d->N};
+        cuuint64_t strides[3] = {(cuuint64_t)d->Cin * es, (cuuint64_t)d->Wi * d->Cin * es, (cuuint64_t)d->Hi * d->Wi * d->Cin * es};
+        cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = encode(&ma, dt, 4, const_cast<void*>(d->in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(A) failed (%d)", (int)r); return ARSEG_E_CUDA; }
+    }
+    {
+        const cuuint64_t K = (cuuint64_t)d->KH * d->KW * d->Cin;
+        cuuint64_t dims[2] = {K, (cuuint64_t)d->Cout};
+        cuuint64_t strides[1] = {K * es};
+        cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)block_n};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&mb, dt, 2, const_cast<void*>(d->w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(B) failed (%d)", (int)r); return ARSEG_E_CUDA; }
+    }
+    if (tf32) {
+        if (block_n == 128) return launch_tc<float, 128, 3>(ma, mb, p, st);
+        if (block_n == 64) return launch_tc<float, 64, 4>(ma, mb, p, st);
+        return launch_tc<float, 32, 4>(ma, mb, p, st);
+    }
+    if (block_n == 128) return launch_tc<__nv_bfloat16, 128, 3>(ma, mb, p, st);
+    if (block_n == 64) return launch_tc<__nv_bfloat16, 64, 4>(ma, mb, p, st);
+    return launch_tc<__nv_bfloat16, 32, 4>(ma, mb, p, st);
+}
+
+}  // namespace arseg

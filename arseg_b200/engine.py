@@ -1,0 +1,455 @@
+"""Execution plans: the LR-branch networks of AR-Seg expressed as sequences of C-ABI kernel launches.
+
+A `Plan` is built once per (architecture, batch, resolution, precision): it folds BatchNorm into
+per-channel scale/shift, repacks weights OIHW -> [O][KH][KW][I], pre-allocates every activation buffer
+and records the launches as pre-bound ctypes calls.  `Plan.run()` replays them on the current stream
+(optionally through a CUDA graph), so the steady-state step has no Python-side tensor work.
+
+Precision modes
+  'fp32' : fp32 NHWC activations, SIMT implicit-GEMM convs (exact fp32 FMA; the parity gate)
+  'tf32' : fp32 NHWC activations, tcgen05 kind::tf32 convs (what cuDNN does for the reference on Ampere+)
+  'bf16' : bf16 NHWC activations, tcgen05 kind::f16 convs, fp32 accumulate / epilogue
+Layers the tcgen05 engine does not take (stride 2, Cout < 16, tiny spatial extents) run on the SIMT engine
+in the same dtype.
+
+Reference structure restated here (file:line in /root/reference): model/extractors.py:30-66,108-158;
+model/pspnet.py:14-46,103-131,198-231; model/bisenet.py:25-113,162-180,207-223,243-306,326-340,360-399,
+481-575; model/pspnet_semseg.py:12-30,118-250.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+from .ops import dtype_code
+
+SD = Dict[str, torch.Tensor]
+
+_PRECISIONS = {
+    "fp32": (torch.float32, L.CONV_SIMT_F32),
+    "tf32": (torch.float32, L.CONV_TC_TF32),
+    "bf16": (torch.bfloat16, L.CONV_TC_BF16),
+}
+
+
+def fold_bn(sd: SD, bn: str, conv_bias: Optional[torch.Tensor] = None, eps: float = 1e-5) -> Tuple[torch.Tensor, torch.Tensor]:
+    """BatchNorm2d(eval) folded to y = x*scale + shift (conv bias absorbed)."""
+    g, b = sd[bn + "weight"].double(), sd[bn + "bias"].double()
+    m, v = sd[bn + "running_mean"].double(), sd[bn + "running_var"].double()
+    scale = g / torch.sqrt(v + eps)
+    shift = b - m * scale
+    if conv_bias is not None:
+        shift = shift + conv_bias.double() * scale
+    return scale.float(), shift.float()
+
+
+class Plan:
+    def __init__(self, device: torch.device, precision: str = "fp32"):
+        if precision not in _PRECISIONS:
+            raise ValueError("precision must be one of %s" % list(_PRECISIONS))
+        self.device = torch.device(device)
+        self.precision = precision
+        self.act_dtype, self.engine = _PRECISIONS[precision]
+        self.lib = L.load()
+        self.steps: List[Callable[[int], int]] = []
+        self.names: List[str] = []
+        self.keep: List[object] = []       # keeps device tensors / ctypes structs alive
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.conv_flops = 0                # 2*MACs of conv/linear layers as executed
+        self.n_launches = 0
+
+    # -- helpers -------------------------------------------------------------------------------
+    def dev(self, t: torch.Tensor, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+        t = t.detach().to(device=self.device, dtype=dtype or t.dtype).contiguous()
+        self.keep.append(t)
+        return t
+
+    def empty(self, shape: Sequence[int], dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+        t = torch.empty(tuple(shape), dtype=dtype or self.act_dtype, device=self.device)
+        self.keep.append(t)
+        return t
+
+    def _add(self, name: str, fn: Callable[[int], int]) -> None:
+        self.steps.append(fn)
+        self.names.append(name)
+        self.n_launches += 1
+
+    def conv_weight(self, w: torch.Tensor) -> torch.Tensor:
+        """OIHW -> [O][KH][KW][I] in the activation dtype."""
+        return self.dev(w.detach().permute(0, 2, 3, 1).contiguous(), self.act_dtype)
+
+    # -- ops -----------------------------------------------------------------------------------
+    def conv(self, x: torch.Tensor, w_oihw: torch.Tensor, scale=None, shift=None, *, stride=1, pad=0, dil=1,
+             act=L.ACT_NONE, slope=0.0, residual=None, out=None, coff=0, name="conv") -> torch.Tensor:
+        N, Hi, Wi, Cin = x.shape
+        Cout, _, KH, KW = w_oihw.shape
+        Ho = (Hi + 2 * pad - dil * (KH - 1) - 1) // stride + 1
+        Wo = (Wi + 2 * pad - dil * (KW - 1) - 1) // stride + 1
+        w = self.conv_weight(w_oihw)
+        sc = self.dev(scale, torch.float32) if scale is not None else None
+        sh = self.dev(shift, torch.float32) if shift is not None else None
+        if out is None:
+            out = self.empty((N, Ho, Wo, Cout))
+        engine = self.engine
+        es = 4 if self.act_dtype == torch.float32 else 2
+        tc_ok = (engine != L.CONV_SIMT_F32 and stride == 1 and Cin % (128 // es) == 0 and Cout >= 16
+                 and Ho == Hi and Wo == Wi and Hi * Wi >= 64)
+        if not tc_ok:
+            engine = L.CONV_SIMT_F32
+        d = L.ConvDesc(x.data_ptr(), w.data_ptr(), sc.data_ptr() if sc is not None else None,
+                       sh.data_ptr() if sh is not None else None, residual.data_ptr() if residual is not None else None,
+                       out.data_ptr(), dtype_code(self.act_dtype), N, Hi, Wi, Cin, Cout, KH, KW, stride, pad, dil,
+                       out.shape[-1], coff, act, float(slope), engine)
+        self.keep.append(d)
+        fn = self.lib.arseg_conv2d_nhwc
+        self._add("%s[%s %dx%d %d->%d @%dx%d]" % (name, {1: "simt", 2: "tf32", 3: "bf16"}[engine], KH, KW, Cin, Cout, Ho, Wo),
+                  lambda s, d=d: fn(C.byref(d), s))
+        self.conv_flops += 2 * N * Ho * Wo * Cout * Cin * KH * KW
+        return out
+
+    def stem(self, x_nchw: torch.Tensor, w_oihw: torch.Tensor, scale, shift, name="stem") -> torch.Tensor:
+        N, _, H, W = x_nchw.shape
+        Cout = w_oihw.shape[0]
+        Ho, Wo = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+        w = self.dev(w_oihw.detach().permute(0, 2, 3, 1).contiguous(), torch.float32)
+        sc, sh = self.dev(scale, torch.float32), self.dev(shift, torch.float32)
+        out = self.empty((N, Ho, Wo, Cout))
+        fn = self.lib.arseg_conv_stem7x7s2
+        args = (x_nchw.data_ptr(), w.data_ptr(), sc.data_ptr(), sh.data_ptr(), out.data_ptr(), dtype_code(self.act_dtype),
+                N, H, W, Cout)
+        self._add(name, lambda s: fn(*args, s))
+        self.conv_flops += 2 * N * Ho * Wo * Cout * 147
+        return out
+
+    def maxpool(self, x: torch.Tensor) -> torch.Tensor:
+        N, H, W, Cc = x.shape
+        out = self.empty((N, (H - 1) // 2 + 1, (W - 1) // 2 + 1, Cc))
+        fn = self.lib.arseg_maxpool3x3s2_nhwc
+        args = (x.data_ptr(), out.data_ptr(), dtype_code(self.act_dtype), N, H, W, Cc)
+        self._add("maxpool", lambda s: fn(*args, s))
+        return out
+
+    def resize(self, x: torch.Tensor, Ho: int, Wo: int, mode: int, out=None, coff=0, name="resize") -> torch.Tensor:
+        N, Hi, Wi, Cc = x.shape
+        if out is None:
+            out = self.empty((N, Ho, Wo, Cc), x.dtype)
+        fn = self.lib.arseg_resize_nhwc
+        args = (x.data_ptr(), out.data_ptr(), dtype_code(x.dtype), N, Hi, Wi, Cc, Ho, Wo, out.shape[-1], coff, mode)
+        self._add(name, lambda s: fn(*args, s))
+        return out
+
+    def resize_nchw(self, x: torch.Tensor, Ho: int, Wo: int, mode: int, name="resize_nchw") -> torch.Tensor:
+        N, Cc, Hi, Wi = x.shape
+        out = self.empty((N, Cc, Ho, Wo), torch.float32)
+        fn = self.lib.arseg_resize_nchw_f32
+        args = (x.data_ptr(), out.data_ptr(), N * Cc, Hi, Wi, Ho, Wo, mode)
+        self._add(name, lambda s: fn(*args, s))
+        return out
+
+    def avgpool(self, x: torch.Tensor, Ho: int, Wo: int, fp32_out: bool = False) -> torch.Tensor:
+        N, H, W, Cc = x.shape
+        odt = torch.float32 if fp32_out else x.dtype
+        out = self.empty((N, Ho, Wo, Cc), odt)
+        fn = self.lib.arseg_adaptive_avgpool_nhwc
+        args = (x.data_ptr(), out.data_ptr(), dtype_code(x.dtype), dtype_code(odt), N, H, W, Cc, Ho, Wo)
+        self._add("avgpool%dx%d" % (Ho, Wo), lambda s: fn(*args, s))
+        return out
+
+    def gmaxpool(self, x: torch.Tensor) -> torch.Tensor:
+        N, H, W, Cc = x.shape
+        out = self.empty((N, Cc), torch.float32)
+        fn = self.lib.arseg_global_maxpool_nhwc
+        args = (x.data_ptr(), out.data_ptr(), dtype_code(x.dtype), N, H, W, Cc)
+        self._add("gmaxpool", lambda s: fn(*args, s))
+        return out
+
+    def linear(self, x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], relu: bool, name="linear") -> torch.Tensor:
+        N, K = x.shape[0], x.numel() // x.shape[0]
+        M = w.shape[0]
+        wd = self.dev(w.reshape(M, K), torch.float32)
+        bd = self.dev(b, torch.float32) if b is not None else None
+        out = self.empty((N, M), torch.float32)
+        fn = self.lib.arseg_linear_f32
+        args = (x.data_ptr(), wd.data_ptr(), bd.data_ptr() if bd is not None else None, out.data_ptr(), N, K, M, int(relu))
+        self._add(name, lambda s: fn(*args, s))
+        self.conv_flops += 2 * N * K * M
+        return out
+
+    def gate(self, feat: torch.Tensor, gate: torch.Tensor, gs, gb, add_identity=False, add_chan=None, add_pix=None,
+             name="gate") -> torch.Tensor:
+        N, H, W, Cc = feat.shape
+        gsd = self.dev(gs, torch.float32) if gs is not None else None
+        gbd = self.dev(gb, torch.float32) if gb is not None else None
+        out = self.empty((N, H, W, Cc), feat.dtype)
+        fn = self.lib.arseg_gate_nhwc
+        args = (feat.data_ptr(), gate.data_ptr(), gsd.data_ptr() if gsd is not None else None,
+                gbd.data_ptr() if gbd is not None else None, int(add_identity),
+                add_chan.data_ptr() if add_chan is not None else None, add_pix.data_ptr() if add_pix is not None else None,
+                out.data_ptr(), dtype_code(feat.dtype), N, H, W, Cc)
+        self._add(name, lambda s: fn(*args, s))
+        return out
+
+    def to_nchw(self, x: torch.Tensor, name="nhwc_to_nchw") -> torch.Tensor:
+        N, H, W, Cc = x.shape
+        out = self.empty((N, Cc, H, W), torch.float32)
+        fn = self.lib.arseg_nhwc_to_nchw
+        args = (x.data_ptr(), dtype_code(x.dtype), out.data_ptr(), N, Cc, H, W)
+        self._add(name, lambda s: fn(*args, s))
+        return out
+
+    def creff(self, hr: torch.Tensor, lr: torch.Tensor, sd: SD, prefix: str, k: int, *, flow: Optional[torch.Tensor] = None,
+              hr_shared=False, lr_layout=L.NHWC, wcls=None, bcls=None, log_softmax=False, want_p=True, want_logits=True,
+              want_argmax=False, name="creff_fused"):
+        """Fused MV-warp + CReFF (+ classifier).  hr NCHW fp32 [1|N,C,H,W]; lr [N,h,w,C] NHWC (or NCHW fp32)."""
+        _, Cc, H, W = hr.shape
+        if lr_layout == L.NHWC:
+            N, h, w, _ = lr.shape
+        else:
+            N, _, h, w = lr.shape
+        f32 = torch.float32
+        ws = [self.dev(sd[prefix + n].reshape(-1), f32) for n in
+              ("lr_query_conv.weight", "lr_query_conv.bias", "hr_key_conv.weight", "hr_key_conv.bias",
+               "hr_value_conv.weight", "hr_value_conv.bias")]
+        ncls = 0
+        wc = bc = None
+        if wcls is not None:
+            ncls = wcls.shape[0]
+            wc = self.dev(wcls.reshape(ncls, Cc), f32)
+            bc = self.dev(bcls, f32) if bcls is not None else None
+        out_p = self.empty((N, Cc, H, W), f32) if want_p else None
+        out_l = self.empty((N, ncls, H, W), f32) if (want_logits and ncls) else None
+        out_a = self.empty((N, H, W), torch.uint8) if (want_argmax and ncls) else None
+        Hm, Wm = (flow.shape[1], flow.shape[2]) if flow is not None else (0, 0)
+        a = L.CreffArgs(hr.data_ptr(), int(hr_shared), flow.data_ptr() if flow is not None else None,
+                        dtype_code(flow.dtype) if flow is not None else 0, Hm, Wm, lr.data_ptr(), lr_layout,
+                        dtype_code(lr.dtype), h, w, *[t.data_ptr() for t in ws],
+                        wc.data_ptr() if wc is not None else None, bc.data_ptr() if bc is not None else None, ncls,
+                        int(log_softmax), out_p.data_ptr() if out_p is not None else None,
+                        out_l.data_ptr() if out_l is not None else None, out_a.data_ptr() if out_a is not None else None,
+                        N, Cc, H, W, k)
+        self.keep.append(a)
+        fn = self.lib.arseg_creff_fused_fwd
+        self._add(name, lambda s, a=a: fn(C.byref(a), s))
+        return out_p, out_l, out_a
+
+    def log_softmax_nchw(self, x: torch.Tensor) -> torch.Tensor:
+        N, K, H, W = x.shape
+        out = self.empty((N, K, H, W), torch.float32)
+        fn = self.lib.arseg_log_softmax_nchw
+        args = (x.data_ptr(), out.data_ptr(), N, K, H, W)
+        self._add("log_softmax", lambda s: fn(*args, s))
+        return out
+
+    def resize_argmax(self, logits: torch.Tensor, Ho: int, Wo: int, mode: int, want_logits=False):
+        N, K, H, W = logits.shape
+        pred = self.empty((N, Ho, Wo), torch.uint8)
+        up = self.empty((N, K, Ho, Wo), torch.float32) if want_logits else None
+        fn = self.lib.arseg_resize_argmax_nchw
+        args = (logits.data_ptr(), up.data_ptr() if up is not None else None, pred.data_ptr(), N, K, H, W, Ho, Wo, mode)
+        self._add("resize_argmax", lambda s: fn(*args, s))
+        return pred, up
+
+    # -- execution -----------------------------------------------------------------------------
+    def launch(self) -> None:
+        """Enqueue every kernel of the plan on the current stream."""
+        with torch.cuda.device(self.device):
+            s = torch.cuda.current_stream().cuda_stream
+            for name, fn in zip(self.names, self.steps):
+                rc = fn(s)
+                if rc != L.OK:
+                    L.check(rc, name)
+
+    def capture(self) -> None:
+        """Capture the launch sequence into a CUDA graph (replayed by run())."""
+        with torch.cuda.device(self.device):
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self.launch()          # warm-up outside capture (function attributes, TMA entry point)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.launch()
+            self.graph = g
+
+    def run(self) -> None:
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.launch()
+
+
+# ==============================================================================================
+# network builders (functional over a reference-keyed state_dict)
+# ==============================================================================================
+
+def _cbr(pl: Plan, sd: SD, p: str, x, *, stride=1, pad=1, out=None, coff=0, name=None):
+    """ConvBNReLU (model/bisenet.py:162-180): conv(no bias) + BN + ReLU."""
+    sc, sh = fold_bn(sd, p + "bn.")
+    return pl.conv(x, sd[p + "conv.weight"], sc, sh, stride=stride, pad=pad, act=L.ACT_RELU, out=out, coff=coff,
+                   name=name or p.rstrip("."))
+
+
+def _basic_block(pl: Plan, sd: SD, p: str, x, stride: int, dil1: int, dil2: int, ds_stride: int):
+    """BasicBlock (model/extractors.py:36-66 / model/bisenet.py:31-60)."""
+    s1, b1 = fold_bn(sd, p + "bn1.")
+    t = pl.conv(x, sd[p + "conv1.weight"], s1, b1, stride=stride, pad=dil1, dil=dil1, act=L.ACT_RELU, name=p + "conv1")
+    res = x
+    if (p + "downsample.0.weight") in sd:
+        sd_, bd_ = fold_bn(sd, p + "downsample.1.")
+        res = pl.conv(x, sd[p + "downsample.0.weight"], sd_, bd_, stride=ds_stride, pad=0, name=p + "downsample")
+    s2, b2 = fold_bn(sd, p + "bn2.")
+    return pl.conv(t, sd[p + "conv2.weight"], s2, b2, pad=dil2, dil=dil2, act=L.ACT_RELU, residual=res, name=p + "conv2")
+
+
+def _resnet_os8(pl: Plan, sd: SD, p: str, x_nchw, semseg: bool):
+    """Dilated ResNet-18, output stride 8 (model/extractors.py:108-158; semseg rewrite model/pspnet_semseg.py:145-154)."""
+    if semseg:
+        c1, b1, lp = p + "layer0.0.", p + "layer0.1.", p
+    else:
+        c1, b1, lp = p + "feats.conv1.", p + "feats.bn1.", p + "feats."
+    sc, sh = fold_bn(sd, b1)
+    x = pl.stem(x_nchw, sd[c1 + "weight"], sc, sh)
+    x = pl.maxpool(x)
+    x = _basic_block(pl, sd, lp + "layer1.0.", x, 1, 1, 1, 1)
+    x = _basic_block(pl, sd, lp + "layer1.1.", x, 1, 1, 1, 1)
+    x = _basic_block(pl, sd, lp + "layer2.0.", x, 2, 1, 1, 2)
+    x = _basic_block(pl, sd, lp + "layer2.1.", x, 1, 1, 1, 1)
+    x = _basic_block(pl, sd, lp + "layer3.0.", x, 1, 1, 2 if semseg else 1, 1)
+    x3 = _basic_block(pl, sd, lp + "layer3.1.", x, 1, 2, 2, 1)
+    x = _basic_block(pl, sd, lp + "layer4.0.", x3, 1, 1, 4 if semseg else 1, 1)
+    x4 = _basic_block(pl, sd, lp + "layer4.1.", x, 1, 4, 4, 1)
+    return x4, x3
+
+
+def build_psp_phase1(pl: Plan, sd: SD, x_nchw: torch.Tensor, p: str = "", sizes=(1, 2, 3, 6), aux: bool = True):
+    """PSPNetWithFuse.forward_phase1 (model/pspnet.py:198-217) -> (cls fp32 [N,ncls] | None, p NHWC [N,h,w,64])."""
+    f, x3 = _resnet_os8(pl, sd, p, x_nchw, semseg=False)
+    N, h, w, Cf = f.shape
+    cat = pl.empty((N, h, w, Cf * (len(sizes) + 1)))
+    for i, s in enumerate(sizes):                                   # PSPModule stages (model/pspnet.py:22-30)
+        t = pl.avgpool(f, s, s)
+        t = pl.conv(t, sd[p + "psp.stages.%d.1.weight" % i], name="psp.stage%d" % i)
+        pl.resize(t, h, w, L.RESIZE_BILINEAR, out=cat, coff=i * Cf, name="psp.up%d" % i)
+    pl.resize(f, h, w, L.RESIZE_NEAREST, out=cat, coff=len(sizes) * Cf, name="psp.cat_feats")
+    t = pl.conv(cat, sd[p + "psp.bottleneck.weight"], None, sd[p + "psp.bottleneck.bias"], act=L.ACT_RELU, name="psp.bottleneck")
+    for u in ("up_1.", "up_2.", "up_3."):                           # PSPUpsample (model/pspnet.py:34-46)
+        Nn, hh, ww, _ = t.shape
+        t = pl.resize(t, 2 * hh, 2 * ww, L.RESIZE_BILINEAR, name=u + "upsample")
+        sc, sh = fold_bn(sd, p + u + "conv.1.", sd[p + u + "conv.0.bias"])
+        t = pl.conv(t, sd[p + u + "conv.0.weight"], sc, sh, pad=1, act=L.ACT_PRELU,
+                    slope=float(sd[p + u + "conv.2.weight"].reshape(-1)[0]), name=u + "conv")
+    cls = None
+    if aux:                                                         # model/pspnet.py:215-217
+        a = pl.gmaxpool(x3)
+        a = pl.linear(a, sd[p + "classifier.0.weight"], sd[p + "classifier.0.bias"], True, "classifier.0")
+        cls = pl.linear(a, sd[p + "classifier.2.weight"], sd[p + "classifier.2.bias"], False, "classifier.2")
+    return cls, t
+
+
+def build_semseg_phase1(pl: Plan, sd: SD, x_nchw: torch.Tensor, p: str = "", bins=(1, 2, 3, 6)):
+    """pspnet_semseg.PSPNetWithFuse.forward_phase1 (model/pspnet_semseg.py:223-235) -> (x_tmp NHWC, p NHWC [N,h,w,512])."""
+    x4, x3 = _resnet_os8(pl, sd, p, x_nchw, semseg=True)
+    N, h, w, Cf = x4.shape
+    red = Cf // len(bins)
+    cat = pl.empty((N, h, w, 2 * Cf))
+    pl.resize(x4, h, w, L.RESIZE_NEAREST, out=cat, coff=0, name="ppm.cat_x")          # x first (:27)
+    for i, b in enumerate(bins):
+        t = pl.avgpool(x4, b, b)
+        sc, sh = fold_bn(sd, p + "ppm.features.%d.2." % i)
+        t = pl.conv(t, sd[p + "ppm.features.%d.1.weight" % i], sc, sh, act=L.ACT_RELU, name="ppm.branch%d" % i)
+        pl.resize(t, h, w, L.RESIZE_BILINEAR_AC, out=cat, coff=Cf + i * red, name="ppm.up%d" % i)
+    sc, sh = fold_bn(sd, p + "cls.1.")
+    t = pl.conv(cat, sd[p + "cls.0.weight"], sc, sh, pad=1, act=L.ACT_RELU, name="cls.0")
+    return x3, t
+
+
+def _arm(pl: Plan, sd: SD, p: str, x, add_chan=None, add_pix=None):
+    """AttentionRefinementModule (model/bisenet.py:243-260) + the branch sum that follows it (:295/:301)."""
+    feat = _cbr(pl, sd, p + "conv.", x)
+    pooled = pl.avgpool(feat, 1, 1, fp32_out=True)
+    g = pl.linear(pooled, sd[p + "conv_atten.weight"], None, False, p + "conv_atten")
+    gs, gb = fold_bn(sd, p + "bn_atten.")
+    return pl.gate(feat, g, gs, gb, add_chan=add_chan, add_pix=add_pix, name=p + "gate")
+
+
+def build_bisenet_phase1(pl: Plan, sd: SD, x_nchw: torch.Tensor, p: str = "", aux: bool = True):
+    """BiSeNetV1WithFuse.forward_phase1 (model/bisenet.py:546-563), aux_mode='train'
+    -> (out16 NCHW | None, out32 NCHW | None, middle_feat NHWC [N,h8,w8,256])."""
+    r = p + "cp.resnet."
+    sc, sh = fold_bn(sd, r + "bn1.")
+    x = pl.stem(x_nchw, sd[r + "conv1.weight"], sc, sh, name="cp.stem")
+    x = pl.maxpool(x)
+    x = _basic_block(pl, sd, r + "layer1.0.", x, 1, 1, 1, 1)
+    x = _basic_block(pl, sd, r + "layer1.1.", x, 1, 1, 1, 1)
+    x = _basic_block(pl, sd, r + "layer2.0.", x, 2, 1, 1, 2)
+    f8 = _basic_block(pl, sd, r + "layer2.1.", x, 1, 1, 1, 1)
+    x = _basic_block(pl, sd, r + "layer3.0.", f8, 2, 1, 1, 2)
+    f16 = _basic_block(pl, sd, r + "layer3.1.", x, 1, 1, 1, 1)
+    x = _basic_block(pl, sd, r + "layer4.0.", f16, 2, 1, 1, 2)
+    f32 = _basic_block(pl, sd, r + "layer4.1.", x, 1, 1, 1, 1)
+    # ContextPath.forward (model/bisenet.py:289-306)
+    pooled = pl.avgpool(f32, 1, 1, fp32_out=True)
+    sca, sha = fold_bn(sd, p + "cp.conv_avg.bn.")
+    w_avg = sd[p + "cp.conv_avg.conv.weight"].reshape(sd[p + "cp.conv_avg.conv.weight"].shape[0], -1) * sca[:, None]
+    avg = pl.linear(pooled, w_avg, sha, True, "cp.conv_avg")                      # 1x1 conv + BN + ReLU on [N,512]
+    f32s = _arm(pl, sd, p + "cp.arm32.", f32, add_chan=avg)
+    N, h32, w32, _ = f32s.shape
+    _, h16, w16, _ = f16.shape
+    up = pl.resize(f32s, 2 * h32, 2 * w32, L.RESIZE_NEAREST, name="cp.up32")
+    up = pl.resize(up, h16, w16, L.RESIZE_BILINEAR_AC, name="cp.up32_fit")
+    f32u = _cbr(pl, sd, p + "cp.conv_head32.", up)
+    f16s = _arm(pl, sd, p + "cp.arm16.", f16, add_pix=f32u)
+    up = pl.resize(f16s, 2 * h16, 2 * w16, L.RESIZE_NEAREST, name="cp.up16")
+    h8, w8 = 2 * h16, 2 * w16
+    cat = pl.empty((N, h8, w8, 256))
+    _cbr(pl, sd, p + "cp.conv_head16.", up, out=cat, coff=128)                     # feat_cp8 -> cat[..., 128:]
+    # SpatialPath (model/bisenet.py:326-340)
+    sc, sh = fold_bn(sd, p + "sp.conv1.bn.")
+    s = pl.stem(x_nchw, sd[p + "sp.conv1.conv.weight"], sc, sh, name="sp.conv1")
+    s = _cbr(pl, sd, p + "sp.conv2.", s, stride=2)
+    s = _cbr(pl, sd, p + "sp.conv3.", s, stride=2)
+    s = _cbr(pl, sd, p + "sp.conv_out.", s, pad=0)
+    pl.resize(s, h8, w8, L.RESIZE_BILINEAR_AC, out=cat, coff=0, name="sp.fit")     # feat_sp -> cat[..., :128] (:550)
+    # FeatureFusionModule (model/bisenet.py:387-399)
+    feat = _cbr(pl, sd, p + "ffm.convblk.", cat, pad=0)
+    pooled = pl.avgpool(feat, 1, 1, fp32_out=True)
+    g = pl.linear(pooled, sd[p + "ffm.conv.weight"], None, False, "ffm.conv")
+    gs, gb = fold_bn(sd, p + "ffm.bn.")
+    fuse = pl.gate(feat, g, gs, gb, add_identity=True, name="ffm.gate")
+    mid = _cbr(pl, sd, p + "conv_out.conv.", fuse)                                 # feat_conv_out (:554)
+    out16 = out32 = None
+    if aux:                                                                        # dead work in evaluation (:556-559)
+        cp8 = pl.empty((N, h8, w8, 128))
+        # feat_cp8 lives in cat[..., 128:]; the aux head needs it dense
+        out16 = _bise_out(pl, sd, p + "conv_out16.", cat, 8, src_coff=128, src_c=128, tmp=cp8)
+        out32 = _bise_out(pl, sd, p + "conv_out32.", f32u, 16)
+    return out16, out32, mid
+
+
+def _bise_out(pl: Plan, sd: SD, p: str, x, up: int, src_coff: int = 0, src_c: Optional[int] = None, tmp=None):
+    """BiSeNetOutput (model/bisenet.py:207-223): ConvBNReLU 3x3 -> 1x1 (+bias) -> xup bilinear (align_corners=False)."""
+    if src_c is not None:
+        x = _slice_channels(pl, x, src_coff, src_c, tmp)
+    t = _cbr(pl, sd, p + "conv.", x)
+    t = pl.conv(t, sd[p + "conv_out.weight"], None, sd[p + "conv_out.bias"], name=p + "conv_out")
+    N, h, w, _ = t.shape
+    t = pl.resize(t, h * up, w * up, L.RESIZE_BILINEAR, name=p + "up")
+    return pl.to_nchw(t)
+
+
+def _slice_channels(pl: Plan, x: torch.Tensor, coff: int, c: int, out: torch.Tensor) -> torch.Tensor:
+    """Dense copy of the channel slice x[..., coff:coff+c]: a 1x1 SIMT conv with a 0/1 selection weight
+    (exact: x*1 plus zeros).  Only the aux heads use it, which are dead work in evaluation."""
+    eye = torch.zeros(c, x.shape[-1], 1, 1)
+    eye[torch.arange(c), coff + torch.arange(c), 0, 0] = 1.0
+    saved = pl.engine
+    pl.engine = L.CONV_SIMT_F32
+    try:
+        return pl.conv(x, eye, out=out, name="slice[%d:%d]" % (coff, coff + c))
+    finally:
+        pl.engine = saved

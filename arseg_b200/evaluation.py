@@ -1,0 +1,140 @@
+"""Host-side mirror of the reference's evaluation path (evaluation.py:61-87, 148-215).
+
+* `warpFeature(feature, flow)`            -- same name / arguments as evaluation.py:61 (one kernel).
+* `nonkey_step(net, imgs, ref_p, flow)`   -- the literal per-frame sequence evaluation.py:176-204 through
+                                             the drop-in modules (forward_phase1 / forward_phase2).
+* `NonKeyEngine`                          -- the fused throughput path: all non-keyframes of a GOP batched,
+                                             MV field consumed in its on-disk int16 quarter-pel format,
+                                             warp + CReFF + classifier + argmax in one kernel, whole step
+                                             captured in a CUDA graph.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from . import _lib as L
+from . import engine as E
+from . import ops
+
+ARCH_INFO = {
+    # arch: (feature channels of p, feature stride of p w.r.t. the frame, n_classes)
+    "camvid-psp18": (64, 1, 12),
+    "camvid-bise18": (256, 8, 12),
+    "cityscapes-psp18": (512, 8, 19),
+    "cityscapes-bise18": (256, 8, 19),
+}
+
+
+def warpFeature(feature: torch.Tensor, flow: torch.Tensor) -> torch.Tensor:
+    """evaluation.py:61-87: backward bilinear warp of `feature` [B,C,H,W] by `flow` [B,H,W,2] (pixels)."""
+    return ops.warp_feature(feature, flow)
+
+
+def resize_flow(flow: torch.Tensor, Hf: int, Wf: int) -> torch.Tensor:
+    """evaluation.py:177-180 on the GPU: flow f64 [B,H,W,2] -> [B,Hf,Wf,2], both components scaled by Hf/H.
+    (float64 planes are resized in float64 by the caller's torch in the reference; here the field is
+    passed un-resized to the fused kernel instead -- this helper exists for the literal API path and runs
+    the arithmetic in float64 on the device with torch only when sizes differ.)"""
+    B, H, W, _ = flow.shape
+    if (H, W) == (Hf, Wf):
+        return flow * Hf / H
+    f = flow.permute(0, 3, 1, 2) * Hf / H
+    f = torch.nn.functional.interpolate(f, [Hf, Wf], mode="bilinear", align_corners=True)
+    return f.permute(0, 2, 3, 1).contiguous()
+
+
+def nonkey_step(net, imgs: torch.Tensor, ref_p: torch.Tensor, flow: torch.Tensor, scale: float = 0.5,
+                label_size: Optional[Sequence[int]] = None):
+    """evaluation.py:176-204 with `net` = one of the drop-in *WithFuse modules.
+    Returns (preds uint8 [N,H,W], logits fp32 [N,ncls,H,W], fused p, lr p)."""
+    flow = resize_flow(flow, ref_p.shape[-2], ref_p.shape[-1])                       # :177-180
+    warped = warpFeature(ref_p, flow)                                                # :183
+    N, _, H, W = imgs.shape
+    new_hw = [int(H * scale), int(W * scale)]                                        # :186-187
+    x = ops.resize_nchw(imgs, new_hw, L.RESIZE_BILINEAR_AC)                          # :188
+    lr_p = net.forward_phase1(x)[-1]                                                 # :190-191
+    out, fused = net.forward_phase2(lr_p, warped)                                    # :193
+    size = list(label_size) if label_size is not None else [H, W]
+    preds, logits = ops.resize_argmax(out, size, L.RESIZE_BILINEAR_AC, want_logits=True)   # :201-204
+    return preds, logits, fused, lr_p
+
+
+class NonKeyEngine:
+    """All non-keyframes of a GOP in one captured step.
+
+    Inputs (device-resident static buffers): `imgs` fp32 [N,3,H,W], `mv` int16 [N,H,W,2] quarter-pel
+    (dataset/camvid.py:624-626), `ref_p` fp32 NCHW [1,C,Hf,Wf] = the keyframe feature (shared by the GOP).
+    Output: `preds` uint8 [N,H,W] (+ `logits` at feature resolution when want_logits).
+    """
+
+    def __init__(self, arch: str, sd: Dict[str, torch.Tensor], n_frames: int, H: int, W: int, scale: float = 0.5,
+                 precision: str = "tf32", k: int = 7, device="cuda:0", want_logits: bool = False, want_p: bool = False,
+                 graph: bool = True):
+        if arch not in ARCH_INFO:
+            raise KeyError(arch)
+        self.arch, self.N, self.H, self.W, self.scale, self.k = arch, n_frames, H, W, scale, k
+        C_, stride, ncls = ARCH_INFO[arch]
+        self.C, self.ncls = C_, ncls
+        self.Hf, self.Wf = H // stride, W // stride
+        self.h, self.w = int(H * scale), int(W * scale)
+        self.device = torch.device(device)
+        with torch.no_grad(), torch.cuda.device(self.device):
+            pl = E.Plan(self.device, precision)
+            self.plan = pl
+            self.imgs = pl.empty((n_frames, 3, H, W), torch.float32)
+            self.mv = pl.empty((n_frames, H, W, 2), torch.int16)
+            self.ref_p = pl.empty((1, C_, self.Hf, self.Wf), torch.float32)
+            self.imgs.zero_(); self.mv.zero_(); self.ref_p.zero_()
+            x = pl.resize_nchw(self.imgs, self.h, self.w, L.RESIZE_BILINEAR_AC, name="frame_downscale")   # evaluation.py:186-188
+            if arch == "camvid-psp18":
+                _, p = E.build_psp_phase1(pl, sd, x, "", aux=False)
+                fin, logsm = "final_conv.", True
+            elif arch == "cityscapes-psp18":
+                _, p = E.build_semseg_phase1(pl, sd, x, "")
+                fin, logsm = "cls.4.", False
+            else:
+                _, _, p = E.build_bisenet_phase1(pl, sd, x, "", aux=False)
+                fin, logsm = "conv_out.conv_out.", False
+            self.lr_p = p
+            direct = arch == "camvid-psp18"     # logits already at frame resolution: argmax inside the kernel
+            out_p, out_l, out_a = pl.creff(self.ref_p, p, sd, "fuse_attention.", k, flow=self.mv, hr_shared=True,
+                                           lr_layout=L.NHWC, wcls=sd[fin + "weight"], bcls=sd[fin + "bias"],
+                                           log_softmax=logsm, want_p=want_p, want_logits=(want_logits or not direct),
+                                           want_argmax=direct)
+            self.fused_p, self.logits = out_p, out_l
+            if direct:
+                self.preds = out_a
+            elif arch.endswith("bise18"):
+                # forward_phase2's x8 up-sampling (align_corners=False, model/bisenet.py:573) then evaluation.py:201-204
+                H8, W8 = self.Hf * 8, self.Wf * 8
+                if (H8, W8) == (H, W):
+                    self.preds, _ = pl.resize_argmax(out_l, H, W, L.RESIZE_BILINEAR)
+                else:
+                    up = pl.resize_nchw(out_l, H8, W8, L.RESIZE_BILINEAR, name="out_upsample")
+                    self.preds, _ = pl.resize_argmax(up, H, W, L.RESIZE_BILINEAR_AC)
+            else:
+                self.preds, _ = pl.resize_argmax(out_l, H, W, L.RESIZE_BILINEAR_AC)          # evaluation.py:201-204
+            if graph:
+                pl.capture()
+        self.conv_flops_per_frame = pl.conv_flops / n_frames
+        self.launches_per_step = pl.n_launches
+
+    def set_inputs(self, imgs: torch.Tensor, mv: torch.Tensor, ref_p: torch.Tensor) -> None:
+        self.imgs.copy_(imgs, non_blocking=True)
+        self.mv.copy_(mv, non_blocking=True)
+        self.ref_p.copy_(ref_p, non_blocking=True)
+
+    def step(self) -> torch.Tensor:
+        """One pass over the N non-keyframes with inputs already resident in HBM."""
+        self.plan.run()
+        return self.preds
+
+    def step_host(self, imgs_pinned: torch.Tensor, mv_pinned: torch.Tensor, preds_pinned: torch.Tensor) -> torch.Tensor:
+        """End-to-end step from pinned host buffers: H2D frames + MV fields, compute, D2H class maps."""
+        self.imgs.copy_(imgs_pinned, non_blocking=True)
+        self.mv.copy_(mv_pinned, non_blocking=True)
+        self.plan.run()
+        preds_pinned.copy_(self.preds, non_blocking=True)
+        return preds_pinned

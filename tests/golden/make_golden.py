@@ -139,6 +139,25 @@ def main():
                  fused=fused.numpy()[:, ::8], fused_sum=fused.double().sum().item(),
                  warped=warped.numpy()[:, ::8], warped_sum=warped.double().sum().item(),
                  n_state=len(sd), state_sum=float(sum(t.double().sum().item() for t in sd.values())))
+    # state_dict contract: key -> shape for every net of the evaluation.py:24-36 registries
+    import json
+    specs = {}
+    torch.manual_seed(233)
+    hr_builders = {
+        "camvid-psp18": lambda: psp.PSPNet(sizes=(1, 2, 3, 6), n_classes=12, psp_size=512, deep_features_size=256,
+                                           backend="resnet18", pretrained=False),
+        "camvid-bise18": lambda: bise.BiSeNetV1(n_classes=12, backend="resnet18"),
+        "cityscapes-psp18": lambda: semseg.PSPNetWithFuse(bins=(1, 2, 3, 6), classes=19, feat_dim=512, layers=18, pretrained=False),
+        "cityscapes-bise18": lambda: bise.BiSeNetV1(n_classes=19, backend="resnet18"),
+    }
+    for arch, fn in hr_builders.items():
+        specs["hr/" + arch] = {k: list(v.shape) for k, v in fn().state_dict().items()}
+    for arch in ("camvid-psp18", "camvid-bise18", "cityscapes-psp18"):
+        specs["lr/" + arch] = {k: list(v.shape) for k, v in build_ref_net(arch, psp, bise, semseg).state_dict().items()}
+    specs["lr/cityscapes-bise18"] = {k: list(v.shape) for k, v in
+                                     bise.BiSeNetV1WithFuse(n_classes=19, backend="resnet18").state_dict().items()}
+    with open(os.path.join(HERE, "state_specs.json"), "w") as f:
+        json.dump(specs, f, indent=0, sort_keys=True)
     print("goldens written to", HERE)
 
 
