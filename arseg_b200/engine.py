@@ -282,6 +282,27 @@ class Plan:
         else:
             self.launch()
 
+    def profile(self, iters: int = 5, warmup: int = 2) -> List[Tuple[str, float]]:
+        """Per-kernel device time (ms, mean over `iters`) with CUDA events on the launching stream."""
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream()
+            s = stream.cuda_stream
+            n = len(self.steps)
+            tot = [0.0] * n
+            for it in range(warmup + iters):
+                evs = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+                evs[0].record(stream)
+                for i, fn in enumerate(self.steps):
+                    rc = fn(s)
+                    if rc != L.OK:
+                        L.check(rc, self.names[i])
+                    evs[i + 1].record(stream)
+                torch.cuda.synchronize()
+                if it >= warmup:
+                    for i in range(n):
+                        tot[i] += evs[i].elapsed_time(evs[i + 1])
+            return [(self.names[i], tot[i] / iters) for i in range(n)]
+
 
 # ==============================================================================================
 # network builders (functional over a reference-keyed state_dict)

@@ -1,0 +1,147 @@
+"""GPU parity tests, module and pipeline level.
+
+* drop-in modules (forward_phase1 / forward_phase2 / warpFeature) against the golden vectors recorded from
+  the UNMODIFIED reference (tests/golden/*.npz) and against the oracle;
+* the fused NonKeyEngine against the literal per-frame API sequence;
+* full-size (720x960) size-independent properties.
+
+Tolerances: 'fp32' precision = exact-arithmetic kernels: 1e-4 of the tensor's max magnitude and identical
+argmax maps (up to ties: <= 0.05 % pixels).  'tf32' (tcgen05 kind::tf32, the arithmetic cuDNN applies to the
+reference on Ampere-or-newer GPUs): 1e-2 max / 2e-3 rms, argmax agreement >= 99 %.  'bf16': 6e-2 max /
+2e-2 rms, argmax agreement >= 95 % on these random-weight nets (near-tie logits).
+"""
+import numpy as np
+import pytest
+import torch
+
+from arseg_b200 import _lib as L
+from arseg_b200 import evaluation as ev
+from arseg_b200 import models, ops, synth
+from oracle import arseg_oracle as O
+from tests.util import CASES, case_setup, load_golden, rel_err, rms_err
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+DEV = "cuda:0"
+
+TOL = {"fp32": (1e-4, 5e-5, 5e-4), "tf32": (1e-2, 2e-3, 1e-2), "bf16": (6e-2, 2e-2, 5e-2)}  # max, rms, argmax mismatch
+
+
+def _net(arch, sd, precision):
+    net = models.models_fuse[arch]()
+    net.load_state_dict(sd)
+    net.precision = precision
+    return net.to(DEV).eval()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("name", CASES)
+def test_dropin_modules_match_reference_golden(name, precision):
+    g = load_golden(name)
+    arch, _, sd, imgs, ref_p, mv, flow, scale = case_setup(g)
+    net = _net(arch, sd, precision)
+    tmax, trms, targ = TOL[precision]
+    preds, logits, fused, lr_p = ev.nonkey_step(net, imgs.to(DEV), ref_p.to(DEV), flow.to(DEV), scale)
+    assert rel_err(lr_p[:, ::4], torch.from_numpy(g["lr_p"])) < tmax
+    assert rms_err(lr_p[:, ::4], torch.from_numpy(g["lr_p"])) < trms
+    assert rel_err(fused[:, ::8], torch.from_numpy(g["fused"])) < tmax
+    assert rel_err(logits, torch.from_numpy(g["logits"])) < tmax
+    mism = float((preds.cpu().numpy() != g["preds"]).mean())
+    assert mism <= targ, mism
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_warp_feature_matches_reference_golden(name):
+    g = load_golden(name)
+    arch, _, sd, imgs, ref_p, mv, flow, scale = case_setup(g)
+    fl = ev.resize_flow(flow.to(DEV), ref_p.shape[-2], ref_p.shape[-1])
+    warped = ev.warpFeature(ref_p.to(DEV), fl)
+    assert rel_err(warped[:, ::8], torch.from_numpy(g["warped"])) < 2e-5
+
+
+@pytest.mark.parametrize("name", ["camvid_psp18_s05", "camvid_bise18_s05"])
+def test_phase1_api_tuple(name):
+    """forward_phase1 returns the reference's tuple (aux outputs included) -- checked against the oracle."""
+    g = load_golden(name)
+    arch, _, sd, imgs, ref_p, mv, flow, scale = case_setup(g)
+    net = _net(arch, sd, "fp32")
+    x = torch.nn.functional.interpolate(imgs, synth.lr_size(imgs.shape[2], imgs.shape[3], scale), mode="bilinear", align_corners=True)
+    got = net.forward_phase1(x.to(DEV))
+    ref = O._PHASES[arch][0](sd, x)
+    assert len(got) == len(ref)
+    for a, b in zip(got, ref):
+        assert tuple(a.shape) == tuple(b.shape)
+        assert rel_err(a, b) < 1e-4
+
+
+@pytest.mark.parametrize("arch,H,W", [("camvid-psp18", 64, 96), ("camvid-bise18", 96, 128), ("cityscapes-psp18", 64, 128)])
+def test_hr_keyframe_forward(arch, H, W):
+    """HR branch on the same kernels: last output = p, first = logits (evaluation.py:119,173-174)."""
+    net = models.models[arch]()
+    sd = synth.synth_state_dict(net.state_dict(), 4)
+    net.load_state_dict(sd)
+    net.precision = "fp32"
+    net = net.to(DEV).eval()
+    x = synth.synth_frame(1, H, W, 2)
+    got = net(x.to(DEV))
+    ref = {"camvid-psp18": O.pspnet_hr, "camvid-bise18": O.bisenet_hr, "cityscapes-psp18": O.semseg_hr}[arch](sd, x)
+    assert len(got) == len(ref)
+    for a, b in zip(got, ref):
+        assert tuple(a.shape) == tuple(b.shape)
+        assert rel_err(a, b) < 1e-4
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("name", CASES)
+def test_engine_matches_literal_api(name, precision):
+    """NonKeyEngine (batched, int16 MVs, fused warp+CReFF+classifier+argmax, CUDA graph) == per-frame API path."""
+    g = load_golden(name)
+    arch, _, sd, imgs, ref_p, mv, flow, scale = case_setup(g)
+    H, W = imgs.shape[-2:]
+    N = 3
+    frames = torch.cat([imgs] + [synth.synth_frame(1, H, W, 100 + i) for i in range(N - 1)])
+    mvs = np.stack([mv] + [synth.synth_mv_int16(H, W, 200 + i, distance=2 + 4 * i) for i in range(N - 1)])
+    eng = ev.NonKeyEngine(arch, sd, N, H, W, scale, precision, want_logits=True, want_p=True, device=DEV)
+    eng.set_inputs(frames.to(DEV), torch.from_numpy(mvs).to(DEV), ref_p.to(DEV))
+    preds = eng.step().cpu()
+    torch.cuda.synchronize()
+    net = _net(arch, sd, precision)
+    tmax, trms, targ = TOL[precision]
+    for i in range(N):
+        fl = torch.from_numpy(mvs[i].astype(np.float64) / 4.0).unsqueeze(0)
+        p_i, logits_i, fused_i, _ = ev.nonkey_step(net, frames[i:i + 1].to(DEV), ref_p.to(DEV), fl.to(DEV), scale)
+        assert rel_err(eng.fused_p[i:i + 1], fused_i) < max(tmax, 1e-4)
+        assert float((preds[i] != p_i[0].cpu()).float().mean()) <= targ
+    if precision == "fp32":   # frame 0 is the golden case
+        assert float((preds[0].numpy() != g["preds"][0]).mean()) <= 5e-4
+    # replaying the captured graph is deterministic
+    again = eng.step().cpu()
+    assert torch.equal(again, preds)
+
+
+def test_full_size_properties_camvid_psp():
+    """720x960 (BASELINE config 2 shapes), size-independent properties of the fused kernel:
+    (1) warp inside the kernel == warpFeature kernel followed by the pre-warped kernel;
+    (2) frames of a batch are independent (batched == one at a time, bit-exact);
+    (3) argmax output == argmax of the returned log-probs; log-probs exponentiate to 1."""
+    C, H, W, h, w, k, ncls = 64, 720, 960, 360, 480, 7, 12
+    net = models.models_fuse["camvid-psp18"]()
+    sd = synth.synth_state_dict(net.state_dict(), 4)
+    args = [sd["fuse_attention.%s.%s" % (n, l)].reshape(-1).contiguous().to(DEV)
+            for n in ("lr_query_conv", "hr_key_conv", "hr_value_conv") for l in ("weight", "bias")]
+    wcls, bcls = sd["final_conv.weight"].reshape(ncls, C).to(DEV), sd["final_conv.bias"].to(DEV)
+    hr = (synth.synth_feature(1, C, H, W, 1) * 0.5).to(DEV)
+    lr = (synth.synth_feature(2, C, h, w, 2) * 0.4).to(DEV)
+    mvs = torch.from_numpy(np.stack([synth.synth_mv_int16(H, W, 3, 11), synth.synth_mv_int16(H, W, 4, 5)])).to(DEV)
+    p, l, a = ops.creff_fused(hr, lr, *args, k, flow=mvs, wcls=wcls, bcls=bcls, log_softmax=True, want_argmax=True, hr_shared=True)
+    for i in range(2):
+        flow = (mvs[i:i + 1].double() / 4.0)
+        warped = ops.warp_feature(hr, flow)
+        p1, l1, a1 = ops.creff_fused(warped, lr[i:i + 1].contiguous(), *args, k, wcls=wcls, bcls=bcls, log_softmax=True, want_argmax=True)
+        assert rel_err(p1, p[i:i + 1]) < 1e-6
+        assert rel_err(l1, l[i:i + 1]) < 1e-6
+        pi, li, ai = ops.creff_fused(hr, lr[i:i + 1].contiguous(), *args, k, flow=mvs[i:i + 1].contiguous(), wcls=wcls, bcls=bcls,
+                                     log_softmax=True, want_argmax=True, hr_shared=True)
+        assert torch.equal(pi, p[i:i + 1]) and torch.equal(li, l[i:i + 1]) and torch.equal(ai, a[i:i + 1])
+    assert torch.equal(a.long(), l.argmax(1))
+    assert (l.exp().sum(1) - 1).abs().max() < 1e-4

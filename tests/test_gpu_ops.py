@@ -1,0 +1,276 @@
+"""GPU parity tests, op level: every C-ABI kernel against the oracle / the ATen CPU op the reference calls.
+
+Tolerances (stated per test): exact-arithmetic fp32 kernels agree with the CPU fp32 reference up to
+summation order -> 2e-5 relative to the tensor's max magnitude; TF32 tensor-core convs 2e-3; bf16 2e-2.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from arseg_b200 import _lib as L
+from arseg_b200 import ops
+from oracle import arseg_oracle as O
+from tests.util import rel_err, rms_err
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+DEV = "cuda:0"
+FP32_TOL = 2e-5
+
+
+def rnd(*shape, seed=0, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g, dtype=dtype)
+
+
+# ---------------------------------------------------------------- localAttention boundary
+@pytest.mark.parametrize("shape,k", [((2, 8, 9, 37), (3, 3)), ((1, 64, 24, 40), (7, 7)), ((1, 5, 1, 33), (5, 5)),
+                                     ((2, 6, 11, 13), (3, 5)), ((1, 16, 20, 70), (9, 9))])
+def test_local_attention_forward_ops(shape, k):
+    q, kk = rnd(*shape, seed=1), rnd(*shape, seed=2)
+    s_ref = O.similar_forward(q, kk, *k)
+    s = ops.similar_forward(q.to(DEV), kk.to(DEV), *k)
+    assert s.shape == s_ref.shape
+    assert rel_err(s, s_ref) < FP32_TOL
+    a = torch.softmax(s_ref, dim=3)
+    o_ref = O.weighting_forward(kk, a, *k)
+    o = ops.weighting_forward(kk.to(DEV), a.to(DEV), *k)
+    assert rel_err(o, o_ref) < FP32_TOL
+
+
+def test_local_attention_zero_padding_takes_softmax_mass():
+    """out-of-image taps give logit exactly 0 (not -inf)."""
+    q, k = rnd(1, 4, 6, 6, seed=3), rnd(1, 4, 6, 6, seed=4)
+    s = ops.similar_forward(q.to(DEV), k.to(DEV), 3, 3).cpu()
+    assert (s[0, 0, 0, [0, 1, 2, 3, 6]] == 0).all()     # corner pixel: 5 of 9 taps are outside
+    assert (s[0, 2, 2] != 0).all()
+
+
+@pytest.mark.parametrize("k", [(3, 3), (7, 7), (3, 5)])
+def test_local_attention_backward_ops(k):
+    shape = (2, 6, 10, 35)
+    x, y = rnd(*shape, seed=5), rnd(*shape, seed=6)
+    T = k[0] * k[1]
+    g_s = rnd(2, 10, 35, T, seed=7)
+    for is_ori in (True, False):
+        ref = O.similar_backward(x, g_s, *k, is_ori)
+        got = ops.similar_backward(x.to(DEV), g_s.to(DEV), *k, is_ori)
+        assert rel_err(got, ref) < FP32_TOL
+    a = torch.softmax(g_s, 3)
+    ref = O.weighting_backward_ori(a, y, *k)
+    assert rel_err(ops.weighting_backward_ori(a.to(DEV), y.to(DEV), *k), ref) < FP32_TOL
+    ref = O.weighting_backward_weight(x, y, *k)
+    assert rel_err(ops.weighting_backward_weight(x.to(DEV), y.to(DEV), *k), ref) < FP32_TOL
+
+
+def test_local_attention_rejects_bad_input():
+    with pytest.raises(RuntimeError):
+        ops.similar_forward(torch.zeros(1, 2, 4, 4, device=DEV, dtype=torch.float64), torch.zeros(1, 2, 4, 4, device=DEV, dtype=torch.float64), 3, 3)
+    with pytest.raises(RuntimeError):
+        ops.similar_forward(torch.zeros(1, 2, 4, 4, device=DEV), torch.zeros(1, 2, 4, 4, device=DEV), 4, 4)  # even window
+
+
+# ---------------------------------------------------------------- warpFeature / resize
+@pytest.mark.parametrize("fdtype", [torch.float64, torch.float32])
+def test_warp_feature(fdtype):
+    feat = rnd(2, 7, 19, 45, seed=8)
+    g = torch.Generator().manual_seed(9)
+    flow = (torch.randint(-6, 7, (2, 19, 45, 2), generator=g).to(fdtype))
+    flow[0, :4] *= 10          # far out-of-image samples -> zeros padding
+    ref = O.warp_feature(feat, flow)
+    got = ops.warp_feature(feat.to(DEV), flow.to(DEV))
+    assert rel_err(got, ref) < FP32_TOL
+
+
+@pytest.mark.parametrize("mode,kw", [(L.RESIZE_BILINEAR, dict(mode="bilinear", align_corners=False)),
+                                     (L.RESIZE_BILINEAR_AC, dict(mode="bilinear", align_corners=True)),
+                                     (L.RESIZE_NEAREST, dict(mode="nearest"))])
+@pytest.mark.parametrize("sizes", [((23, 30), (46, 60)), ((72, 96), (36, 48)), ((12, 15), (23, 30)), ((9, 12), (72, 96))])
+def test_resize_nchw(mode, kw, sizes):
+    (hi, wi), (ho, wo) = sizes
+    x = rnd(2, 3, hi, wi, seed=10)
+    ref = F.interpolate(x, size=(ho, wo), **kw)
+    got = ops.resize_nchw(x.to(DEV), (ho, wo), mode)
+    assert rel_err(got, ref) < FP32_TOL
+
+
+def test_layout_roundtrip_and_resize_nhwc_slice():
+    x = rnd(2, 12, 9, 14, seed=11)
+    nhwc = ops.nchw_to_nhwc(x.to(DEV))
+    assert torch.equal(nhwc.cpu(), x.permute(0, 2, 3, 1).contiguous())
+    assert torch.equal(ops.nhwc_to_nchw(nhwc).cpu(), x)
+    bf = ops.nchw_to_nhwc(x.to(DEV), torch.bfloat16)
+    assert torch.equal(bf.cpu(), x.permute(0, 2, 3, 1).contiguous().bfloat16())
+
+
+# ---------------------------------------------------------------- conv engines
+def conv_ref(x, w, scale, shift, res, stride, pad, dil, act, slope):
+    y = F.conv2d(x.double(), w.double(), None, stride, pad, dil)
+    if scale is not None:
+        y = y * scale.double().view(1, -1, 1, 1)
+    if shift is not None:
+        y = y + shift.double().view(1, -1, 1, 1)
+    if res is not None:
+        y = y + res.double()
+    if act == L.ACT_RELU:
+        y = F.relu(y)
+    elif act == L.ACT_PRELU:
+        y = torch.where(y > 0, y, y * slope)
+    return y.float()
+
+
+def run_conv(x, w, scale, shift, res, stride, pad, dil, act, slope, engine, dtype=torch.float32):
+    xd = ops.nchw_to_nhwc(x.to(DEV), dtype)
+    wd = w.permute(0, 2, 3, 1).contiguous().to(DEV, dtype)
+    rd = ops.nchw_to_nhwc(res.to(DEV), dtype) if res is not None else None
+    y = ops.conv2d_nhwc(xd, wd, scale.to(DEV) if scale is not None else None, shift.to(DEV) if shift is not None else None,
+                        rd, stride, pad, dil, act, slope, engine)
+    return ops.nhwc_to_nchw(y).cpu()
+
+
+CONV_CASES = [
+    # N, Cin, Cout, H, W, k, stride, pad, dil, residual, act
+    (2, 64, 64, 23, 30, 3, 1, 1, 1, True, L.ACT_RELU),
+    (1, 64, 128, 24, 32, 3, 2, 1, 1, False, L.ACT_RELU),
+    (1, 64, 128, 24, 32, 1, 2, 0, 1, False, L.ACT_NONE),
+    (1, 128, 256, 12, 15, 3, 1, 2, 2, True, L.ACT_RELU),
+    (1, 256, 512, 12, 15, 3, 1, 4, 4, False, L.ACT_PRELU),
+    (2, 512, 128, 6, 6, 1, 1, 0, 1, False, L.ACT_NONE),
+    (1, 64, 12, 20, 28, 1, 1, 0, 1, False, L.ACT_NONE),
+    (1, 192, 96, 17, 21, 3, 1, 1, 1, False, L.ACT_RELU),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_simt_fp32(case):
+    N, Ci, Co, H, W, k, s, p, d, has_res, act = case
+    x, w = rnd(N, Ci, H, W, seed=20), rnd(Co, Ci, k, k, seed=21) * (1.0 / (Ci * k * k) ** 0.5)
+    scale, shift = torch.rand(Co) + 0.5, rnd(Co, seed=22) * 0.1
+    Ho, Wo = (H + 2 * p - d * (k - 1) - 1) // s + 1, (W + 2 * p - d * (k - 1) - 1) // s + 1
+    res = rnd(N, Co, Ho, Wo, seed=23) if has_res else None
+    ref = conv_ref(x, w, scale, shift, res, s, p, d, act, 0.25)
+    got = run_conv(x, w, scale, shift, res, s, p, d, act, 0.25, L.CONV_SIMT_F32)
+    assert got.shape == ref.shape
+    assert rel_err(got, ref) < FP32_TOL
+
+
+TC_CASES = [c for c in CONV_CASES if c[6] == 1 and c[2] >= 16] + [
+    (2, 64, 64, 45, 60, 3, 1, 1, 1, True, L.ACT_RELU),
+    (1, 1024, 256, 18, 24, 3, 1, 1, 1, False, L.ACT_PRELU),
+    (1, 2560, 1024, 9, 12, 1, 1, 0, 1, False, L.ACT_RELU),
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+@pytest.mark.parametrize("engine,dtype,tol", [(L.CONV_TC_TF32, torch.float32, 2e-3), (L.CONV_TC_BF16, torch.bfloat16, 2e-2)])
+def test_conv_tcgen05(case, engine, dtype, tol):
+    N, Ci, Co, H, W, k, s, p, d, has_res, act = case
+    x, w = rnd(N, Ci, H, W, seed=30), rnd(Co, Ci, k, k, seed=31) * (1.0 / (Ci * k * k) ** 0.5)
+    scale, shift = torch.rand(Co) + 0.5, rnd(Co, seed=32) * 0.1
+    res = rnd(N, Co, H, W, seed=33) if has_res else None
+    if dtype == torch.bfloat16:   # reference on the bf16-rounded operands: isolates accumulation error
+        x, w = x.bfloat16().float(), w.bfloat16().float()
+        res = res.bfloat16().float() if res is not None else None
+    ref = conv_ref(x, w, scale, shift, res, s, p, d, act, 0.25)
+    got = run_conv(x, w, scale, shift, res, s, p, d, act, 0.25, engine, dtype)
+    assert got.shape == ref.shape
+    assert rel_err(got, ref) < tol, (rel_err(got, ref), rms_err(got, ref))
+    assert rms_err(got, ref) < tol / 4
+
+
+def test_conv_output_channel_slice():
+    """out_cstride / out_coff: the conv writes a channel slice of a wider tensor (fused torch.cat)."""
+    x, w = rnd(1, 64, 10, 12, seed=40), rnd(32, 64, 1, 1, seed=41) * 0.1
+    xd = ops.nchw_to_nhwc(x.to(DEV))
+    wd = w.permute(0, 2, 3, 1).contiguous().to(DEV)
+    out = torch.full((1, 10, 12, 96), 7.0, device=DEV)
+    ops.conv2d_nhwc(xd, wd, out=out, out_coff=32)
+    ref = F.conv2d(x, w).permute(0, 2, 3, 1)
+    assert rel_err(out[..., 32:64], ref) < FP32_TOL
+    assert (out[..., :32] == 7).all() and (out[..., 64:] == 7).all()
+
+
+# ---------------------------------------------------------------- fused CReFF
+def creff_sd(C, seed=50):
+    from arseg_b200 import synth
+    spec = {"fuse_attention.%s.%s" % (n, l): torch.empty((C, 1, 3, 3) if l == "weight" else (C,))
+            for n in ("lr_query_conv", "hr_key_conv", "hr_value_conv") for l in ("weight", "bias")}
+    return synth.synth_state_dict(spec, seed)
+
+
+def creff_args(sd):
+    return [sd["fuse_attention.%s.%s" % (n, l)].reshape(-1).contiguous().to(DEV)
+            for n in ("lr_query_conv", "hr_key_conv", "hr_value_conv") for l in ("weight", "bias")]
+
+
+@pytest.mark.parametrize("k", [3, 5, 7, 9])
+@pytest.mark.parametrize("C,H,W,h,w", [(64, 24, 40, 12, 20), (16, 17, 35, 11, 23)])
+def test_creff_fused_prewarped(k, C, H, W, h, w):
+    """MyAttention.forward semantics (model/attention.py:184-213) as one kernel, all window sizes."""
+    sd = creff_sd(C)
+    hr, lr = rnd(1, C, H, W, seed=51) * 0.6, rnd(1, C, h, w, seed=52) * 0.4
+    ref = O.creff(sd, "fuse_attention.", hr, lr, k)
+    out_p, _, _ = ops.creff_fused(hr.to(DEV), lr.to(DEV), *creff_args(sd), k, want_logits=False)
+    assert rel_err(out_p, ref) < 5e-5
+
+
+@pytest.mark.parametrize("flow_kind", ["i16", "f64", "f32"])
+@pytest.mark.parametrize("stride", [1, 8])
+def test_creff_fused_with_mv_warp_and_classifier(flow_kind, stride):
+    """evaluation.py:177-183 + MyAttention + final_conv + log-softmax + argmax in one launch."""
+    from arseg_b200 import synth
+    C, ncls, k = 64, 12, 7
+    Hm, Wm = 48 * stride, 64 * stride // 2 * 2
+    H, W, h, w = Hm // stride, Wm // stride, Hm // stride // 2, Wm // stride // 2
+    sd = creff_sd(C)
+    hr, lr = rnd(1, C, H, W, seed=53) * 0.6, rnd(2, C, h, w, seed=54) * 0.4
+    wcls, bcls = rnd(ncls, C, seed=55) * 0.2, rnd(ncls, seed=56) * 0.1
+    mvs = np.stack([synth.synth_mv_int16(Hm, Wm, 60 + i, distance=5 + 3 * i) for i in range(2)])
+    flow64 = torch.from_numpy(mvs.astype(np.float64) / 4.0)
+    refs = []
+    for i in range(2):
+        fl = O.resize_flow(flow64[i:i + 1], H, W)
+        warped = O.warp_feature(hr, fl)
+        fused = O.creff(sd, "fuse_attention.", warped, lr[i:i + 1], k)
+        logits = F.log_softmax(F.conv2d(fused, wcls.view(ncls, C, 1, 1), bcls), dim=1)
+        refs.append((fused, logits))
+    flow = {"i16": torch.from_numpy(mvs), "f64": flow64, "f32": flow64.float()}[flow_kind].to(DEV)
+    out_p, out_l, out_a = ops.creff_fused(hr.to(DEV), lr.to(DEV), *creff_args(sd), k, flow=flow, wcls=wcls.to(DEV),
+                                          bcls=bcls.to(DEV), log_softmax=True, want_argmax=True, hr_shared=True)
+    tol = 5e-5 if flow_kind != "f32" else 5e-3   # an fp32 flow changes the reference's own grid arithmetic
+    for i in range(2):
+        assert rel_err(out_p[i:i + 1], refs[i][0]) < tol
+        assert rel_err(out_l[i:i + 1], refs[i][1]) < tol
+        ref_arg = refs[i][1].argmax(1)
+        mism = (out_a[i:i + 1].cpu().long() != ref_arg).float().mean().item()
+        assert mism < (1e-3 if flow_kind != "f32" else 1e-2)
+        assert torch.equal(out_a[i:i + 1].cpu().long(), out_l[i:i + 1].cpu().argmax(1))
+
+
+def test_creff_fused_nhwc_lr_and_bf16():
+    C, H, W, h, w, k = 64, 24, 40, 12, 20, 7
+    sd = creff_sd(C)
+    hr, lr = rnd(1, C, H, W, seed=57) * 0.6, rnd(1, C, h, w, seed=58) * 0.4
+    ref = O.creff(sd, "fuse_attention.", hr, lr, k)
+    lr_nhwc = ops.nchw_to_nhwc(lr.to(DEV))
+    out_p, _, _ = ops.creff_fused(hr.to(DEV), lr_nhwc, *creff_args(sd), k, want_logits=False, lr_layout=L.NHWC)
+    assert rel_err(out_p, ref) < 5e-5
+    lr_bf = ops.nchw_to_nhwc(lr.to(DEV), torch.bfloat16)
+    ref_bf = O.creff(sd, "fuse_attention.", hr, lr.bfloat16().float(), k)
+    out_p, _, _ = ops.creff_fused(hr.to(DEV), lr_bf, *creff_args(sd), k, want_logits=False, lr_layout=L.NHWC)
+    assert rel_err(out_p, ref_bf) < 5e-5
+
+
+def test_resize_argmax_and_hist():
+    logits = rnd(2, 12, 10, 12, seed=70)
+    ref_l = F.interpolate(logits, size=(80, 96), mode="bilinear", align_corners=True)
+    pred, up = ops.resize_argmax(logits.to(DEV), (80, 96), L.RESIZE_BILINEAR_AC, want_logits=True)
+    assert rel_err(up, ref_l) < FP32_TOL
+    assert (pred.cpu().long() != ref_l.argmax(1)).float().mean() < 1e-3
+    g = torch.Generator().manual_seed(71)
+    label = torch.randint(0, 12, (2, 80, 96), generator=g)
+    label[0, :5] = 255
+    hist = ops.confusion_hist(pred, label.to(DEV), 12).view(12, 12).cpu()
+    ref = O.confusion_hist(pred.cpu().long(), label, 12)
+    assert torch.equal(hist.float(), ref)
