@@ -17,6 +17,8 @@ ACT_NONE, ACT_RELU, ACT_PRELU = 0, 1, 2
 RESIZE_BILINEAR, RESIZE_BILINEAR_AC, RESIZE_NEAREST = 0, 1, 2
 NCHW, NHWC = 0, 1
 CONV_SIMT_F32, CONV_TC_TF32, CONV_TC_BF16 = 1, 2, 3
+CREFF_EXACT_F32, CREFF_MMA_F16 = 0, 1
+ABI_VERSION = 2
 
 vp, ci, cf = C.c_void_p, C.c_int, C.c_float
 
@@ -29,7 +31,7 @@ class ConvDesc(C.Structure):
 
 
 class CreffArgs(C.Structure):
-    _fields_ = [("hr", vp), ("hr_shared", ci), ("flow", vp), ("flow_dtype", ci), ("Hm", ci), ("Wm", ci),
+    _fields_ = [("hr", vp), ("hr_shared", ci), ("hr_layout", ci), ("engine", ci), ("flow", vp), ("flow_dtype", ci), ("Hm", ci), ("Wm", ci),
                 ("lr", vp), ("lr_layout", ci), ("lr_dtype", ci), ("h", ci), ("w", ci),
                 ("wq", vp), ("bq", vp), ("wk", vp), ("bk", vp), ("wv", vp), ("bv", vp), ("wcls", vp), ("bcls", vp),
                 ("ncls", ci), ("log_softmax", ci), ("out_p", vp), ("out_logits", vp), ("out_argmax", vp),
@@ -87,7 +89,7 @@ def load() -> C.CDLL:
                 fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
                 fn.argtypes = args
                 fn.restype = res
-            if lib.arseg_abi_version() != 1:
+            if lib.arseg_abi_version() != ABI_VERSION:
                 raise ArsegError("libarseg_sm100a.so ABI version mismatch")
             _lib = lib
     return _lib

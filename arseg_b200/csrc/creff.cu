@@ -316,6 +316,9 @@ static int creff_launch_k(const CreffParams& p, int layout, int dtype, cudaStrea
     return creff_launch_t<K, ARSEG_NHWC, __nv_bfloat16>(p, st);
 }
 
+bool creff_mma_supported(const arseg_creff_args* a);
+int creff_mma_launch(const arseg_creff_args* a, cudaStream_t st);
+
 }  // namespace arseg
 
 using namespace arseg;
@@ -336,13 +339,20 @@ extern "C" int arseg_creff_fused_fwd(const arseg_creff_args* a, arseg_stream_t s
     ARSEG_REQUIRE(a->lr_layout == ARSEG_NCHW || a->lr_layout == ARSEG_NHWC, "creff: lr layout %d", a->lr_layout);
     if (a->lr_layout == ARSEG_NCHW) ARSEG_REQUIRE(a->lr_dtype == ARSEG_F32, "creff: NCHW lr must be fp32");
     else ARSEG_REQUIRE(a->lr_dtype == ARSEG_F32 || a->lr_dtype == ARSEG_BF16, "creff: lr dtype %d", a->lr_dtype);
+    cudaStream_t st = as_stream(stream);
+    if (a->engine == ARSEG_CREFF_MMA_F16) {
+        if (!creff_mma_supported(a))
+            ARSEG_UNSUPPORTED("creff: the MMA engine needs C=64 (got %d), NHWC hr and lr, k in {3,5,7,9}, ncls <= 32", a->C);
+        return creff_mma_launch(a, st);
+    }
+    ARSEG_REQUIRE(a->engine == ARSEG_CREFF_EXACT_F32, "creff: unknown engine %d", a->engine);
+    if (a->hr_layout != ARSEG_NCHW) ARSEG_UNSUPPORTED("creff: the exact fp32 engine takes hr in NCHW");
     CreffParams p;
     p.hr = a->hr; p.hr_shared = a->hr_shared; p.flow = a->flow; p.flow_dtype = a->flow_dtype; p.Hm = a->Hm; p.Wm = a->Wm;
     p.lr = a->lr; p.h = a->h; p.w = a->w;
     p.wq = a->wq; p.bq = a->bq; p.wk = a->wk; p.bk = a->bk; p.wv = a->wv; p.bv = a->bv; p.wcls = a->wcls; p.bcls = a->bcls;
     p.ncls = a->ncls; p.log_softmax = a->log_softmax; p.out_p = a->out_p; p.out_logits = a->out_logits;
     p.out_argmax = a->out_argmax; p.N = a->N; p.C = a->C; p.H = a->H; p.W = a->W;
-    cudaStream_t st = as_stream(stream);
     switch (a->k) {
         case 3: return creff_launch_k<3>(p, a->lr_layout, a->lr_dtype, st);
         case 5: return creff_launch_k<5>(p, a->lr_layout, a->lr_dtype, st);

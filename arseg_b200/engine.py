@@ -202,9 +202,23 @@ class Plan:
 
     def creff(self, hr: torch.Tensor, lr: torch.Tensor, sd: SD, prefix: str, k: int, *, flow: Optional[torch.Tensor] = None,
               hr_shared=False, lr_layout=L.NHWC, wcls=None, bcls=None, log_softmax=False, want_p=True, want_logits=True,
-              want_argmax=False, name="creff_fused"):
-        """Fused MV-warp + CReFF (+ classifier).  hr NCHW fp32 [1|N,C,H,W]; lr [N,h,w,C] NHWC (or NCHW fp32)."""
+              want_argmax=False, name="creff_fused", engine=None):
+        """Fused MV-warp + CReFF (+ classifier).  hr NCHW fp32 [1|N,C,H,W]; lr [N,h,w,C] NHWC (or NCHW fp32).
+        engine None: exact fp32 SIMT kernel in 'fp32' plans; tensor-core window attention (f16 operands, fp32
+        accumulate) in 'tf32'/'bf16' plans when C == 64 (hr is first converted to NHWC by one transpose launch)."""
         _, Cc, H, W = hr.shape
+        if engine is None:
+            mma_ok = (self.precision != "fp32" and Cc == 64 and lr_layout == L.NHWC and k in (3, 5, 7, 9)
+                      and (wcls is None or wcls.shape[0] <= 32))
+            engine = L.CREFF_MMA_F16 if mma_ok else L.CREFF_EXACT_F32
+        hr_layout = L.NCHW
+        if engine == L.CREFF_MMA_F16:
+            hr_nhwc = self.empty((hr.shape[0], H, W, Cc), torch.float32)
+            fn_t = self.lib.arseg_nchw_to_nhwc
+            targs = (hr.data_ptr(), hr_nhwc.data_ptr(), L.F32, hr.shape[0], Cc, H, W)
+            self._add("hr_nchw_to_nhwc", lambda s: fn_t(*targs, s))
+            hr, hr_layout = hr_nhwc, L.NHWC
+            name = name + "_mma"
         if lr_layout == L.NHWC:
             N, h, w, _ = lr.shape
         else:
@@ -223,7 +237,7 @@ class Plan:
         out_l = self.empty((N, ncls, H, W), f32) if (want_logits and ncls) else None
         out_a = self.empty((N, H, W), torch.uint8) if (want_argmax and ncls) else None
         Hm, Wm = (flow.shape[1], flow.shape[2]) if flow is not None else (0, 0)
-        a = L.CreffArgs(hr.data_ptr(), int(hr_shared), flow.data_ptr() if flow is not None else None,
+        a = L.CreffArgs(hr.data_ptr(), int(hr_shared), hr_layout, engine, flow.data_ptr() if flow is not None else None,
                         dtype_code(flow.dtype) if flow is not None else 0, Hm, Wm, lr.data_ptr(), lr_layout,
                         dtype_code(lr.dtype), h, w, *[t.data_ptr() for t in ws],
                         wc.data_ptr() if wc is not None else None, bc.data_ptr() if bc is not None else None, ncls,

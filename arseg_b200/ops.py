@@ -186,10 +186,16 @@ def conv2d_nhwc(x, w, scale=None, shift=None, residual=None, stride=1, pad=0, di
 
 
 def creff_fused(hr, lr, wq, bq, wk, bk, wv, bv, k, flow=None, flow_hw=None, wcls=None, bcls=None, log_softmax=False,
-                lr_layout=L.NCHW, want_p=True, want_logits=True, want_argmax=False, hr_shared=False, n_frames=None):
-    """Fused (MV warp +) CReFF (+ classifier).  hr NCHW fp32 [1|N,C,H,W]; lr NCHW fp32 [N,C,h,w] or NHWC [N,h,w,C]."""
+                lr_layout=L.NCHW, want_p=True, want_logits=True, want_argmax=False, hr_shared=False, n_frames=None,
+                engine=L.CREFF_EXACT_F32, hr_layout=L.NCHW):
+    """Fused (MV warp +) CReFF (+ classifier).  hr fp32 NCHW [1|N,C,H,W] (or NHWC [1|N,H,W,C] with hr_layout=NHWC);
+    lr NCHW fp32 [N,C,h,w] or NHWC [N,h,w,C].  engine: L.CREFF_EXACT_F32 (fp32 SIMT, NCHW hr) or L.CREFF_MMA_F16
+    (tensor-core window attention, TF32-class error, C=64, NHWC hr and lr)."""
     _chk_cuda("creff_fused", hr, lr, wq, bq, wk, bk, wv, bv, flow, wcls, bcls)
-    Nh, Cc, H, W = hr.shape
+    if hr_layout == L.NHWC:
+        Nh, H, W, Cc = hr.shape
+    else:
+        Nh, Cc, H, W = hr.shape
     if lr_layout == L.NCHW:
         N, C2, h, w = lr.shape
     else:
@@ -203,7 +209,7 @@ def creff_fused(hr, lr, wq, bq, wk, bk, wv, bv, k, flow=None, flow_hw=None, wcls
     out_l = torch.empty((N, ncls, H, W), dtype=torch.float32, device=dev) if (want_logits and ncls) else None
     out_a = torch.empty((N, H, W), dtype=torch.uint8, device=dev) if (want_argmax and ncls) else None
     Hm, Wm = (flow.shape[1], flow.shape[2]) if flow is not None else (0, 0)
-    a = L.CreffArgs(_p(hr), int(hr_shared), _p(flow), dtype_code(flow.dtype) if flow is not None else 0, Hm, Wm,
+    a = L.CreffArgs(_p(hr), int(hr_shared), hr_layout, engine, _p(flow), dtype_code(flow.dtype) if flow is not None else 0, Hm, Wm,
                     _p(lr), lr_layout, dtype_code(lr.dtype), h, w, _p(wq), _p(bq), _p(wk), _p(bk), _p(wv), _p(bv),
                     _p(wcls), _p(bcls), ncls, int(log_softmax), _p(out_p), _p(out_l), _p(out_a), N, Cc, H, W, k)
     with torch.cuda.device(dev):

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define ARSEG_ABI_VERSION 1
+#define ARSEG_ABI_VERSION 2
 
 enum { ARSEG_OK = 0, ARSEG_E_BADARG = -1, ARSEG_E_UNSUPPORTED = -2, ARSEG_E_CUDA = -3 };
 enum { ARSEG_F32 = 0, ARSEG_BF16 = 1, ARSEG_F64 = 2, ARSEG_I16 = 3 };
@@ -34,6 +34,9 @@ enum { ARSEG_RESIZE_BILINEAR = 0, ARSEG_RESIZE_BILINEAR_AC = 1, ARSEG_RESIZE_NEA
 enum { ARSEG_NCHW = 0, ARSEG_NHWC = 1 };
 /* convolution engines: SIMT fp32 (exact-order fp32 FMA), tcgen05 kind::tf32, tcgen05 kind::f16 (bf16) */
 enum { ARSEG_CONV_SIMT_F32 = 1, ARSEG_CONV_TC_TF32 = 2, ARSEG_CONV_TC_BF16 = 3 };
+/* CReFF engines: exact fp32 SIMT (any C, NCHW hr), or tensor-core window attention (mma.sync f16 operands with
+ * fp32 accumulate -- TF32-class error; C = 64, NHWC hr and lr) */
+enum { ARSEG_CREFF_EXACT_F32 = 0, ARSEG_CREFF_MMA_F16 = 1 };
 
 typedef void* arseg_stream_t;
 
@@ -142,8 +145,11 @@ int arseg_gate_nhwc(const void* feat, const float* gate, const float* gate_scale
  *    final_conv/log-softmax of model/pspnet.py:226-229, + argmax of evaluation.py:204)
  * ---------------------------------------------------------------------------------------------- */
 typedef struct arseg_creff_args {
-    const float* hr;        /* keyframe feature p_HR, NCHW fp32 [Nhr,C,H,W]; Nhr = 1 (shared by all N frames) or N */
+    const float* hr;        /* keyframe feature p_HR fp32, NCHW [Nhr,C,H,W] or NHWC [Nhr,H,W,C] (hr_layout);
+                               Nhr = 1 (shared by all N frames) or N */
     int hr_shared;          /* 1: hr has batch 1 and is broadcast over the N frames */
+    int hr_layout;          /* ARSEG_NCHW (required by ARSEG_CREFF_EXACT_F32) | ARSEG_NHWC (required by ARSEG_CREFF_MMA_F16) */
+    int engine;             /* ARSEG_CREFF_*; an engine that does not support the arguments returns ARSEG_E_UNSUPPORTED */
     const void* flow;       /* NULL: hr is already warped (MyAttention.forward semantics).
                                else MV field [N,Hm,Wm,2] at FRAME resolution: ARSEG_I16 quarter-pel
                                (dataset/camvid.py:624-626 on-disk format), or ARSEG_F32/ARSEG_F64 pixels */

@@ -274,3 +274,62 @@ def test_resize_argmax_and_hist():
     hist = ops.confusion_hist(pred, label.to(DEV), 12).view(12, 12).cpu()
     ref = O.confusion_hist(pred.cpu().long(), label, 12)
     assert torch.equal(hist.float(), ref)
+
+
+# ---------------------------------------------------------------- fused CReFF, tensor-core engine
+# Tolerance: Q, K, V, P and the classifier operands are rounded to f16 (11-bit significand, the same as
+# TF32) and accumulated in fp32 -> 3e-3 relative to the tensor's max magnitude (measured ~5e-4).
+MMA_TOL = 3e-3
+
+
+@pytest.mark.parametrize("k", [3, 5, 7, 9])
+@pytest.mark.parametrize("H,W,h,w", [(32, 48, 16, 24), (24, 40, 12, 20), (17, 35, 11, 23)])
+def test_creff_mma_prewarped(k, H, W, h, w):
+    C = 64
+    sd = creff_sd(C)
+    hr, lr = rnd(1, C, H, W, seed=51) * 0.6, rnd(1, C, h, w, seed=52) * 0.4
+    ref = O.creff(sd, "fuse_attention.", hr, lr, k)
+    out_p, _, _ = ops.creff_fused(ops.nchw_to_nhwc(hr.to(DEV)), ops.nchw_to_nhwc(lr.to(DEV)), *creff_args(sd), k,
+                                  want_logits=False, lr_layout=L.NHWC, hr_layout=L.NHWC, engine=L.CREFF_MMA_F16)
+    assert out_p.shape == ref.shape
+    assert rel_err(out_p, ref) < MMA_TOL, rel_err(out_p, ref)
+    assert rms_err(out_p, ref) < MMA_TOL / 4
+
+
+@pytest.mark.parametrize("flow_kind", ["i16", "f64"])
+@pytest.mark.parametrize("stride", [1, 8])
+@pytest.mark.parametrize("lr_dtype", [torch.float32, torch.bfloat16])
+def test_creff_mma_with_mv_warp_and_classifier(flow_kind, stride, lr_dtype):
+    from arseg_b200 import synth
+    C, ncls, k = 64, 12, 7
+    Hm, Wm = 48 * stride, 64 * stride
+    H, W, h, w = Hm // stride, Wm // stride, Hm // stride // 2, Wm // stride // 2
+    sd = creff_sd(C)
+    hr, lr = rnd(1, C, H, W, seed=53) * 0.6, rnd(2, C, h, w, seed=54) * 0.4
+    if lr_dtype == torch.bfloat16:
+        lr = lr.bfloat16().float()
+    wcls, bcls = rnd(ncls, C, seed=55) * 0.2, rnd(ncls, seed=56) * 0.1
+    mvs = np.stack([synth.synth_mv_int16(Hm, Wm, 60 + i, distance=5 + 3 * i) for i in range(2)])
+    flow64 = torch.from_numpy(mvs.astype(np.float64) / 4.0)
+    flow = {"i16": torch.from_numpy(mvs), "f64": flow64}[flow_kind].to(DEV)
+    out_p, out_l, out_a = ops.creff_fused(ops.nchw_to_nhwc(hr.to(DEV)), ops.nchw_to_nhwc(lr.to(DEV), lr_dtype), *creff_args(sd), k,
+                                          flow=flow, wcls=wcls.to(DEV), bcls=bcls.to(DEV), log_softmax=True, want_argmax=True,
+                                          hr_shared=True, lr_layout=L.NHWC, hr_layout=L.NHWC, engine=L.CREFF_MMA_F16)
+    for i in range(2):
+        fl = O.resize_flow(flow64[i:i + 1], H, W)
+        warped = O.warp_feature(hr, fl)
+        fused = O.creff(sd, "fuse_attention.", warped, lr[i:i + 1], k)
+        logits = F.log_softmax(F.conv2d(fused, wcls.view(ncls, C, 1, 1), bcls), dim=1)
+        assert rel_err(out_p[i:i + 1], fused) < MMA_TOL, rel_err(out_p[i:i + 1], fused)
+        assert rel_err(out_l[i:i + 1], logits) < MMA_TOL, rel_err(out_l[i:i + 1], logits)
+        mism = (out_a[i:i + 1].cpu().long() != logits.argmax(1)).float().mean().item()
+        assert mism < 5e-3, mism
+        assert torch.equal(out_a[i:i + 1].cpu().long(), out_l[i:i + 1].cpu().argmax(1))
+
+
+def test_creff_mma_rejects_unsupported():
+    sd = creff_sd(16)
+    hr, lr = rnd(1, 16, 16, 16, seed=1), rnd(1, 16, 8, 8, seed=2)
+    with pytest.raises(L.ArsegError):
+        ops.creff_fused(ops.nchw_to_nhwc(hr.to(DEV)), ops.nchw_to_nhwc(lr.to(DEV)), *creff_args(sd), 7, want_logits=False,
+                        lr_layout=L.NHWC, hr_layout=L.NHWC, engine=L.CREFF_MMA_F16)
