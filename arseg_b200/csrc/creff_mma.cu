@@ -169,155 +169,206 @@ __device__ __forceinline__ float2 ld2(const __nv_bfloat16* p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Producer: bilinear gather of a (OR+2)x(OC+2) fp32 tile from an NHWC source in 4-row strips through the
-// smem ring, followed by NOUT depthwise 3x3 convolutions (+bias) written as swizzled f16 rows.
+// Producer (warp specialised).  A (OR+2)x(OC+2) fp32 tile is gathered bilinearly from an NHWC source in
+// 4-row strips into the smem ring by warps 0-7, and consumed by warps 8-15, which apply NOUT depthwise 3x3
+// convolutions (+bias) and write swizzled f16 rows.  The two groups hand strips over through named barriers
+// (FULL[s&1]: strip s is in the ring; EMPTY[s&1]: strip s has been consumed, its ring rows may be reused), so
+// the gather of strip s+1/s+2 overlaps the convolutions of strip s.
 //   MODE 0: source = lr (lr_up tile), NOUT = 1 (Q);   MODE 1: source = hr (warped tile), NOUT = 2 (K, V)
 // ---------------------------------------------------------------------------------------------
+constexpr int BAR_FULL = 1, BAR_EMPTY = 3, BAR_GATHER = 5;   // named barrier ids (0 = __syncthreads)
+__device__ __forceinline__ void nbar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void nbar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// four consecutive channels of a source pixel as float4
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+    return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                       __uint_as_float(u.y & 0xffff0000u));
+}
+// (lo, hi) -> packed f16x2 with saturation to +-65504 (one F2FP.SATFINITE)
+__device__ __forceinline__ uint32_t pack_h2_sat(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
+template <int K, int MODE> struct PCfg {
+    using Cf = MCfg<K>;
+    static constexpr int OR = MODE ? Cf::KR : MT, OC = MODE ? Cf::KC : MT;   // output tile
+    static constexpr int IR = OR + 2, IC = OC + 2;                           // input tile
+    static constexpr int ORG = MODE ? Cf::R + 1 : 1;                         // input tile origin = (y0-ORG, x0-ORG)
+    static constexpr int NSTEP = (OR + MSR - 1) / MSR;
+    static constexpr int PPH = (MSR * IC + 15) / 16;                         // positions per half-warp per step
+    static constexpr int JA = (PPH + 1) / 2, JB = PPH - JA;
+    static constexpr int RSTRIDE = Cf::WC * MC;                              // ring row stride (floats)
+    static constexpr int CHALF = (OC + 1) / 2;
+};
+
+template <int K, int MODE, typename TSRC>
+__device__ __forceinline__ void gather_role(const CreffMmaParams& p, const TSRC* __restrict__ src, int srcW, int n, int y0, int x0,
+                                            float* ring, float4* posw, int* posi) {
+    using Cf = MCfg<K>;
+    using Pc = PCfg<K, MODE>;
+    constexpr int IR = Pc::IR, IC = Pc::IC, NSTEP = Pc::NSTEP;
+    const int gt = threadIdx.x, lane = gt & 31, hw = gt >> 4, cl = lane & 15;   // gt in [0,256)
+    const float lsh = resize_scale(p.h, p.H, ARSEG_RESIZE_BILINEAR_AC), lsw = resize_scale(p.w, p.W, ARSEG_RESIZE_BILINEAR_AC);
+    // gather step g (g = -1: rows 0,1; g >= 0: rows 4g+2 .. 4g+5); position records of step g in buffer g&1
+    auto step_rows = [&](int g, int& r0, int& nr) {
+        if (g < 0) { r0 = 0; nr = 2; } else { r0 = MSR * g + 2; nr = min(MSR, IR - r0); }
+    };
+    auto compute_pos = [&](int g) {
+        int r0, nr; step_rows(g, r0, nr);
+        if (gt < nr * IC) {
+            const int rr = r0 + gt / IC, cc = gt % IC;
+            const int fy = y0 - Pc::ORG + rr, fx = x0 - Pc::ORG + cc;
+            PosRec r = MODE ? pos_hr(p, n, fy, fx) : pos_lr(p, lsh, lsw, fy, fx);
+            posw[(g & 1) * Cf::POS_N + gt] = r.w;
+            posi[(g & 1) * Cf::POS_N + gt] = r.info;
+        }
+    };
+    float4 tap[Pc::JA][4];
+    auto issue = [&](int buf, int npos, int j0, int nj) {
+#pragma unroll
+        for (int j = 0; j < Pc::JA; ++j) {
+            if (j < nj) {
+                const int i = hw + 16 * (j0 + j);
+                int info = -1;
+                if (i < npos) info = posi[buf * Cf::POS_N + i];
+                if (info >= 0) {
+                    const int dx = (info >> 1) & 1, dy = info & 1;
+                    const TSRC* s = src + (size_t)(info >> 2) * MC + 4 * cl;
+                    const TSRC* s2 = s + (size_t)dy * srcW * MC;
+                    tap[j][0] = ld4(s);
+                    tap[j][1] = ld4(s + dx * MC);
+                    tap[j][2] = ld4(s2);
+                    tap[j][3] = ld4(s2 + dx * MC);
+                } else {
+                    tap[j][0] = tap[j][1] = tap[j][2] = tap[j][3] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        }
+    };
+    auto commit = [&](int buf, int r0, int npos, int j0, int nj) {
+#pragma unroll
+        for (int j = 0; j < Pc::JA; ++j) {
+            if (j < nj) {
+                const int i = hw + 16 * (j0 + j);
+                if (i < npos) {
+                    const float4 w = posw[buf * Cf::POS_N + i];
+                    float4 v;
+                    v.x = tap[j][0].x * w.x + tap[j][1].x * w.y + tap[j][2].x * w.z + tap[j][3].x * w.w;
+                    v.y = tap[j][0].y * w.x + tap[j][1].y * w.y + tap[j][2].y * w.z + tap[j][3].y * w.w;
+                    v.z = tap[j][0].z * w.x + tap[j][1].z * w.y + tap[j][2].z * w.z + tap[j][3].z * w.w;
+                    v.w = tap[j][0].w * w.x + tap[j][1].w * w.y + tap[j][2].w * w.z + tap[j][3].w * w.w;
+                    const int rr = r0 + i / IC, cc = i % IC;
+                    *reinterpret_cast<float4*>(ring + (rr % MRING) * Pc::RSTRIDE + cc * MC + 4 * cl) = v;
+                }
+            }
+        }
+    };
+    compute_pos(-1);
+    nbar_sync(BAR_GATHER, 256);
+#pragma unroll 1
+    for (int g = -1; g < NSTEP; ++g) {
+        const int buf = g & 1;
+        if (g >= 2) nbar_sync(BAR_EMPTY + buf, MTHREADS);     // strip g-2 consumed: its ring rows are free
+        int r0, nr; step_rows(g, r0, nr);
+        const int npos = nr * IC;
+        issue(buf, npos, 0, Pc::JA);
+        if (g + 1 < NSTEP) compute_pos(g + 1);                // f64 MV arithmetic overlaps the loads in flight
+        commit(buf, r0, npos, 0, Pc::JA);
+        if (Pc::JB > 0) {
+            issue(buf, npos, Pc::JA, Pc::JB);
+            commit(buf, r0, npos, Pc::JA, Pc::JB);
+        }
+        nbar_sync(BAR_GATHER, 256);                           // position records of step g+1 visible to the group
+        if (g >= 0) nbar_arrive(BAR_FULL + buf, MTHREADS);    // strip g (ring rows <= 4g+5) is complete
+    }
+}
+
+template <int K, int MODE>
+__device__ __forceinline__ void dw_role(const CreffMmaParams& p, int y0, int x0, const float* ring, uint8_t* out1, uint8_t* out2,
+                                        const float* __restrict__ w1g, const float* __restrict__ b1g,
+                                        const float* __restrict__ w2g, const float* __restrict__ b2g) {
+    using Cf = MCfg<K>;
+    using Pc = PCfg<K, MODE>;
+    constexpr int OR = Pc::OR, OC = Pc::OC, NSTEP = Pc::NSTEP, NOUT = MODE ? 2 : 1;
+    const int lane = threadIdx.x & 31, dwarp = (threadIdx.x >> 5) - 8;
+    // this lane's channel pair (2*lane, 2*lane+1)
+    float2 w1[9], w2[9], b1, b2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        w1[t] = make_float2(__ldg(w1g + (2 * lane) * 9 + t), __ldg(w1g + (2 * lane + 1) * 9 + t));
+        w2[t] = NOUT == 2 ? make_float2(__ldg(w2g + (2 * lane) * 9 + t), __ldg(w2g + (2 * lane + 1) * 9 + t)) : make_float2(0.f, 0.f);
+    }
+    b1 = make_float2(__ldg(b1g + 2 * lane), __ldg(b1g + 2 * lane + 1));
+    if (NOUT == 2) b2 = make_float2(__ldg(b2g + 2 * lane), __ldg(b2g + 2 * lane + 1));
+    const int rsub = dwarp >> 1;
+    const int c_lo = (dwarp & 1) * Pc::CHALF, c_hi = min(OC, c_lo + Pc::CHALF);
+    const uint32_t lane_off = (uint32_t)((lane & 3) * 4);
+    const int lane_chunk = lane >> 2;
+#pragma unroll 1
+    for (int s = 0; s < NSTEP; ++s) {
+        nbar_sync(BAR_FULL + (s & 1), MTHREADS);
+        const int orow = MSR * s + rsub;
+        if (orow < OR) {
+            const float* rp0 = ring + (orow % MRING) * Pc::RSTRIDE + 2 * lane;
+            const float* rp1 = ring + ((orow + 1) % MRING) * Pc::RSTRIDE + 2 * lane;
+            const float* rp2 = ring + ((orow + 2) % MRING) * Pc::RSTRIDE + 2 * lane;
+            bool row_ok = true;
+            if (MODE) { const int fy = y0 - Cf::R + orow; row_ok = fy >= 0 && fy < p.H; }
+            float2 win[3][3];   // [input row][slot]; slot (x - c_lo + d) % 3 holds input column x + d
+            win[0][0] = *reinterpret_cast<const float2*>(rp0 + c_lo * MC);
+            win[1][0] = *reinterpret_cast<const float2*>(rp1 + c_lo * MC);
+            win[2][0] = *reinterpret_cast<const float2*>(rp2 + c_lo * MC);
+            win[0][1] = *reinterpret_cast<const float2*>(rp0 + (c_lo + 1) * MC);
+            win[1][1] = *reinterpret_cast<const float2*>(rp1 + (c_lo + 1) * MC);
+            win[2][1] = *reinterpret_cast<const float2*>(rp2 + (c_lo + 1) * MC);
+            for (int xb = c_lo; xb < c_hi; xb += 3) {
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
+                    const int x = xb + u;
+                    if (x < c_hi) {
+                        const int sa = u, sb = (u + 1) % 3, sc = (u + 2) % 3;     // slots of columns x, x+1, x+2
+                        win[0][sc] = *reinterpret_cast<const float2*>(rp0 + (x + 2) * MC);
+                        win[1][sc] = *reinterpret_cast<const float2*>(rp1 + (x + 2) * MC);
+                        win[2][sc] = *reinterpret_cast<const float2*>(rp2 + (x + 2) * MC);
+                        float2 a1 = b1;
+                        a1 = __ffma2_rn(w1[0], win[0][sa], a1); a1 = __ffma2_rn(w1[1], win[0][sb], a1); a1 = __ffma2_rn(w1[2], win[0][sc], a1);
+                        a1 = __ffma2_rn(w1[3], win[1][sa], a1); a1 = __ffma2_rn(w1[4], win[1][sb], a1); a1 = __ffma2_rn(w1[5], win[1][sc], a1);
+                        a1 = __ffma2_rn(w1[6], win[2][sa], a1); a1 = __ffma2_rn(w1[7], win[2][sb], a1); a1 = __ffma2_rn(w1[8], win[2][sc], a1);
+                        float2 a2 = b2;
+                        if (NOUT == 2) {
+                            a2 = __ffma2_rn(w2[0], win[0][sa], a2); a2 = __ffma2_rn(w2[1], win[0][sb], a2); a2 = __ffma2_rn(w2[2], win[0][sc], a2);
+                            a2 = __ffma2_rn(w2[3], win[1][sa], a2); a2 = __ffma2_rn(w2[4], win[1][sb], a2); a2 = __ffma2_rn(w2[5], win[1][sc], a2);
+                            a2 = __ffma2_rn(w2[6], win[2][sa], a2); a2 = __ffma2_rn(w2[7], win[2][sb], a2); a2 = __ffma2_rn(w2[8], win[2][sc], a2);
+                        }
+                        if (MODE) {   // K / V are exactly 0 outside the image (attention zero padding)
+                            const int fx = x0 - Cf::R + x;
+                            if (!(row_ok && fx >= 0 && fx < p.W)) { a1 = make_float2(0.f, 0.f); a2 = make_float2(0.f, 0.f); }
+                        }
+                        const int pos = orow * OC + x;
+                        const uint32_t off = (uint32_t)(pos * 128 + (((lane_chunk ^ pos) & 7) << 4)) + lane_off;
+                        *reinterpret_cast<uint32_t*>(out1 + off) = pack_h2_sat(a1.x, a1.y);
+                        if (NOUT == 2) *reinterpret_cast<uint32_t*>(out2 + off) = pack_h2_sat(a2.x, a2.y);
+                    }
+                }
+            }
+        }
+        if (s + 2 < NSTEP) nbar_arrive(BAR_EMPTY + (s & 1), MTHREADS);
+    }
+}
+
 template <int K, int MODE, typename TSRC>
 __device__ __forceinline__ void produce(const CreffMmaParams& p, const TSRC* __restrict__ src, int srcW, int n, int y0, int x0,
                                         float* ring, float4* posw, int* posi, uint8_t* out1, uint8_t* out2,
                                         const float* __restrict__ w1g, const float* __restrict__ b1g,
                                         const float* __restrict__ w2g, const float* __restrict__ b2g) {
-    using Cf = MCfg<K>;
-    constexpr int OR = MODE ? Cf::KR : MT, OC = MODE ? Cf::KC : MT;     // output tile
-    constexpr int IR = OR + 2, IC = OC + 2;                             // input tile
-    constexpr int ORG = MODE ? Cf::R + 1 : 1;                           // input tile origin = (y0-ORG, x0-ORG)
-    constexpr int RC = MODE ? Cf::RC_KV : 2;                            // depthwise column run per warp
-    constexpr int NSTEP = (OR + MSR - 1) / MSR;
-    constexpr int PPW = Cf::PPW;
-    constexpr int NOUT = MODE ? 2 : 1;
-    constexpr int RSTRIDE = Cf::WC * MC;                                // ring row stride (floats)
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const float lsh = resize_scale(p.h, p.H, ARSEG_RESIZE_BILINEAR_AC), lsw = resize_scale(p.w, p.W, ARSEG_RESIZE_BILINEAR_AC);
-
-    // gather step g (g = -1: rows 0,1; g >= 0: rows 4g+2 .. 4g+5) uses position buffer `buf`
-    auto step_rows = [&](int g, int& r0, int& nr) {
-        if (g < 0) { r0 = 0; nr = 2; } else { r0 = MSR * g + 2; nr = min(MSR, IR - r0); }
-    };
-    auto compute_pos = [&](int g, int buf) {
-        int r0, nr; step_rows(g, r0, nr);
-        if (tid < nr * IC) {
-            const int rr = r0 + tid / IC, cc = tid % IC;
-            const int fy = y0 - ORG + rr, fx = x0 - ORG + cc;
-            PosRec r = MODE ? pos_hr(p, n, fy, fx) : pos_lr(p, lsh, lsw, fy, fx);
-            posw[buf * Cf::POS_N + tid] = r.w;
-            posi[buf * Cf::POS_N + tid] = r.info;
-        }
-    };
-    float2 tap[PPW][4];
-    auto issue = [&](int g, int buf) {
-        int r0, nr; step_rows(g, r0, nr);
-        const int npos = nr * IC;
-#pragma unroll
-        for (int j = 0; j < PPW; ++j) {
-            const int i = warp + 16 * j;
-            int info = -1;
-            if (i < npos) info = posi[buf * Cf::POS_N + i];
-            if (info >= 0) {
-                const int dx = (info >> 1) & 1, dy = info & 1;
-                const TSRC* s = src + (size_t)(info >> 2) * MC + 2 * lane;
-                tap[j][0] = ld2(s);
-                tap[j][1] = ld2(s + dx * MC);
-                tap[j][2] = ld2(s + (size_t)dy * srcW * MC);
-                tap[j][3] = ld2(s + (size_t)dy * srcW * MC + dx * MC);
-            } else {
-                tap[j][0] = tap[j][1] = tap[j][2] = tap[j][3] = make_float2(0.f, 0.f);
-            }
-        }
-    };
-    auto commit = [&](int g, int buf) {
-        int r0, nr; step_rows(g, r0, nr);
-        const int npos = nr * IC;
-#pragma unroll
-        for (int j = 0; j < PPW; ++j) {
-            const int i = warp + 16 * j;
-            if (i < npos) {
-                const float4 w = posw[buf * Cf::POS_N + i];
-                float2 v;
-                v.x = tap[j][0].x * w.x + tap[j][1].x * w.y + tap[j][2].x * w.z + tap[j][3].x * w.w;
-                v.y = tap[j][0].y * w.x + tap[j][1].y * w.y + tap[j][2].y * w.z + tap[j][3].y * w.w;
-                const int rr = r0 + i / IC, cc = i % IC;
-                *reinterpret_cast<float2*>(ring + (rr % MRING) * RSTRIDE + cc * MC + 2 * lane) = v;
-            }
-        }
-    };
-
-    // depthwise weights of this lane's channel: warps 0-7 -> channels 0..31, warps 8-15 -> 32..63
-    const int ch = ((warp >> 3) << 5) + lane;
-    const int run = warp & 7;
-    float w1[9], w2[9], b1, b2 = 0.f;
-#pragma unroll
-    for (int t = 0; t < 9; ++t) { w1[t] = __ldg(w1g + ch * 9 + t); w2[t] = NOUT == 2 ? __ldg(w2g + ch * 9 + t) : 0.f; }
-    b1 = __ldg(b1g + ch);
-    if (NOUT == 2) b2 = __ldg(b2g + ch);
-
-    auto dw_strip = [&](int s) {
-        const int c0 = run * RC;
-        if (c0 >= OC) return;
-        const int rlo = MSR * s;
-        float win[3][RC + 2];
-        auto load_row = [&](int rr, float (&dst)[RC + 2]) {
-            const float* rp = ring + (rr % MRING) * RSTRIDE + ch;
-#pragma unroll
-            for (int c = 0; c < RC + 2; ++c) dst[c] = (c0 + c < IC) ? rp[(c0 + c) * MC] : 0.f;
-        };
-        load_row(rlo, win[0]);
-        load_row(rlo + 1, win[1]);
-#pragma unroll
-        for (int k = 0; k < MSR; ++k) {
-            const int orow = rlo + k;
-            if (orow < OR) {
-                load_row(orow + 2, win[(k + 2) % 3]);
-                const float (&ra)[RC + 2] = win[k % 3];
-                const float (&rb)[RC + 2] = win[(k + 1) % 3];
-                const float (&rc)[RC + 2] = win[(k + 2) % 3];
-#pragma unroll
-                for (int c = 0; c < RC; ++c) {
-                    const int col = c0 + c;
-                    if (col < OC) {
-                        float a1 = b1;
-                        a1 = fmaf(w1[0], ra[c], a1); a1 = fmaf(w1[1], ra[c + 1], a1); a1 = fmaf(w1[2], ra[c + 2], a1);
-                        a1 = fmaf(w1[3], rb[c], a1); a1 = fmaf(w1[4], rb[c + 1], a1); a1 = fmaf(w1[5], rb[c + 2], a1);
-                        a1 = fmaf(w1[6], rc[c], a1); a1 = fmaf(w1[7], rc[c + 1], a1); a1 = fmaf(w1[8], rc[c + 2], a1);
-                        float a2 = b2;
-                        if (NOUT == 2) {
-                            a2 = fmaf(w2[0], ra[c], a2); a2 = fmaf(w2[1], ra[c + 1], a2); a2 = fmaf(w2[2], ra[c + 2], a2);
-                            a2 = fmaf(w2[3], rb[c], a2); a2 = fmaf(w2[4], rb[c + 1], a2); a2 = fmaf(w2[5], rb[c + 2], a2);
-                            a2 = fmaf(w2[6], rc[c], a2); a2 = fmaf(w2[7], rc[c + 1], a2); a2 = fmaf(w2[8], rc[c + 2], a2);
-                        }
-                        if (MODE) {   // K / V are exactly 0 outside the image (attention zero padding)
-                            const int fy = y0 - Cf::R + orow, fx = x0 - Cf::R + col;
-                            if (fy < 0 || fy >= p.H || fx < 0 || fx >= p.W) { a1 = 0.f; a2 = 0.f; }
-                        }
-                        const int pos = orow * OC + col;
-                        const uint32_t off = swz(pos, ch);
-                        *reinterpret_cast<__half*>(out1 + off) = __float2half_rn(clamp_h(a1));
-                        if (NOUT == 2) *reinterpret_cast<__half*>(out2 + off) = __float2half_rn(clamp_h(a2));
-                    }
-                }
-            }
-        }
-    };
-
-    // ---- prologue: ring rows 0..5 ----
-    compute_pos(-1, 1);
-    compute_pos(0, 0);
+    if (threadIdx.x < 256) gather_role<K, MODE, TSRC>(p, src, srcW, n, y0, x0, ring, posw, posi);
+    else dw_role<K, MODE>(p, y0, x0, ring, out1, out2, w1g, b1g, w2g, b2g);
     __syncthreads();
-    issue(-1, 1); commit(-1, 1);
-    issue(0, 0); commit(0, 0);
-    __syncthreads();
-    if (NSTEP > 1) compute_pos(1, 1);
-    __syncthreads();
-    // ---- steady state: taps of strip s+1 in flight while the depthwise convs of strip s run ----
-#pragma unroll 1
-    for (int s = 0; s < NSTEP; ++s) {
-        const bool more = s + 1 < NSTEP;
-        if (more) issue(s + 1, (s + 1) & 1);
-        dw_strip(s);
-        if (more) commit(s + 1, (s + 1) & 1);
-        if (s + 2 < NSTEP) compute_pos(s + 2, s & 1);
-        __syncthreads();
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
