@@ -21,29 +21,17 @@
 //
 // HBM traffic per launch: hr (NHWC fp32, read through L2; frames of a GOP are scheduled tile-major so
 // the shared keyframe tile stays L2 resident), lr, MV field, logits (+ argmax, + fused p if asked).
-#include "common.cuh"
-#include <cuda_fp16.h>
+#include "creff_mma_common.cuh"
+#include <cstdlib>
 
 namespace arseg {
 
 constexpr int MT = 16;            // tile edge (pixels)
 constexpr int MTHREADS = 512;     // 16 warps
-constexpr int MC = 64;            // channels
 constexpr int MSR = 4;            // strip rows
 constexpr int MRING = 10;         // ring rows
 constexpr int MCLS_LD = 72;       // f16 row stride of the classifier weights in smem (bank-conflict pad)
 constexpr int MOUT_LD = 260;      // fp32 row stride of the staged logits planes
-
-struct CreffMmaParams {
-    const float* hr; int hr_shared;
-    const void* flow; int flow_dtype, Hm, Wm;
-    const void* lr; int h, w;
-    const float *wq, *bq, *wk, *bk, *wv, *bv, *wcls, *bcls;
-    int ncls, log_softmax;
-    float* out_p; float* out_logits; uint8_t* out_argmax;
-    int N, C, H, W;
-    int tiles_x, tiles_y;
-};
 
 template <int K> struct MCfg {
     static constexpr int R = K / 2;
@@ -61,114 +49,6 @@ template <int K> struct MCfg {
 };
 
 // ---------------------------------------------------------------------------------------------
-// small PTX wrappers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ float clamp_h(float v) { return fminf(fmaxf(v, -60000.f), 60000.f); }
-__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-}
-// byte offset of channel `ch` of row `pos` in a swizzled [pos][64 x f16] tile
-__device__ __forceinline__ uint32_t swz(int pos, int ch) {
-    return (uint32_t)(pos * 128 + ((((ch >> 3) ^ pos) & 7) << 4) + (ch & 7) * 2);
-}
-__device__ __forceinline__ uint32_t swz_chunk(int pos, int chunk) { return (uint32_t)(pos * 128 + (((chunk ^ pos) & 7) << 4)); }
-
-__device__ __forceinline__ double mflow_raw(const void* flow, int dtype, size_t idx) {
-    if (dtype == ARSEG_I16) return (double)reinterpret_cast<const int16_t*>(flow)[idx] / 4.0;  // dataset/camvid.py:625
-    if (dtype == ARSEG_F64) return reinterpret_cast<const double*>(flow)[idx];
-    return (double)reinterpret_cast<const float*>(flow)[idx];
-}
-// evaluation.py:177-180 at one feature pixel (f64): flow * Hf/Hm, bilinear align_corners=True resize
-__device__ __forceinline__ void mflow_at(const CreffMmaParams& p, int n, int fy, int fx, double& u, double& v) {
-    const size_t base = (size_t)n * p.Hm * p.Wm;
-    const double sc = (double)p.H / (double)p.Hm;
-    if (p.Hm == p.H && p.Wm == p.W) {
-        const size_t i = (base + (size_t)fy * p.Wm + fx) * 2;
-        u = mflow_raw(p.flow, p.flow_dtype, i) * sc;
-        v = mflow_raw(p.flow, p.flow_dtype, i + 1) * sc;
-        return;
-    }
-    const double sh = p.H > 1 ? (double)(p.Hm - 1) / (double)(p.H - 1) : 0.0;
-    const double sw = p.W > 1 ? (double)(p.Wm - 1) / (double)(p.W - 1) : 0.0;
-    const double ry = sh * fy, rx = sw * fx;
-    int ya = min((int)ry, p.Hm - 1), xa = min((int)rx, p.Wm - 1);
-    const int yb = ya + (ya < p.Hm - 1 ? 1 : 0), xb = xa + (xa < p.Wm - 1 ? 1 : 0);
-    const double ly1 = ry - ya, ly0 = 1.0 - ly1, lx1 = rx - xa, lx0 = 1.0 - lx1;
-    double r[2];
-#pragma unroll
-    for (int ch = 0; ch < 2; ++ch) {
-        const double a = mflow_raw(p.flow, p.flow_dtype, (base + (size_t)ya * p.Wm + xa) * 2 + ch) * sc;
-        const double b = mflow_raw(p.flow, p.flow_dtype, (base + (size_t)ya * p.Wm + xb) * 2 + ch) * sc;
-        const double c = mflow_raw(p.flow, p.flow_dtype, (base + (size_t)yb * p.Wm + xa) * 2 + ch) * sc;
-        const double d = mflow_raw(p.flow, p.flow_dtype, (base + (size_t)yb * p.Wm + xb) * 2 + ch) * sc;
-        r[ch] = ly0 * (lx0 * a + lx1 * b) + ly1 * (lx0 * c + lx1 * d);
-    }
-    u = r[0]; v = r[1];
-}
-
-// Per-position gather record: 4 tap weights (invalid taps already zeroed) + packed source address:
-// info = (pixel index of the NW tap, clamped into the image) << 2 | dx << 1 | dy, or -1 = "all zero".
-struct PosRec { float4 w; int info; };
-
-// warped-hr sample (evaluation.py:61-87) at feature pixel (fy,fx); zero outside the image (depthwise padding)
-__device__ __forceinline__ PosRec pos_hr(const CreffMmaParams& p, int n, int fy, int fx) {
-    PosRec r; r.w = make_float4(0.f, 0.f, 0.f, 0.f); r.info = -1;
-    if (fy < 0 || fy >= p.H || fx < 0 || fx >= p.W) return r;
-    float ix = (float)fx, iy = (float)fy;
-    if (p.flow) {
-        double u, v;
-        mflow_at(p, n, fy, fx, u, v);
-        warp_source_pos(fx, fy, u, v, p.W, p.H, ix, iy);
-    }
-    if (!(ix > -1.5f && ix < (float)p.W + 0.5f && iy > -1.5f && iy < (float)p.H + 0.5f)) return r;  // all taps outside
-    const float fxn = floorf(ix), fyn = floorf(iy);
-    const int xa = (int)fxn, ya = (int)fyn, xb = xa + 1, yb = ya + 1;
-    const bool vxa = xa >= 0 && xa < p.W, vxb = xb >= 0 && xb < p.W, vya = ya >= 0 && ya < p.H, vyb = yb >= 0 && yb < p.H;
-    const float wxa = (fxn + 1.f) - ix, wxb = ix - fxn, wya = (fyn + 1.f) - iy, wyb = iy - fyn;   // grid_sample weights
-    r.w.x = (vya && vxa) ? wxa * wya : 0.f;
-    r.w.y = (vya && vxb) ? wxb * wya : 0.f;
-    r.w.z = (vyb && vxa) ? wxa * wyb : 0.f;
-    r.w.w = (vyb && vxb) ? wxb * wyb : 0.f;
-    const int cxa = min(max(xa, 0), p.W - 1), cxb = min(max(xb, 0), p.W - 1);
-    const int cya = min(max(ya, 0), p.H - 1), cyb = min(max(yb, 0), p.H - 1);
-    r.info = ((cya * p.W + cxa) << 2) | ((cxb - cxa) << 1) | (cyb - cya);
-    return r;
-}
-// lr_up sample (model/attention.py:191, bilinear align_corners=True); zero outside the image
-__device__ __forceinline__ PosRec pos_lr(const CreffMmaParams& p, float lsh, float lsw, int fy, int fx) {
-    PosRec r; r.w = make_float4(0.f, 0.f, 0.f, 0.f); r.info = -1;
-    if (fy < 0 || fy >= p.H || fx < 0 || fx >= p.W) return r;
-    int ya, yb, xa, xb; float lya, lyb, lxa, lxb;
-    bilinear_src(lsh, fy, p.h, ARSEG_RESIZE_BILINEAR_AC, ya, yb, lya, lyb);
-    bilinear_src(lsw, fx, p.w, ARSEG_RESIZE_BILINEAR_AC, xa, xb, lxa, lxb);
-    r.w = make_float4(lya * lxa, lya * lxb, lyb * lxa, lyb * lxb);
-    r.info = ((ya * p.w + xa) << 2) | ((xb - xa) << 1) | (yb - ya);
-    return r;
-}
-
-// two consecutive channels of a source pixel as float2
-__device__ __forceinline__ float2 ld2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
-__device__ __forceinline__ float2 ld2(const __nv_bfloat16* p) {
-    const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(p));
-    return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
-}
-
-// ---------------------------------------------------------------------------------------------
 // Producer (warp specialised).  A (OR+2)x(OC+2) fp32 tile is gathered bilinearly from an NHWC source in
 // 4-row strips into the smem ring by warps 0-7, and consumed by warps 8-15, which apply NOUT depthwise 3x3
 // convolutions (+bias) and write swizzled f16 rows.  The two groups hand strips over through named barriers
@@ -176,24 +56,6 @@ __device__ __forceinline__ float2 ld2(const __nv_bfloat16* p) {
 // the gather of strip s+1/s+2 overlaps the convolutions of strip s.
 //   MODE 0: source = lr (lr_up tile), NOUT = 1 (Q);   MODE 1: source = hr (warped tile), NOUT = 2 (K, V)
 // ---------------------------------------------------------------------------------------------
-constexpr int BAR_FULL = 1, BAR_EMPTY = 3, BAR_GATHER = 5;   // named barrier ids (0 = __syncthreads)
-__device__ __forceinline__ void nbar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void nbar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-
-// four consecutive channels of a source pixel as float4
-__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-__device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
-    const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
-    return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
-                       __uint_as_float(u.y & 0xffff0000u));
-}
-// (lo, hi) -> packed f16x2 with saturation to +-65504 (one F2FP.SATFINITE)
-__device__ __forceinline__ uint32_t pack_h2_sat(float lo, float hi) {
-    uint32_t r;
-    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-    return r;
-}
-
 template <int K, int MODE> struct PCfg {
     using Cf = MCfg<K>;
     static constexpr int OR = MODE ? Cf::KR : MT, OC = MODE ? Cf::KC : MT;   // output tile
@@ -683,6 +545,15 @@ bool creff_mma_supported(const arseg_creff_args* a) {
            (!a->wcls || a->ncls <= 32) && ((size_t)a->H * a->W < (1u << 29)) && ((size_t)a->h * a->w < (1u << 29));
 }
 
+int creff_march_launch(CreffMmaParams& p, int k, bool lr_bf16, cudaStream_t st);   // creff_march.cu
+
+// ARSEG_CREFF_MMA_F16 runs the column-marching engine (creff_march.cu); ARSEG_CREFF_TILE=1 selects the older
+// square-tile engine of this file (kept for A/B measurements).
+static bool use_tile_engine() {
+    const char* e = getenv("ARSEG_CREFF_TILE");
+    return e && e[0] == '1';
+}
+
 int creff_mma_launch(const arseg_creff_args* a, cudaStream_t st) {
     CreffMmaParams p;
     p.hr = a->hr; p.hr_shared = a->hr_shared; p.flow = a->flow; p.flow_dtype = a->flow_dtype; p.Hm = a->Hm; p.Wm = a->Wm;
@@ -691,6 +562,7 @@ int creff_mma_launch(const arseg_creff_args* a, cudaStream_t st) {
     p.ncls = a->ncls; p.log_softmax = a->log_softmax; p.out_p = a->out_p; p.out_logits = a->out_logits;
     p.out_argmax = a->out_argmax; p.N = a->N; p.C = a->C; p.H = a->H; p.W = a->W;
     const bool bf = a->lr_dtype == ARSEG_BF16;
+    if (!use_tile_engine()) return creff_march_launch(p, a->k, bf, st);
     switch (a->k) {
         case 3: return bf ? creff_mma_launch_t<3, __nv_bfloat16>(p, st) : creff_mma_launch_t<3, float>(p, st);
         case 5: return bf ? creff_mma_launch_t<5, __nv_bfloat16>(p, st) : creff_mma_launch_t<5, float>(p, st);

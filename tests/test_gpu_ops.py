@@ -327,6 +327,46 @@ def test_creff_mma_with_mv_warp_and_classifier(flow_kind, stride, lr_dtype):
         assert torch.equal(out_a[i:i + 1].cpu().long(), out_l[i:i + 1].cpu().argmax(1))
 
 
+@pytest.mark.parametrize("k", [3, 7, 9])
+@pytest.mark.parametrize("seg_rows", [8, 12])
+def test_creff_march_row_segments_are_seamless(k, seg_rows, monkeypatch):
+    """The column-marching engine splits a frame into row segments (one CTA each); every pixel's arithmetic is
+    independent of the split, so the segmented result must equal the single-segment one bit for bit."""
+    from arseg_b200 import synth
+    C, ncls, H, W, h, w = 64, 12, 42, 52, 21, 26
+    sd = creff_sd(C)
+    hr, lr = rnd(1, C, H, W, seed=153) * 0.6, rnd(2, C, h, w, seed=154) * 0.4
+    wcls, bcls = rnd(ncls, C, seed=155) * 0.2, rnd(ncls, seed=156) * 0.1
+    mvs = torch.from_numpy(np.stack([synth.synth_mv_int16(H, W, 160 + i, distance=4 + 5 * i) for i in range(2)])).to(DEV)
+
+    def run():
+        return ops.creff_fused(ops.nchw_to_nhwc(hr.to(DEV)), ops.nchw_to_nhwc(lr.to(DEV)), *creff_args(sd), k, flow=mvs,
+                               wcls=wcls.to(DEV), bcls=bcls.to(DEV), log_softmax=True, want_argmax=True, hr_shared=True,
+                               lr_layout=L.NHWC, hr_layout=L.NHWC, engine=L.CREFF_MMA_F16)
+    monkeypatch.setenv("ARSEG_CREFF_SEG_ROWS", "4096")
+    one = run()
+    monkeypatch.setenv("ARSEG_CREFF_SEG_ROWS", str(seg_rows))
+    seg = run()
+    for a, b in zip(one, seg):
+        assert torch.equal(a, b)
+    flow64 = mvs.cpu().double() / 4.0
+    for i in range(2):
+        fused = O.creff(sd, "fuse_attention.", O.warp_feature(hr, O.resize_flow(flow64[i:i + 1], H, W)), lr[i:i + 1], k)
+        assert rel_err(seg[0][i:i + 1], fused) < MMA_TOL
+
+
+def test_creff_tile_engine_still_matches(monkeypatch):
+    """ARSEG_CREFF_TILE=1 selects the square-tile engine (kept for A/B measurements)."""
+    monkeypatch.setenv("ARSEG_CREFF_TILE", "1")
+    C, H, W, h, w, k = 64, 32, 48, 16, 24, 7
+    sd = creff_sd(C)
+    hr, lr = rnd(1, C, H, W, seed=51) * 0.6, rnd(1, C, h, w, seed=52) * 0.4
+    ref = O.creff(sd, "fuse_attention.", hr, lr, k)
+    out_p, _, _ = ops.creff_fused(ops.nchw_to_nhwc(hr.to(DEV)), ops.nchw_to_nhwc(lr.to(DEV)), *creff_args(sd), k,
+                                  want_logits=False, lr_layout=L.NHWC, hr_layout=L.NHWC, engine=L.CREFF_MMA_F16)
+    assert rel_err(out_p, ref) < MMA_TOL
+
+
 def test_creff_mma_rejects_unsupported():
     sd = creff_sd(16)
     hr, lr = rnd(1, 16, 16, 16, seed=1), rnd(1, 16, 8, 8, seed=2)
