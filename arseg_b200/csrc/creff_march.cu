@@ -10,9 +10,9 @@
 //     ((16+k+1)/16 gather, (16+k-1)/16 depthwise) instead of the (16+k+1)^2/256 of a square tile.
 //   * three warp-specialised roles run CONCURRENTLY on different steps of the march, handing rows over through
 //     mbarriers (4-deep, indexed by step):
-//       G (8 warps): bilinear gather of the MV-warped hr rows and the lr_up rows into fp32 row rings
+//       G (6 warps): bilinear gather of the MV-warped hr rows and the lr_up rows into fp32 row rings
 //                    (half-warp per position, float4 per lane; f64 MV arithmetic one position per thread);
-//       D (4 warps): the three depthwise 3x3 convolutions (FFMA2, x-marching register window): K,V -> f16
+//       D (6 warps): the three depthwise 3x3 convolutions (FFMA2, x-marching register window): K,V -> f16
 //                    rings, Q -> f16 tile, lr_up centre (the residual) -> fp32 tile;
 //       C (4 warps): one 4x4-pixel block each: S = Q K^T (mma.sync m16n8k16 f16, fp32 accumulate) on the
 //                    (k+3)^2 key patch, masked softmax in registers, O = resid*sum + P V, classifier MMA,
@@ -28,13 +28,17 @@ namespace arseg {
 
 constexpr int XSW = 16;                 // strip width (pixels)
 constexpr int XTHREADS = 512;
-constexpr int XG_THREADS = 256, XD_THREADS = 128, XC_THREADS = 128;
+constexpr int XG_WARPS = 6, XD_WARPS = 6, XC_WARPS = 4;                 // warps 0-5 / 6-11 / 12-15
+static_assert((XG_WARPS + XD_WARPS) % 4 == 0 && XC_WARPS % 4 == 0, "setmaxnreg works on whole warpgroups");
+constexpr int XG_THREADS = 32 * XG_WARPS, XD_THREADS = 32 * XD_WARPS, XC_THREADS = 32 * XC_WARPS;
+constexpr int XNHW = XG_THREADS / 16;   // gather half-warps: one position each per slot
 constexpr int XHR_RING = 10, XLR_RING = 10;   // fp32 row rings (rows)
+constexpr int XJA = 4;                  // gather positions in flight per half-warp (ring of single-position slots)
 constexpr int XRES_LD = 72;             // floats per residual row (bank-conflict pad)
 constexpr int XCLS_LD = 72;             // f16 per classifier-weight row
-constexpr int XJA = 4;                  // gather positions in flight per half-warp
 constexpr int XNB = 4;                  // mbarriers per hand-off (indexed by step & 3)
 constexpr int XBAR_G = 1;               // named barrier of the G group
+constexpr int XQG = 2;                  // QK n-tiles interleaved (the legacy tensor pipe takes ~17 clk per MMA per SMSP)
 
 template <int K> struct XCfg {
     static constexpr int R = K / 2;
@@ -47,15 +51,20 @@ template <int K> struct XCfg {
     static constexpr int KVR = P0 + 4 * SL;                 // K/V ring rows
     static constexpr int WN = K + 3, NK = WN * WN;          // key patch of a 4x4 block
     static constexpr int NT16 = (NK + 15) / 16, NT8 = 2 * NT16;
-    static constexpr int PMAX = (G0 * HC > 4 * HC + 4 * LC) ? G0 * HC : 4 * HC + 4 * LC;   // positions per G step
+    static constexpr int PREAL = (G0 * HC > 4 * HC + 4 * LC) ? G0 * HC : 4 * HC + 4 * LC;  // positions per G step
+    static constexpr int PMAX = ((PREAL + XNHW * XJA - 1) / (XNHW * XJA)) * (XNHW * XJA);  // padded with no-op records
     static constexpr size_t KV_BYTES = (size_t)KVR * KVC * 128;
     static constexpr size_t HR_BYTES = (size_t)XHR_RING * HC * 256;
     static constexpr size_t LR_BYTES = (size_t)XLR_RING * LC * 256;
     static constexpr size_t Q_BYTES = 64 * 128;
     static constexpr size_t RES_BYTES = 64 * XRES_LD * 4;
-    static constexpr size_t POS_BYTES = 2 * (size_t)PMAX * 24;
+    static constexpr size_t POS_BYTES = (size_t)PMAX * 24;
     static constexpr size_t CLS_BYTES = 32 * XCLS_LD * 2 + 32 * 4;
-    static constexpr size_t SMEM = 2 * KV_BYTES + HR_BYTES + LR_BYTES + Q_BYTES + RES_BYTES + POS_BYTES + CLS_BYTES + 4 * XNB * 8;
+    static constexpr size_t SCRATCH_BYTES = 256;                  // ring-like slot the no-op gather records write to
+    static constexpr size_t DWW_BYTES = 3 * 10 * 32 * 8;          // depthwise weights + bias, float2 per lane
+    static_assert(CLS_BYTES <= Q_BYTES, "classifier staging aliases the Q tile");
+    static constexpr size_t SMEM = 2 * KV_BYTES + HR_BYTES + LR_BYTES + SCRATCH_BYTES + Q_BYTES + RES_BYTES + POS_BYTES + DWW_BYTES + 4 * XNB * 8;
+    static_assert(PMAX <= XG_THREADS, "one position record per G thread");
     static_assert(4 + 2 * R <= KVR, "K/V ring too small for one consumer step");
     static_assert(SMEM <= 232448, "shared memory budget");
 };
@@ -77,9 +86,9 @@ __device__ __forceinline__ void xbar_wait(uint64_t* bars, int step) {
     for (int spin = 0; !ok; ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+            : "=r"(ok) : "r"(addr), "r"(parity), "r"(2000u) : "memory");
         if (!ok && (spin & 1023) == 1023) {          // bounded: a protocol bug must not hang the GPU box
             if (t0 == 0) t0 = clock64();
             else if (clock64() - t0 > 4000000000LL) {
@@ -98,6 +107,20 @@ __device__ __forceinline__ uint32_t q_off(int row, int col, int chunk) {
     return (uint32_t)((row * XSW + col) * 128 + (((chunk ^ ((col & 3) | ((row & 1) << 2))) & 7) << 4));
 }
 
+// Optional timeline trace (compile with -DARSEG_XTRACE): lane 0 of the first warp of every role of CTA XTRACE_CTA
+// records (role, step, tag, clock64) tuples; read back with arseg_debug_creff_trace().
+#ifdef ARSEG_XTRACE
+constexpr int XTRACE_STEPS = 256, XTRACE_TAGS = 8, XTRACE_N = 3 * XTRACE_STEPS * XTRACE_TAGS;
+__device__ long long g_xtrace[XTRACE_N];
+__device__ __forceinline__ void xtrace(int role, int step, int tag) {
+    if (blockIdx.x == 148 * 2 + 7 && (threadIdx.x == 0 || threadIdx.x == 32 * XG_WARPS || threadIdx.x == 384) && step + 1 < XTRACE_STEPS)
+        g_xtrace[(role * XTRACE_STEPS + step + 1) * XTRACE_TAGS + tag] = clock64();
+}
+#define XTRACE(role, step, tag) xtrace(role, step, tag)
+#else
+#define XTRACE(role, step, tag)
+#endif
+
 struct XSmem {
     uint8_t *sK, *sV, *rings, *sQ;
     float* sRes;
@@ -105,6 +128,7 @@ struct XSmem {
     int2* posid;
     __half* s_wc;
     float* s_bc;
+    float2* s_dw;     // [3 convs: k, v, q][9 taps + bias][32 lanes] (channels 2*lane, 2*lane+1)
     uint64_t *gfull, *ddone, *cdone, *qlempty;
 };
 
@@ -125,109 +149,145 @@ __device__ __forceinline__ void x_step_geom(int t, int& h0, int& nh, int& l0, in
 template <int K, typename TLR>
 __device__ __forceinline__ void x_g_role(const CreffMmaParams& p, const XSmem& sm, int n, int x0, int ya, int S) {
     using Cf = XCfg<K>;
+    constexpr int NHW = XNHW;                             // half-warps: one gather position each
+    constexpr int LR_ES = (int)sizeof(TLR);
+    constexpr int SCRATCH_IDX = (int)((Cf::HR_BYTES + Cf::LR_BYTES) / 256);
     const int gt = threadIdx.x, lane = gt & 31, hw = gt >> 4, cl = lane & 15;
     const float lsh = resize_scale(p.h, p.H, ARSEG_RESIZE_BILINEAR_AC), lsw = resize_scale(p.w, p.W, ARSEG_RESIZE_BILINEAR_AC);
-    const float* __restrict__ hr = p.hr + (p.hr_shared ? 0 : (size_t)n * p.H * p.W * MC) + 4 * cl;
-    const TLR* __restrict__ lr = reinterpret_cast<const TLR*>(p.lr) + (size_t)n * p.h * p.w * MC + 4 * cl;
-    const int hr_rs = p.W * MC, lr_rs = p.w * MC;
+    // this lane's 4 channels of a source pixel; tap byte offsets come from the position records
+    const char* const hrb = reinterpret_cast<const char*>(p.hr + (p.hr_shared ? 0 : (size_t)n * p.H * p.W * MC) + 4 * cl);
+    const char* const lrb = reinterpret_cast<const char*>(reinterpret_cast<const TLR*>(p.lr) + (size_t)n * p.h * p.w * MC + 4 * cl);
+    const double rcp_w = 2.0 / (double)max(p.W - 1, 1), rcp_h = 2.0 / (double)max(p.H - 1, 1);
 
+    // position record q of a step (one per G thread): bilinear weights (invalid taps zeroed) + {byte offset of the NW
+    // tap, flags}: flags = ring offset / 256 | dx << 12 | dy << 13 | lr << 14 | all-zero << 15.  The record list is
+    // padded to a multiple of NHW * XJA with no-op records (zero weights, scratch destination), so the gather loop
+    // is branch-free.  Single-buffered: the records of step t+1 are written after the last use of those of step t.
+    const bool mv_fast = p.flow && p.flow_dtype == ARSEG_I16 && p.Hm == p.H && p.Wm == p.W;
+    const int* const mvp = reinterpret_cast<const int*>(p.flow) + (size_t)n * p.H * p.W;
+    auto padded = [](int npos) { return ((npos + NHW * XJA - 1) / (NHW * XJA)) * (NHW * XJA); };
     auto compute_pos = [&](int t) {
         int h0, nh, l0, nl;
         x_step_geom<K>(t, h0, nh, l0, nl);
-        const int nhp = nh * Cf::HC;
-        if (gt < nhp + nl * Cf::LC) {
-            PosRec r; int dst;
-            if (gt < nhp) {
-                const int rr = gt / Cf::HC, cc = gt - rr * Cf::HC, row = h0 + rr;
-                r = pos_hr(p, n, ya - Cf::R - 1 + row, x0 - Cf::R - 1 + cc);
-                dst = ((row % XHR_RING) * Cf::HC + cc) * 256;
-            } else {
-                const int q = gt - nhp, rr = q / Cf::LC, cc = q - rr * Cf::LC, row = l0 + rr;
-                r = pos_lr(p, lsh, lsw, ya - 1 + row, x0 - 1 + cc);
-                dst = ((int)Cf::HR_BYTES + ((row % XLR_RING) * Cf::LC + cc) * 256) | (1 << 30);
-            }
-            const int buf = (t + 1) & 1;
-            sm.posw[buf * Cf::PMAX + gt] = r.w;
-            sm.posid[buf * Cf::PMAX + gt] = make_int2(r.info, dst);
+        const int nhp = nh * Cf::HC, npos = nhp + nl * Cf::LC;
+        const int q = gt;
+        if (q >= padded(npos)) return;
+        PosRec r; r.w = make_float4(0.f, 0.f, 0.f, 0.f); r.info = -1;
+        int fl = SCRATCH_IDX, off = 0;
+        if (q < nhp) {
+            const int rr = q / Cf::HC, cc = q - rr * Cf::HC, row = h0 + rr;
+            const int fy = ya - Cf::R - 1 + row, fx = x0 - Cf::R - 1 + cc;
+            int mv = 0;
+            if (mv_fast && fy >= 0 && fy < p.H && fx >= 0 && fx < p.W) mv = __ldg(mvp + (size_t)fy * p.W + fx);
+            r = pos_hr(p, n, fy, fx, rcp_w, rcp_h, mv_fast ? &mv : nullptr);
+            fl = (row % XHR_RING) * Cf::HC + cc;
+            off = (r.info >> 2) * (MC * 4);
+        } else if (q < npos) {
+            const int q2 = q - nhp, rr = q2 / Cf::LC, cc = q2 - rr * Cf::LC, row = l0 + rr;
+            r = pos_lr(p, lsh, lsw, ya - 1 + row, x0 - 1 + cc);
+            fl = ((int)(Cf::HR_BYTES / 256) + (row % XLR_RING) * Cf::LC + cc) | (1 << 14);
+            off = (r.info >> 2) * (MC * LR_ES);
         }
+        if (r.info < 0) { off = 0; fl = (fl & ~(1 << 14)) | 1 << 15; }     // outside the image / padding: exact zeros
+        else fl |= ((r.info >> 1) & 1) << 12 | (r.info & 1) << 13;
+        sm.posw[q] = r.w;
+        sm.posid[q] = make_int2(off, fl);
     };
+    const uint32_t hr_rs = (uint32_t)p.W * MC * 4, lr_rs = (uint32_t)p.w * MC * LR_ES;
     float4 tap[XJA][4];
-    auto issue = [&](int buf, int npos, int j0) {
-#pragma unroll
-        for (int j = 0; j < XJA; ++j) {
-            const int i = hw + 16 * (j0 + j);
-            int2 id = make_int2(-1, 0);
-            if (i < npos) id = sm.posid[buf * Cf::PMAX + i];
-            if (id.x >= 0) {
-                const int dx = (id.x >> 1) & 1, dy = id.x & 1;
-                const size_t pix = (size_t)(id.x >> 2) * MC;
-                if (!(id.y >> 30)) {
-                    const float* s = hr + pix;
-                    const float* s2 = s + dy * hr_rs;
-                    tap[j][0] = ld4(s); tap[j][1] = ld4(s + dx * MC); tap[j][2] = ld4(s2); tap[j][3] = ld4(s2 + dx * MC);
-                } else {
-                    const TLR* s = lr + pix;
-                    const TLR* s2 = s + dy * lr_rs;
-                    tap[j][0] = ld4(s); tap[j][1] = ld4(s + dx * MC); tap[j][2] = ld4(s2); tap[j][3] = ld4(s2 + dx * MC);
-                }
-            } else {
-                tap[j][0] = tap[j][1] = tap[j][2] = tap[j][3] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+    auto issue = [&](float4 (&tp)[4], int j) {
+#ifdef ARSEG_XTRACE
+        if (p.dbg & 4) return;
+#endif
+        const int2 id = sm.posid[hw + NHW * j];
+        const bool islr = (id.y >> 14) & 1;
+        const uint32_t dxb = (id.y & (1 << 12)) ? (islr ? MC * LR_ES : MC * 4) : 0u;
+        const uint32_t dyb = (id.y & (1 << 13)) ? (islr ? lr_rs : hr_rs) : 0u;
+        if (LR_ES == 4 || !islr) {
+            const char* a = (islr ? lrb : hrb) + (uint32_t)id.x;
+            tp[0] = ld4(reinterpret_cast<const float*>(a));
+            tp[1] = ld4(reinterpret_cast<const float*>(a + dxb));
+            tp[2] = ld4(reinterpret_cast<const float*>(a + dyb));
+            tp[3] = ld4(reinterpret_cast<const float*>(a + dxb + dyb));
+        } else {
+            const char* a = lrb + (uint32_t)id.x;
+            tp[0] = ld4(reinterpret_cast<const TLR*>(a));
+            tp[1] = ld4(reinterpret_cast<const TLR*>(a + dxb));
+            tp[2] = ld4(reinterpret_cast<const TLR*>(a + dyb));
+            tp[3] = ld4(reinterpret_cast<const TLR*>(a + dxb + dyb));
         }
     };
-    auto commit = [&](int buf, int npos, int j0) {
-#pragma unroll
-        for (int j = 0; j < XJA; ++j) {
-            const int i = hw + 16 * (j0 + j);
-            if (i < npos) {
-                const float4 w = sm.posw[buf * Cf::PMAX + i];
-                const int dst = sm.posid[buf * Cf::PMAX + i].y & 0x3fffffff;
-                float4 v;
-                v.x = tap[j][0].x * w.x + tap[j][1].x * w.y + tap[j][2].x * w.z + tap[j][3].x * w.w;
-                v.y = tap[j][0].y * w.x + tap[j][1].y * w.y + tap[j][2].y * w.z + tap[j][3].y * w.w;
-                v.z = tap[j][0].z * w.x + tap[j][1].z * w.y + tap[j][2].z * w.z + tap[j][3].z * w.w;
-                v.w = tap[j][0].w * w.x + tap[j][1].w * w.y + tap[j][2].w * w.z + tap[j][3].w * w.w;
-                *reinterpret_cast<float4*>(sm.rings + dst + 16 * cl) = v;
-            }
-        }
+    auto commit = [&](const float4 (&tp)[4], int j) {
+        const int i = hw + NHW * j;
+        const float4 w = sm.posw[i];
+        const int fl = sm.posid[i].y;
+        float4 v;
+        v.x = tp[0].x * w.x + tp[1].x * w.y + tp[2].x * w.z + tp[3].x * w.w;
+        v.y = tp[0].y * w.x + tp[1].y * w.y + tp[2].y * w.z + tp[3].y * w.w;
+        v.z = tp[0].z * w.x + tp[1].z * w.y + tp[2].z * w.z + tp[3].z * w.w;
+        v.w = tp[0].w * w.x + tp[1].w * w.y + tp[2].w * w.z + tp[3].w * w.w;
+        if (fl & (1 << 15)) v = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(sm.rings + (fl & 0xfff) * 256 + 16 * cl) = v;
     };
 
     compute_pos(-1);
     nbar_sync(XBAR_G, XG_THREADS);
 #pragma unroll 1
     for (int t = -1; t <= S; ++t) {
-        const int buf = (t + 1) & 1;
         int h0, nh, l0, nl;
         x_step_geom<K>(t, h0, nh, l0, nl);
-        const int npos = nh * Cf::HC + nl * Cf::LC;
-        if (t >= 1) xbar_wait(sm.ddone, t - 2);       // D step t-2 done: the ring rows this step overwrites are free
-        issue(buf, npos, 0);
-        if (t < S) compute_pos(t + 1);                // f64 MV arithmetic overlaps the loads in flight
-        commit(buf, npos, 0);
+        const int nj = padded(nh * Cf::HC + nl * Cf::LC) / NHW;   // positions of this half-warp (multiple of XJA)
+        XTRACE(0, t, 0);
+        // rolling pipeline: XJA positions' loads are always in flight while the oldest one is combined and stored
+#pragma unroll
+        for (int j = 0; j < XJA; ++j) issue(tap[j], j);
+        if (t >= 1) xbar_wait(sm.ddone, t - 2);           // D step t-2 done: the ring rows this step overwrites are free
+        XTRACE(0, t, 1);
 #pragma unroll 1
-        for (int j0 = XJA; 16 * j0 < npos; j0 += XJA) {
-            issue(buf, npos, j0);
-            commit(buf, npos, j0);
+        for (int j0 = 0; j0 < nj; j0 += XJA) {
+            if (j0 + XJA < nj) {
+#pragma unroll
+                for (int j = 0; j < XJA; ++j) { commit(tap[j], j0 + j); issue(tap[j], j0 + j + XJA); }
+            } else {
+#pragma unroll
+                for (int j = 0; j < XJA; ++j) commit(tap[j], j0 + j);
+            }
         }
-        nbar_sync(XBAR_G, XG_THREADS);                // position records of step t+1 visible to the group
+        XTRACE(0, t, 2);
         xbar_arrive(sm.gfull, t);
+        nbar_sync(XBAR_G, XG_THREADS);                    // every G thread is done with the records of step t
+        if (t < S) compute_pos(t + 1);
+        nbar_sync(XBAR_G, XG_THREADS);                    // records of step t+1 visible to the group
+        XTRACE(0, t, 3);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// D role: depthwise 3x3 convolutions.  Warp dw owns row dw of every 4-row strip.
-//   NOUT = 2: K/V row from the hr ring (input rows kr..kr+2, columns x..x+2); NOUT = 1: Q row + residual from lr ring.
+// D role: depthwise 3x3 convolutions.  Warp d = 3 * rp + third owns column third `third` of rows rp and rp + 2 of
+// every 4-row strip and convolves the two rows in one loop (two independent FFMA2 streams per warp).
+//   NOUT = 2: K/V rows from the hr ring (input rows kr..kr+2, columns x..x+2); NOUT = 1: Q rows + residual from lr ring.
 // ---------------------------------------------------------------------------------------------
-template <int NOUT, int INC, int OUTC, typename Store>
-__device__ __forceinline__ void x_dw_row(const float* rp0, const float* rp1, const float* rp2, const float2 (&w1)[9], const float2 b1,
-                                         const float2 (&w2)[9], const float2 b2, Store&& store) {
-    float2 win[3][3];   // [input row][slot]; slot (x + d) % 3 holds input column x + d
-    win[0][0] = *reinterpret_cast<const float2*>(rp0);
-    win[1][0] = *reinterpret_cast<const float2*>(rp1);
-    win[2][0] = *reinterpret_cast<const float2*>(rp2);
-    win[0][1] = *reinterpret_cast<const float2*>(rp0 + MC);
-    win[1][1] = *reinterpret_cast<const float2*>(rp1 + MC);
-    win[2][1] = *reinterpret_cast<const float2*>(rp2 + MC);
+template <int NOUT, typename Store>
+__device__ __forceinline__ void x_dw_rows2(const float* ra0, const float* ra1, const float* ra2, const float* rb0, const float* rb1,
+                                           const float* rb2, const int c_lo, const int OUTC, const float2 (&w1)[10], const float2 (&w2)[10],
+                                           Store&& store) {
+    ra0 += c_lo * MC; ra1 += c_lo * MC; ra2 += c_lo * MC;     // columns c_lo .. c_lo + OUTC - 1 (x below is relative to c_lo)
+    rb0 += c_lo * MC; rb1 += c_lo * MC; rb2 += c_lo * MC;
+    float2 wa[3][3], wb[3][3];   // [input row][slot]; slot (x + d) % 3 holds input column x + d
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        wa[0][c] = *reinterpret_cast<const float2*>(ra0 + c * MC); wa[1][c] = *reinterpret_cast<const float2*>(ra1 + c * MC);
+        wa[2][c] = *reinterpret_cast<const float2*>(ra2 + c * MC);
+        wb[0][c] = *reinterpret_cast<const float2*>(rb0 + c * MC); wb[1][c] = *reinterpret_cast<const float2*>(rb1 + c * MC);
+        wb[2][c] = *reinterpret_cast<const float2*>(rb2 + c * MC);
+    }
+    auto conv = [](const float2 (&w)[10], const float2 (&win)[3][3], int sa, int sb, int sc) {
+        // three independent row chains per output (shorter dependency chains than one 9-deep chain)
+        float2 a0 = __ffma2_rn(w[0], win[0][sa], w[9]), a1 = __fmul2_rn(w[3], win[1][sa]), a2 = __fmul2_rn(w[6], win[2][sa]);
+        a0 = __ffma2_rn(w[1], win[0][sb], a0); a1 = __ffma2_rn(w[4], win[1][sb], a1); a2 = __ffma2_rn(w[7], win[2][sb], a2);
+        a0 = __ffma2_rn(w[2], win[0][sc], a0); a1 = __ffma2_rn(w[5], win[1][sc], a1); a2 = __ffma2_rn(w[8], win[2][sc], a2);
+        return __fadd2_rn(__fadd2_rn(a0, a1), a2);
+    };
 #pragma unroll 1
     for (int xb = 0; xb < OUTC; xb += 3) {
 #pragma unroll
@@ -235,22 +295,17 @@ __device__ __forceinline__ void x_dw_row(const float* rp0, const float* rp1, con
             const int x = xb + u;
             if (x < OUTC) {
                 const int sa = u, sb = (u + 1) % 3, sc = (u + 2) % 3;     // slots of columns x, x+1, x+2
-                win[0][sc] = *reinterpret_cast<const float2*>(rp0 + (x + 2) * MC);
-                win[1][sc] = *reinterpret_cast<const float2*>(rp1 + (x + 2) * MC);
-                win[2][sc] = *reinterpret_cast<const float2*>(rp2 + (x + 2) * MC);
-                // three independent row chains per output (shorter dependency chains than one 9-deep chain)
-                float2 a0 = __ffma2_rn(w1[0], win[0][sa], b1), a1 = __fmul2_rn(w1[3], win[1][sa]), a2 = __fmul2_rn(w1[6], win[2][sa]);
-                a0 = __ffma2_rn(w1[1], win[0][sb], a0); a1 = __ffma2_rn(w1[4], win[1][sb], a1); a2 = __ffma2_rn(w1[7], win[2][sb], a2);
-                a0 = __ffma2_rn(w1[2], win[0][sc], a0); a1 = __ffma2_rn(w1[5], win[1][sc], a1); a2 = __ffma2_rn(w1[8], win[2][sc], a2);
-                const float2 r1 = __fadd2_rn(__fadd2_rn(a0, a1), a2);
-                float2 r2 = make_float2(0.f, 0.f);
-                if (NOUT == 2) {
-                    float2 c0 = __ffma2_rn(w2[0], win[0][sa], b2), c1 = __fmul2_rn(w2[3], win[1][sa]), c2 = __fmul2_rn(w2[6], win[2][sa]);
-                    c0 = __ffma2_rn(w2[1], win[0][sb], c0); c1 = __ffma2_rn(w2[4], win[1][sb], c1); c2 = __ffma2_rn(w2[7], win[2][sb], c2);
-                    c0 = __ffma2_rn(w2[2], win[0][sc], c0); c1 = __ffma2_rn(w2[5], win[1][sc], c1); c2 = __ffma2_rn(w2[8], win[2][sc], c2);
-                    r2 = __fadd2_rn(__fadd2_rn(c0, c1), c2);
-                }
-                store(x, r1, r2, win[1][sb]);
+                wa[0][sc] = *reinterpret_cast<const float2*>(ra0 + (x + 2) * MC);
+                wa[1][sc] = *reinterpret_cast<const float2*>(ra1 + (x + 2) * MC);
+                wa[2][sc] = *reinterpret_cast<const float2*>(ra2 + (x + 2) * MC);
+                wb[0][sc] = *reinterpret_cast<const float2*>(rb0 + (x + 2) * MC);
+                wb[1][sc] = *reinterpret_cast<const float2*>(rb1 + (x + 2) * MC);
+                wb[2][sc] = *reinterpret_cast<const float2*>(rb2 + (x + 2) * MC);
+                const float2 a1 = conv(w1, wa, sa, sb, sc), b1 = conv(w1, wb, sa, sb, sc);
+                float2 a2 = make_float2(0.f, 0.f), b2 = a2;
+                if (NOUT == 2) { a2 = conv(w2, wa, sa, sb, sc); b2 = conv(w2, wb, sa, sb, sc); }
+                store(0, c_lo + x, a1, a2, wa[1][sb]);
+                store(1, c_lo + x, b1, b2, wb[1][sb]);
             }
         }
     }
@@ -259,240 +314,339 @@ __device__ __forceinline__ void x_dw_row(const float* rp0, const float* rp1, con
 template <int K>
 __device__ __forceinline__ void x_d_role(const CreffMmaParams& p, const XSmem& sm, int x0, int ya, int S) {
     using Cf = XCfg<K>;
-    const int lane = threadIdx.x & 31, dw = (threadIdx.x >> 5) - 8;
-    float2 wk[9], wv[9], wq[9];
-#pragma unroll
-    for (int t = 0; t < 9; ++t) {
-        wk[t] = make_float2(__ldg(p.wk + (2 * lane) * 9 + t), __ldg(p.wk + (2 * lane + 1) * 9 + t));
-        wv[t] = make_float2(__ldg(p.wv + (2 * lane) * 9 + t), __ldg(p.wv + (2 * lane + 1) * 9 + t));
-        wq[t] = make_float2(__ldg(p.wq + (2 * lane) * 9 + t), __ldg(p.wq + (2 * lane + 1) * 9 + t));
-    }
-    const float2 bk = make_float2(__ldg(p.bk + 2 * lane), __ldg(p.bk + 2 * lane + 1));
-    const float2 bv = make_float2(__ldg(p.bv + 2 * lane), __ldg(p.bv + 2 * lane + 1));
-    const float2 bq = make_float2(__ldg(p.bq + 2 * lane), __ldg(p.bq + 2 * lane + 1));
+    const int lane = threadIdx.x & 31, d = (threadIdx.x >> 5) - XG_WARPS, third = d % 3, rp = d / 3;
+    constexpr int KV3 = (Cf::KVC + 2) / 3, Q3 = (XSW + 2) / 3;              // columns per third
+    const int kv_lo = third * KV3, kv_n = min(Cf::KVC - kv_lo, KV3);
+    const int q_lo = third * Q3, q_n = min(XSW - q_lo, Q3);
     const float* hring = reinterpret_cast<const float*>(sm.rings) + 2 * lane;
     const float* lring = reinterpret_cast<const float*>(sm.rings + Cf::HR_BYTES) + 2 * lane;
     const int lane_chunk = lane >> 2;
     const uint32_t lane_off = (uint32_t)((lane & 3) * 4);
+    const float2* const swl = sm.s_dw + lane;
 #pragma unroll 1
     for (int t = -1; t <= S; ++t) {
+        XTRACE(1, t, 0);
         xbar_wait(sm.gfull, t);
-        // ---- K/V row kr (relative to image row ya-R) from hr ring rows kr..kr+2 ----
+        XTRACE(1, t, 1);
+        // ---- K/V rows kr, kr+2 (relative to image row ya-R) from hr ring rows kr..kr+2 / kr+2..kr+4 ----
         if (t - Cf::SL >= 0) xbar_wait(sm.cdone, t - Cf::SL);     // the ring rows this step overwrites have been read
-        const int kr = t < 0 ? dw : Cf::P0 + 4 * t + dw;
-        if (t >= 0 || dw < Cf::P0) {
-            const float* rp0 = hring + ((kr) % XHR_RING) * (Cf::HC * MC);
-            const float* rp1 = hring + ((kr + 1) % XHR_RING) * (Cf::HC * MC);
-            const float* rp2 = hring + ((kr + 2) % XHR_RING) * (Cf::HC * MC);
-            const int fy = ya - Cf::R + kr;
-            const bool row_ok = fy >= 0 && fy < p.H;
-            const int pos0 = (kr % Cf::KVR) * Cf::KVC;
+        XTRACE(1, t, 2);
+#ifdef ARSEG_XTRACE
+        if (!(p.dbg & 1))
+#endif
+        if (t >= 0 || rp < Cf::P0) {
+            const int krA = (t < 0 ? 0 : Cf::P0 + 4 * t) + rp, krB = krA + 2;
+            const bool haveB = t >= 0 || rp + 2 < Cf::P0;          // initial step: only P0 rows exist
+            float2 wk[10], wv[10];
+#pragma unroll
+            for (int i = 0; i < 10; ++i) { wk[i] = swl[i * 32]; wv[i] = swl[(10 + i) * 32]; }
+            const float* ra0 = hring + ((krA) % XHR_RING) * (Cf::HC * MC);
+            const float* ra1 = hring + ((krA + 1) % XHR_RING) * (Cf::HC * MC);
+            const float* ra2 = hring + ((krA + 2) % XHR_RING) * (Cf::HC * MC);
+            const float* rb1 = hring + ((krA + 3) % XHR_RING) * (Cf::HC * MC);
+            const float* rb2 = hring + ((krA + 4) % XHR_RING) * (Cf::HC * MC);
+            const int fyA = ya - Cf::R + krA;
+            const bool okA = fyA >= 0 && fyA < p.H, okB = fyA + 2 >= 0 && fyA + 2 < p.H;
+            const int posA = (krA % Cf::KVR) * Cf::KVC, posB = (krB % Cf::KVR) * Cf::KVC;
             const int fx0 = x0 - Cf::R;
-            x_dw_row<2, Cf::HC, Cf::KVC>(rp0, rp1, rp2, wk, bk, wv, bv, [&](int x, float2 a1, float2 a2, float2) {
+            x_dw_rows2<2>(ra0, ra1, ra2, ra2, rb1, rb2, kv_lo, kv_n, wk, wv, [&](int which, int x, float2 a1, float2 a2, float2) {
                 // K / V are exactly 0 outside the image (attention zero padding, model/attention.py:199,207)
                 const int fx = fx0 + x;
-                if (!(row_ok && fx >= 0 && fx < p.W)) { a1 = make_float2(0.f, 0.f); a2 = make_float2(0.f, 0.f); }
-                const uint32_t off = kv_off(pos0 + x, x, lane_chunk) + lane_off;
+                if (!((which ? okB : okA) && fx >= 0 && fx < p.W)) { a1 = make_float2(0.f, 0.f); a2 = make_float2(0.f, 0.f); }
+                if (which && !haveB) return;
+                const uint32_t off = kv_off((which ? posB : posA) + x, x, lane_chunk) + lane_off;
                 *reinterpret_cast<uint32_t*>(sm.sK + off) = pack_h2_sat(a1.x, a1.y);
                 *reinterpret_cast<uint32_t*>(sm.sV + off) = pack_h2_sat(a2.x, a2.y);
             });
         }
-        // ---- Q row qr = 4(t-1)+dw (relative to ya) from lr ring rows qr..qr+2; residual = lr_up centre ----
+        // ---- Q rows qr, qr+2 (qr = 4(t-1)+rp, relative to ya) from the lr ring; residual = lr_up centre ----
+        XTRACE(1, t, 3);
         if (t >= 1) {
-            if (t - 2 >= 0) xbar_wait(sm.qlempty, t - 2);         // C step t-2 has taken Q / residual into registers
-            const int qr = 4 * (t - 1) + dw;
-            const float* rp0 = lring + ((qr) % XLR_RING) * (Cf::LC * MC);
-            const float* rp1 = lring + ((qr + 1) % XLR_RING) * (Cf::LC * MC);
-            const float* rp2 = lring + ((qr + 2) % XLR_RING) * (Cf::LC * MC);
-            x_dw_row<1, Cf::LC, XSW>(rp0, rp1, rp2, wq, bq, wq, bq, [&](int x, float2 a1, float2, float2 centre) {
-                *reinterpret_cast<uint32_t*>(sm.sQ + q_off(dw, x, lane_chunk) + lane_off) = pack_h2_sat(a1.x, a1.y);
-                *reinterpret_cast<float2*>(sm.sRes + (dw * XSW + x) * XRES_LD + 2 * lane) = centre;
-            });
+            xbar_wait(sm.qlempty, t - 2);                         // C step t-2 (-1: prologue) has taken Q / residual into registers
+            XTRACE(1, t, 4);
+#ifdef ARSEG_XTRACE
+            if (!(p.dbg & 1))
+#endif
+            {
+                float2 wq[10];
+#pragma unroll
+                for (int i = 0; i < 10; ++i) wq[i] = swl[(20 + i) * 32];
+                const int qr = 4 * (t - 1) + rp;
+                const float* ra0 = lring + ((qr) % XLR_RING) * (Cf::LC * MC);
+                const float* ra1 = lring + ((qr + 1) % XLR_RING) * (Cf::LC * MC);
+                const float* ra2 = lring + ((qr + 2) % XLR_RING) * (Cf::LC * MC);
+                const float* rb1 = lring + ((qr + 3) % XLR_RING) * (Cf::LC * MC);
+                const float* rb2 = lring + ((qr + 4) % XLR_RING) * (Cf::LC * MC);
+                x_dw_rows2<1>(ra0, ra1, ra2, ra2, rb1, rb2, q_lo, q_n, wq, wq, [&](int which, int x, float2 a1, float2, float2 centre) {
+                    const int row = rp + 2 * which;
+                    *reinterpret_cast<uint32_t*>(sm.sQ + q_off(row, x, lane_chunk) + lane_off) = pack_h2_sat(a1.x, a1.y);
+                    *reinterpret_cast<float2*>(sm.sRes + (row * XSW + x) * XRES_LD + 2 * lane) = centre;
+                });
+            }
         }
         xbar_arrive(sm.ddone, t);
+        XTRACE(1, t, 5);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // C role: attention + classifier for one 4x4 block per warp per step.
 // ---------------------------------------------------------------------------------------------
-template <int K>
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+template <int K, int NCT>
 __device__ __forceinline__ void x_c_role(const CreffMmaParams& p, const XSmem& sm, int n, int x0, int ya, int yb, int S) {
     using Cf = XCfg<K>;
+    constexpr int NT8Q = (Cf::NK + 7) / 8;                // key n-tiles that hold at least one real key
+    constexpr int MW = (2 * NT8Q + 31) / 32;              // 32-bit mask words per query row
     const int lane = threadIdx.x & 31, cw = (threadIdx.x >> 5) - 12;
     const int g = lane >> 2, t = lane & 3, mi = lane >> 3;
-    const int H = p.H, W = p.W;
-    const bool do_cls = p.wcls != nullptr;
-    const int nct = do_cls ? (p.ncls + 7) >> 3 : 0;
-    const size_t plane = (size_t)H * W;
+    const int W = p.W;
+    const size_t plane = (size_t)p.H * W;
 
-    // validity masks of this thread's logits: rows g (m0) and g+8 (m1), keys 8j+2t+e -> bit 2j+e
-    uint64_t m0 = 0, m1 = 0;
+    // validity of this thread's logits: rows g (mA) and g+8 (mB), keys 8j+2t+e -> bit 2j+e.  An invalid logit
+    // (outside the k x k window of its query, or a padding key) starts its accumulator at -inf instead of 0, so
+    // the MMA result is already masked and the softmax needs no selects (ex2(-inf) = 0).
+    uint32_t mA[MW], mB[MW];
+#pragma unroll
+    for (int w = 0; w < MW; ++w) mA[w] = mB[w] = 0u;
     {
         const int qy0 = g >> 2, qx0 = g & 3, qy1 = qy0 + 2;
 #pragma unroll
-        for (int j = 0; j < Cf::NT8; ++j)
+        for (int j = 0; j < NT8Q; ++j)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int nk = 8 * j + 2 * t + e;
                 const int ky = nk / Cf::WN, kx = nk % Cf::WN;
                 const bool okx = nk < Cf::NK && (unsigned)(kx - qx0) < (unsigned)K;
-                if (okx && (unsigned)(ky - qy0) < (unsigned)K) m0 |= 1ull << (2 * j + e);
-                if (okx && (unsigned)(ky - qy1) < (unsigned)K) m1 |= 1ull << (2 * j + e);
+                if (okx && (unsigned)(ky - qy0) < (unsigned)K) mA[(2 * j + e) >> 5] |= 1u << ((2 * j + e) & 31);
+                if (okx && (unsigned)(ky - qy1) < (unsigned)K) mB[(2 * j + e) >> 5] |= 1u << ((2 * j + e) & 31);
             }
     }
-    const uint32_t kb = s_u32(sm.sK), vb = s_u32(sm.sV), qb = s_u32(sm.sQ);
+    // ldmatrix row addresses: key row ky and the column part of the byte offset, per n-tile (QK: 8 keys per tile,
+    // lanes 0-7 of each address group; PV: 16 keys per tile).  ky of a lane is kyq_lo[j] or kyq_lo[j]+1 (compile-time
+    // kyq_lo), selected per lane by a bit of kyq_hi; the ring slot of a key row changes every step.
+    uint32_t cq[NT8Q], cv[Cf::NT16];
+    uint32_t kyq_hi = 0, kyv_hi = 0;
+#pragma unroll
+    for (int j = 0; j < NT8Q; ++j) {
+        int nk = 8 * j + (lane & 7);
+        nk = nk < Cf::NK ? nk : Cf::NK - 1;
+        const int ky = nk / Cf::WN, kx = nk - ky * Cf::WN, col = 4 * cw + kx;
+        if (ky != (8 * j) / Cf::WN) kyq_hi |= 1u << j;
+        cq[j] = (uint32_t)(col * 128 + (((mi ^ col) & 7) << 4));             // chunk mi; chunk 4+mi = ^ 64
+    }
+#pragma unroll
+    for (int i = 0; i < Cf::NT16; ++i) {
+        int nk = 16 * i + ((mi & 1) << 3) + (lane & 7);
+        nk = nk < Cf::NK ? nk : Cf::NK - 1;
+        const int ky = nk / Cf::WN, kx = nk - ky * Cf::WN, col = 4 * cw + kx;
+        const int ky_lo = (16 * i < Cf::NK ? 16 * i : Cf::NK - 1) / Cf::WN;
+        kyv_hi |= (uint32_t)(ky - ky_lo) << (2 * i);                           // 0..3
+        cv[i] = (uint32_t)(col * 128 + ((((mi >> 1) ^ col) & 7) << 4));        // chunk (mi>>1) + 2cp = ^ (cp << 5)
+    }
+    // classifier B fragments (final_conv weights, f16) and biases stay in registers for the whole march
+    constexpr int NCTA = NCT > 0 ? NCT : 1;
+    uint32_t wf[NCTA][4][2];
+    float bcl[NCTA][2];
+#pragma unroll
+    for (int nt = 0; nt < NCT; ++nt) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            const __half* wp = sm.s_wc + (8 * nt + g) * XCLS_LD + 16 * ks + 2 * t;
+            wf[nt][ks][0] = *reinterpret_cast<const uint32_t*>(wp);
+            wf[nt][ks][1] = *reinterpret_cast<const uint32_t*>(wp + 8);
+        }
+#pragma unroll
+        for (int e = 0; e < 2; ++e) bcl[nt][e] = 8 * nt + 2 * t + e < p.ncls ? sm.s_bc[8 * nt + 2 * t + e] : -INFINITY;   // padding classes: -inf
+    }
+    const uint32_t kb = s_u32(sm.sK), vb = s_u32(sm.sV);
+    uint32_t qaddr[4];
+    {
+        const int r = ((mi & 1) << 3) + (lane & 7);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) qaddr[ks] = s_u32(sm.sQ) + q_off(r >> 2, 4 * cw + (r & 3), 2 * ks + (mi >> 1));
+    }
+    const float* const resa = sm.sRes + ((g >> 2) * XSW + 4 * cw + (g & 3)) * XRES_LD + 2 * t;
     const int pxA = x0 + 4 * cw + (g & 3);
+    // output offsets of pixel A (block row g>>2) at step 0; pixel B is 2 rows below; each step advances 4 rows
+    size_t offA = (size_t)(ya + (g >> 2)) * W + pxA;
+    float* const ol = p.out_logits ? p.out_logits + (size_t)n * p.ncls * plane + (size_t)(2 * t) * plane : nullptr;
+    float* const op = p.out_p ? p.out_p + (size_t)n * MC * plane + (size_t)(2 * t) * plane : nullptr;
+    uint8_t* const oa = p.out_argmax ? p.out_argmax + (size_t)n * plane : nullptr;
     int s4 = 0;                                           // (4 s) mod KVR
     // the mbarrier phase of a step is (step+1)/XNB: C has no step -1, so arrive for it once (nobody waits on it)
     xbar_arrive(sm.cdone, -1);
     xbar_arrive(sm.qlempty, -1);
 #pragma unroll 1
-    for (int s = 0; s < S; ++s) {
-        xbar_wait(sm.ddone, s + 1);
-        // ---------------- Q fragments ----------------
-        uint32_t qa[4][4];
-        {
-            const int r = ((mi & 1) << 3) + (lane & 7);
+    for (int s = 0; s < S; ++s, offA += 4 * (size_t)W) {
+        // byte offsets of the K/V ring rows of this step's key rows
+        uint32_t rowb[Cf::WN];
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) ldsm_x4(qa[ks], qb + q_off(r >> 2, 4 * cw + (r & 3), 2 * ks + (mi >> 1)));
-        }
-        // ---------------- S = Q K^T (model/attention.py:199) ----------------
-        float Sx[Cf::NT8][4];
-#pragma unroll
-        for (int j = 0; j < Cf::NT8; ++j) {
-            Sx[j][0] = Sx[j][1] = Sx[j][2] = Sx[j][3] = 0.f;
-            int nk = 8 * j + (lane & 7);
-            nk = nk < Cf::NK ? nk : Cf::NK - 1;
-            const int ky = nk / Cf::WN, kx = nk - ky * Cf::WN;
+        for (int ky = 0; ky < Cf::WN; ++ky) {
             int slot = s4 + ky;
             slot = slot >= Cf::KVR ? slot - Cf::KVR : slot;
-            const int col = 4 * cw + kx, pos = slot * Cf::KVC + col;
-            uint32_t b0[4], b1[4];
-            ldsm_x4(b0, kb + kv_off(pos, col, mi));
-            ldsm_x4(b1, kb + kv_off(pos, col, 4 + mi));
-            mma16816(Sx[j], qa[0], b0[0], b0[1]);
-            mma16816(Sx[j], qa[1], b0[2], b0[3]);
-            mma16816(Sx[j], qa[2], b1[0], b1[1]);
-            mma16816(Sx[j], qa[3], b1[2], b1[3]);
+            rowb[ky] = (uint32_t)(slot * (Cf::KVC * 128));
         }
-        // ---------------- residual lr_up (model/attention.py:191,210) into the O accumulators ----------------
-        // thread (g,t): pixels A = block row g>>2, B = A + 2 rows; channels 8c+2t, 8c+2t+1
-        float O[8][4];
+        XTRACE(2, s, 0);
+        xbar_wait(sm.ddone, s + 1);
+        XTRACE(2, s, 1);
+#ifdef ARSEG_XTRACE
+        if (p.dbg & 2) { xbar_arrive(sm.qlempty, s); xbar_arrive(sm.cdone, s); continue; }
+#endif
+        // ---------------- S = Q K^T (model/attention.py:199) ----------------
+        // n-tiles in groups of XQG with the k-step loop outside: XQG independent accumulator chains in flight
+        float Sx[NT8Q][4];
         {
-            const float* ra = sm.sRes + ((g >> 2) * XSW + 4 * cw + (g & 3)) * XRES_LD + 2 * t;
-            const float* rb = ra + 2 * XSW * XRES_LD;
+            uint32_t qa[4][4];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float2 a = *reinterpret_cast<const float2*>(ra + 8 * c), b = *reinterpret_cast<const float2*>(rb + 8 * c);
-                O[c][0] = a.x; O[c][1] = a.y; O[c][2] = b.x; O[c][3] = b.y;
+            for (int ks = 0; ks < 4; ++ks) ldsm_x4(qa[ks], qaddr[ks]);
+#pragma unroll
+            for (int jg = 0; jg < NT8Q; jg += XQG) {
+                uint32_t bf[XQG][2][4];
+#pragma unroll
+                for (int jj = 0; jj < XQG; ++jj) {
+                    const int j = jg + jj;
+                    if (j < NT8Q) {
+                        constexpr int dummy = 0; (void)dummy;
+                        const int ky_lo = (8 * j) / Cf::WN;
+                        const uint32_t rb = ((kyq_hi >> j) & 1u) ? rowb[ky_lo + 1 < Cf::WN ? ky_lo + 1 : ky_lo] : rowb[ky_lo];
+                        const uint32_t a0 = kb + rb + cq[j];
+                        ldsm_x4(bf[jj][0], a0);
+                        ldsm_x4(bf[jj][1], a0 ^ 64u);
+                        const int b0 = 2 * j, b1 = 2 * j + 1;
+                        Sx[j][0] = (mA[b0 >> 5] >> (b0 & 31)) & 1u ? 0.f : -INFINITY;
+                        Sx[j][1] = (mA[b1 >> 5] >> (b1 & 31)) & 1u ? 0.f : -INFINITY;
+                        Sx[j][2] = (mB[b0 >> 5] >> (b0 & 31)) & 1u ? 0.f : -INFINITY;
+                        Sx[j][3] = (mB[b1 >> 5] >> (b1 & 31)) & 1u ? 0.f : -INFINITY;
+                    }
+                }
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+                    for (int jj = 0; jj < XQG; ++jj)
+                        if (jg + jj < NT8Q) mma16816(Sx[jg + jj], qa[ks], bf[jj][ks >> 1][2 * (ks & 1)], bf[jj][ks >> 1][2 * (ks & 1) + 1]);
             }
+        }
+        // ---------------- residual lr_up (model/attention.py:191,210), kept in registers until the end ----------
+        // thread (g,t): pixels A = block row g>>2, B = A + 2 rows; channels 8c+2t, 8c+2t+1
+        float2 resA[8], resB[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            resA[c] = *reinterpret_cast<const float2*>(resa + 8 * c);
+            resB[c] = *reinterpret_cast<const float2*>(resa + 2 * XSW * XRES_LD + 8 * c);
         }
         xbar_arrive(sm.qlempty, s);
+        XTRACE(2, s, 2);
         // ---------------- softmax over the k*k window of every query (model/attention.py:203) ----------------
-        float mx0 = -INFINITY, mx1 = -INFINITY;
+        float mx0, mx1;
+        {
+            float a[NT8Q], b[NT8Q];
 #pragma unroll
-        for (int j = 0; j < Cf::NT8; ++j)
+            for (int j = 0; j < NT8Q; ++j) { a[j] = fmaxf(Sx[j][0], Sx[j][1]); b[j] = fmaxf(Sx[j][2], Sx[j][3]); }
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                if ((m0 >> (2 * j + e)) & 1) mx0 = fmaxf(mx0, Sx[j][e]);
-                if ((m1 >> (2 * j + e)) & 1) mx1 = fmaxf(mx1, Sx[j][2 + e]);
-            }
+            for (int w = 1; w < NT8Q; w <<= 1)
+#pragma unroll
+                for (int j = 0; j + w < NT8Q; j += 2 * w) { a[j] = fmaxf(a[j], a[j + w]); b[j] = fmaxf(b[j], b[j + w]); }
+            mx0 = a[0]; mx1 = b[0];
+        }
         mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
         mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
         constexpr float LOG2E = 1.4426950408889634f;
         const float o0 = mx0 * LOG2E, o1 = mx1 * LOG2E;
-        float sum0 = 0.f, sum1 = 0.f;
+        // un-normalised P in f16 (A fragments of P V); the row sums come out of the P V MMAs (ones column below)
+        uint32_t pa[Cf::NT16][4];
 #pragma unroll
-        for (int j = 0; j < Cf::NT8; ++j)
+        for (int i = 0; i < Cf::NT16; ++i)
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const float p0 = ((m0 >> (2 * j + e)) & 1) ? exp2f(fmaf(Sx[j][e], LOG2E, -o0)) : 0.f;
-                const float p1 = ((m1 >> (2 * j + e)) & 1) ? exp2f(fmaf(Sx[j][2 + e], LOG2E, -o1)) : 0.f;
-                sum0 += p0; sum1 += p1;
-                Sx[j][e] = p0; Sx[j][2 + e] = p1;
+            for (int h = 0; h < 2; ++h) {
+                const int j = 2 * i + h;
+                if (j < NT8Q) {
+                    pa[i][2 * h] = pack_h2(ex2_approx(fmaf(Sx[j][0], LOG2E, -o0)), ex2_approx(fmaf(Sx[j][1], LOG2E, -o0)));
+                    pa[i][2 * h + 1] = pack_h2(ex2_approx(fmaf(Sx[j][2], LOG2E, -o1)), ex2_approx(fmaf(Sx[j][3], LOG2E, -o1)));
+                } else {
+                    pa[i][2 * h] = 0u; pa[i][2 * h + 1] = 0u;
+                }
             }
-        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
-        sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
-        const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
-        // ---------------- O = resid * sum + P V (model/attention.py:207); P un-normalised f16, 1/sum in fp32 --------
+        XTRACE(2, s, 3);
+        // ---------------- O = P V (model/attention.py:207); row sums = P . 1 on the same tensor pipe ----------------
+        float O[8][4], Ssum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int c = 0; c < 8; ++c) { O[c][0] *= sum0; O[c][1] *= sum0; O[c][2] *= sum1; O[c][3] *= sum1; }
+        for (int c = 0; c < 8; ++c) O[c][0] = O[c][1] = O[c][2] = O[c][3] = 0.f;
 #pragma unroll
         for (int i = 0; i < Cf::NT16; ++i) {
-            uint32_t pa[4];
-            pa[0] = pack_h2(Sx[2 * i][0], Sx[2 * i][1]);
-            pa[1] = pack_h2(Sx[2 * i][2], Sx[2 * i][3]);
-            pa[2] = pack_h2(Sx[2 * i + 1][0], Sx[2 * i + 1][1]);
-            pa[3] = pack_h2(Sx[2 * i + 1][2], Sx[2 * i + 1][3]);
-            int nk = 16 * i + ((mi & 1) << 3) + (lane & 7);
-            nk = nk < Cf::NK ? nk : Cf::NK - 1;
-            const int ky = nk / Cf::WN, kx = nk - ky * Cf::WN;
-            int slot = s4 + ky;
-            slot = slot >= Cf::KVR ? slot - Cf::KVR : slot;
-            const int col = 4 * cw + kx, pos = slot * Cf::KVC + col;
+            const int ky_lo = (16 * i < Cf::NK ? 16 * i : Cf::NK - 1) / Cf::WN;
+            const uint32_t sel = (kyv_hi >> (2 * i)) & 3u;
+            const uint32_t r0 = rowb[ky_lo], r1 = rowb[ky_lo + 1 < Cf::WN ? ky_lo + 1 : ky_lo], r2 = rowb[ky_lo + 2 < Cf::WN ? ky_lo + 2 : ky_lo];
+            uint32_t rsel = sel == 0 ? r0 : (sel == 1 ? r1 : r2);
+            if (Cf::WN < 7) rsel = sel == 3 ? rowb[ky_lo + 3 < Cf::WN ? ky_lo + 3 : ky_lo] : rsel;   // 16 keys span up to 4 rows when WN = 6
+            const uint32_t a0 = vb + rsel + cv[i];
 #pragma unroll
             for (int cp = 0; cp < 4; ++cp) {
                 uint32_t v[4];
-                ldsm_x4_t(v, vb + kv_off(pos, col, 2 * cp + (mi >> 1)));
-                mma16816(O[2 * cp], pa, v[0], v[1]);
-                mma16816(O[2 * cp + 1], pa, v[2], v[3]);
+                ldsm_x4_t(v, a0 ^ (uint32_t)(cp << 5));
+                mma16816(O[2 * cp], pa[i], v[0], v[1]);
+                mma16816(O[2 * cp + 1], pa[i], v[2], v[3]);
             }
+            mma16816(Ssum, pa[i], 0x3C003C00u, 0x3C003C00u);      // B = all ones (f16): every column = row sum of P
         }
         xbar_arrive(sm.cdone, s);
+        XTRACE(2, s, 4);
         s4 += 4; s4 = s4 >= Cf::KVR ? s4 - Cf::KVR : s4;
+        // fused = lr_up + O / sum (model/attention.py:210); the sum is that of the f16-rounded P the MMA consumed
+        {
+            const float inv0 = rcp_approx(Ssum[0]), inv1 = rcp_approx(Ssum[2]);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) { O[c][0] *= inv0; O[c][1] *= inv0; O[c][2] *= inv1; O[c][3] *= inv1; }
-
-        const int pyA = ya + 4 * s + (g >> 2), pyB = pyA + 2;
-        const bool okA = pyA < yb && pxA < W, okB = pyB < yb && pxA < W;
-        if (p.out_p) {
+            for (int c = 0; c < 8; ++c) {
+                O[c][0] = fmaf(O[c][0], inv0, resA[c].x); O[c][1] = fmaf(O[c][1], inv0, resA[c].y);
+                O[c][2] = fmaf(O[c][2], inv1, resB[c].x); O[c][3] = fmaf(O[c][3], inv1, resB[c].y);
+            }
+        }
+        const int pyA = ya + 4 * s + (g >> 2);
+        const bool okA = pyA < yb && pxA < W, okB = pyA + 2 < yb && pxA < W;
+        const size_t offB = offA + 2 * (size_t)W;
+        if (op) {
 #pragma unroll
             for (int c = 0; c < 8; ++c)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    float* op = p.out_p + ((size_t)n * MC + 8 * c + 2 * t + e) * plane;
-                    if (okA) op[(size_t)pyA * W + pxA] = O[c][e];
-                    if (okB) op[(size_t)pyB * W + pxA] = O[c][2 + e];
+                    float* o = op + (size_t)(8 * c + e) * plane;
+                    if (okA) o[offA] = O[c][e];
+                    if (okB) o[offB] = O[c][2 + e];
                 }
         }
-        if (!do_cls) continue;
+        XTRACE(2, s, 5);
+        if (NCT == 0) continue;
 
-        // ---------------- classifier (model/pspnet.py:226) as a [16 x 64] x [64 x 8*nct] MMA ----------------
-        uint32_t fa[4][4];
+        // ---------------- classifier (model/pspnet.py:226) as a [16 x 64] x [64 x 8*NCT] MMA ----------------
+        float Lg[NCT > 0 ? NCT : 1][4];
+        {
+            uint32_t fa[4][4];
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-            fa[ks][0] = pack_h2_sat(O[2 * ks][0], O[2 * ks][1]);
-            fa[ks][1] = pack_h2_sat(O[2 * ks][2], O[2 * ks][3]);
-            fa[ks][2] = pack_h2_sat(O[2 * ks + 1][0], O[2 * ks + 1][1]);
-            fa[ks][3] = pack_h2_sat(O[2 * ks + 1][2], O[2 * ks + 1][3]);
-        }
-        float Lg[4][4];
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-            Lg[nt][0] = Lg[nt][1] = Lg[nt][2] = Lg[nt][3] = 0.f;
-            if (nt < nct) {
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    const __half* wp = sm.s_wc + (8 * nt + g) * XCLS_LD + 16 * ks + 2 * t;
-                    mma16816(Lg[nt], fa[ks], *reinterpret_cast<const uint32_t*>(wp), *reinterpret_cast<const uint32_t*>(wp + 8));
-                }
+            for (int ks = 0; ks < 4; ++ks) {
+                fa[ks][0] = pack_h2_sat(O[2 * ks][0], O[2 * ks][1]);
+                fa[ks][1] = pack_h2_sat(O[2 * ks][2], O[2 * ks][3]);
+                fa[ks][2] = pack_h2_sat(O[2 * ks + 1][0], O[2 * ks + 1][1]);
+                fa[ks][3] = pack_h2_sat(O[2 * ks + 1][2], O[2 * ks + 1][3]);
             }
+#pragma unroll
+            for (int nt = 0; nt < NCT; ++nt) { Lg[nt][0] = Lg[nt][2] = bcl[nt][0]; Lg[nt][1] = Lg[nt][3] = bcl[nt][1]; }
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+                for (int nt = 0; nt < NCT; ++nt) mma16816(Lg[nt], fa[ks], wf[nt][ks][0], wf[nt][ks][1]);
         }
-        // bias, argmax (first maximum, like torch.argmax) and log-softmax per pixel: values of one pixel live in a quad
+        // argmax (first maximum, like torch.argmax) and log-softmax per pixel: the values of one pixel live in a quad
         float lmax0 = -INFINITY, lmax1 = -INFINITY;
         int am0 = 0, am1 = 0;
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
+        for (int nt = 0; nt < NCT; ++nt)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int cls = 8 * nt + 2 * t + e;
-                if (nt < nct && cls < p.ncls) {
-                    const float bc = sm.s_bc[cls];
-                    Lg[nt][e] += bc; Lg[nt][2 + e] += bc;
-                    if (Lg[nt][e] > lmax0) { lmax0 = Lg[nt][e]; am0 = cls; }
-                    if (Lg[nt][2 + e] > lmax1) { lmax1 = Lg[nt][2 + e]; am1 = cls; }
-                }
+                if (Lg[nt][e] > lmax0) { lmax0 = Lg[nt][e]; am0 = cls; }
+                if (Lg[nt][2 + e] > lmax1) { lmax1 = Lg[nt][2 + e]; am1 = cls; }
             }
 #pragma unroll
         for (int d = 1; d <= 2; d <<= 1) {
@@ -503,42 +657,43 @@ __device__ __forceinline__ void x_c_role(const CreffMmaParams& p, const XSmem& s
         }
         float lse0 = 0.f, lse1 = 0.f;
         if (p.log_softmax) {
+            const float q0 = lmax0 * LOG2E, q1 = lmax1 * LOG2E;
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt)
+            for (int nt = 0; nt < NCT; ++nt)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const int cls = 8 * nt + 2 * t + e;
-                    if (nt < nct && cls < p.ncls) { lse0 += expf(Lg[nt][e] - lmax0); lse1 += expf(Lg[nt][2 + e] - lmax1); }
+                    lse0 += ex2_approx(fmaf(Lg[nt][e], LOG2E, -q0));          // padding classes: ex2(-inf) = 0
+                    lse1 += ex2_approx(fmaf(Lg[nt][2 + e], LOG2E, -q1));
                 }
             lse0 += __shfl_xor_sync(0xffffffffu, lse0, 1); lse0 += __shfl_xor_sync(0xffffffffu, lse0, 2);
             lse1 += __shfl_xor_sync(0xffffffffu, lse1, 1); lse1 += __shfl_xor_sync(0xffffffffu, lse1, 2);
-            lse0 = logf(lse0) + lmax0; lse1 = logf(lse1) + lmax1;
+            lse0 = __logf(lse0) + lmax0; lse1 = __logf(lse1) + lmax1;
         }
-        if (p.out_logits) {
-            float* ol = p.out_logits + (size_t)n * p.ncls * plane;
+        XTRACE(2, s, 6);
+        if (ol) {
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt)
+            for (int nt = 0; nt < NCT; ++nt)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const int cls = 8 * nt + 2 * t + e;
-                    if (nt < nct && cls < p.ncls) {
-                        if (okA) ol[cls * plane + (size_t)pyA * W + pxA] = Lg[nt][e] - lse0;
-                        if (okB) ol[cls * plane + (size_t)pyB * W + pxA] = Lg[nt][2 + e] - lse1;
+                    if (8 * nt + 2 * t + e < p.ncls) {
+                        float* o = ol + (size_t)(8 * nt + e) * plane;
+                        if (okA) o[offA] = Lg[nt][e] - lse0;
+                        if (okB) o[offB] = Lg[nt][2 + e] - lse1;
                     }
                 }
         }
-        if (p.out_argmax && t == 0) {
-            uint8_t* oa = p.out_argmax + (size_t)n * plane;
-            if (okA) oa[(size_t)pyA * W + pxA] = (uint8_t)am0;
-            if (okB) oa[(size_t)pyB * W + pxA] = (uint8_t)am1;
+        if (oa && t == 0) {
+            if (okA) oa[offA] = (uint8_t)am0;
+            if (okB) oa[offB] = (uint8_t)am1;
         }
+        XTRACE(2, s, 7);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
-template <int K, typename TLR>
+template <int K, typename TLR, int NCT>
 __global__ void __launch_bounds__(XTHREADS, 1) creff_march_kernel(CreffMmaParams p) {
     using Cf = XCfg<K>;
     extern __shared__ __align__(1024) uint8_t xsm[];
@@ -546,13 +701,16 @@ __global__ void __launch_bounds__(XTHREADS, 1) creff_march_kernel(CreffMmaParams
     sm.sK = xsm;
     sm.sV = sm.sK + Cf::KV_BYTES;
     sm.rings = sm.sV + Cf::KV_BYTES;                                        // hr ring, then lr ring
-    sm.sQ = sm.rings + Cf::HR_BYTES + Cf::LR_BYTES;
+    sm.sQ = sm.rings + Cf::HR_BYTES + Cf::LR_BYTES + Cf::SCRATCH_BYTES;
     sm.sRes = reinterpret_cast<float*>(sm.sQ + Cf::Q_BYTES);
     sm.posw = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(sm.sRes) + Cf::RES_BYTES);
-    sm.posid = reinterpret_cast<int2*>(sm.posw + 2 * Cf::PMAX);
-    sm.s_wc = reinterpret_cast<__half*>(sm.posid + 2 * Cf::PMAX);           // [32][XCLS_LD]
+    sm.posid = reinterpret_cast<int2*>(sm.posw + Cf::PMAX);
+    // classifier weights are staged in the Q tile: C moves them to registers in its prologue, and D's first Q write
+    // (step 1) waits for C's prologue arrival on qlempty(-1)
+    sm.s_wc = reinterpret_cast<__half*>(sm.sQ);                             // [32][XCLS_LD]
     sm.s_bc = reinterpret_cast<float*>(sm.s_wc + 32 * XCLS_LD);             // [32]
-    sm.gfull = reinterpret_cast<uint64_t*>(sm.s_bc + 32);
+    sm.s_dw = reinterpret_cast<float2*>(sm.posid + Cf::PMAX);
+    sm.gfull = reinterpret_cast<uint64_t*>(sm.s_dw + 3 * 10 * 32);
     sm.ddone = sm.gfull + XNB;
     sm.cdone = sm.ddone + XNB;
     sm.qlempty = sm.cdone + XNB;
@@ -575,6 +733,12 @@ __global__ void __launch_bounds__(XTHREADS, 1) creff_march_kernel(CreffMmaParams
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    for (int i = tid; i < 3 * 10 * 32; i += XTHREADS) {
+        const int cv = i / 320, tp = (i / 32) % 10, ln = i % 32;
+        const float* w = cv == 0 ? p.wk : (cv == 1 ? p.wv : p.wq);
+        const float* b = cv == 0 ? p.bk : (cv == 1 ? p.bv : p.bq);
+        sm.s_dw[i] = tp < 9 ? make_float2(__ldg(w + (2 * ln) * 9 + tp), __ldg(w + (2 * ln + 1) * 9 + tp)) : make_float2(__ldg(b + 2 * ln), __ldg(b + 2 * ln + 1));
+    }
     if (p.wcls) {
         for (int i = tid; i < 32 * MC; i += XTHREADS) {
             const int j = i / MC, c = i % MC;
@@ -584,23 +748,30 @@ __global__ void __launch_bounds__(XTHREADS, 1) creff_march_kernel(CreffMmaParams
     }
     __syncthreads();
 
-    if (warp < 8) x_g_role<K, TLR>(p, sm, n, x0, ya, S);
-    else if (warp < 12) x_d_role<K>(p, sm, x0, ya, S);
-    else x_c_role<K>(p, sm, n, x0, ya, yb, S);
+    // register file re-balance (warpgroup-aligned): the kernel starts with 128 per thread; G and D give 16 each to C
+    if (warp < XG_WARPS + XD_WARPS) asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
+    if (warp < XG_WARPS) x_g_role<K, TLR>(p, sm, n, x0, ya, S);
+    else if (warp < XG_WARPS + XD_WARPS) x_d_role<K>(p, sm, x0, ya, S);
+    else x_c_role<K, NCT>(p, sm, n, x0, ya, yb, S);
 }
 
-template <int K, typename TLR>
-static int creff_march_launch_t(CreffMmaParams& p, cudaStream_t st) {
+template <int K, typename TLR, int NCT>
+static int creff_march_launch_n(CreffMmaParams& p, cudaStream_t st) {
     using Cf = XCfg<K>;
-    auto kern = creff_march_kernel<K, TLR>;
+    auto kern = creff_march_kernel<K, TLR, NCT>;
     static bool configured[64] = {false};
     int dev = 0;
     ARSEG_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !configured[dev]) {
         ARSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cf::SMEM));
+        // keep what is left of the 228 KB as L1: the gather's memory-level parallelism is bounded by the L1 lines
+        // its outstanding misses can allocate
+        ARSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)((Cf::SMEM + 1024) * 100 / (228 * 1024)) + 1));
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     p.ncols = ceil_div(p.W, XSW);
+    { const char* d = getenv("ARSEG_CREFF_DBG"); p.dbg = d ? atoi(d) : 0; }
     // row segments: enough CTAs for >= ~6 waves of one-CTA-per-SM, but segments of >= 48 rows (each segment pays
     // ~K+5 redundant halo rows and a 3-step pipeline fill)
     const int sms = sm_count() > 0 ? sm_count() : 148;
@@ -617,6 +788,14 @@ static int creff_march_launch_t(CreffMmaParams& p, cudaStream_t st) {
     return ARSEG_OK;
 }
 
+// classifier n-tiles held in registers: none, <= 16 classes (CamVid 12), <= 32 classes (Cityscapes 19)
+template <int K, typename TLR>
+static int creff_march_launch_t(CreffMmaParams& p, cudaStream_t st) {
+    if (!p.wcls) return creff_march_launch_n<K, TLR, 0>(p, st);
+    if (p.ncls <= 16) return creff_march_launch_n<K, TLR, 2>(p, st);
+    return creff_march_launch_n<K, TLR, 4>(p, st);
+}
+
 int creff_march_launch(CreffMmaParams& p, int k, bool lr_bf16, cudaStream_t st) {
     switch (k) {
         case 3: return lr_bf16 ? creff_march_launch_t<3, __nv_bfloat16>(p, st) : creff_march_launch_t<3, float>(p, st);
@@ -628,3 +807,11 @@ int creff_march_launch(CreffMmaParams& p, int k, bool lr_bf16, cudaStream_t st) 
 }
 
 }  // namespace arseg
+
+#ifdef ARSEG_XTRACE
+extern "C" int arseg_debug_creff_trace(long long* host, int cap) {
+    const int n = cap < arseg::XTRACE_N ? cap : arseg::XTRACE_N;
+    cudaMemcpyFromSymbol(host, arseg::g_xtrace, sizeof(long long) * n);
+    return n;
+}
+#endif

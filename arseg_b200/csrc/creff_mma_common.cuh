@@ -19,6 +19,7 @@ struct CreffMmaParams {
     int N, C, H, W;
     int tiles_x, tiles_y;
     int seg_rows, ncols, nseg;   // column-marching engine: rows per segment, column strips, segments
+    int dbg;                     // ARSEG_XTRACE builds only: bit 0 = D skips its convolutions, bit 1 = C skips its math, bit 2 = G skips loads
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -87,14 +88,29 @@ __device__ __forceinline__ void mflow_at(const CreffMmaParams& p, int n, int fy,
 struct PosRec { float4 w; int info; };
 
 // warped-hr sample (evaluation.py:61-87) at feature pixel (fy,fx); zero outside the image (depthwise padding)
-__device__ __forceinline__ PosRec pos_hr(const CreffMmaParams& p, int n, int fy, int fx) {
+// rcp_w / rcp_h > 0: 2/(W-1), 2/(H-1) in f64 -- the grid normalisation (evaluation.py:80-81) is then a multiply
+// instead of an f64 divide (differs from the divide by <= 1 ulp of f64 BEFORE the cast to fp32, evaluation.py:83)
+// mv_raw != nullptr: the position's MV was loaded by the caller (int16 quarter-pel pair at feature resolution).
+__device__ __forceinline__ PosRec pos_hr(const CreffMmaParams& p, int n, int fy, int fx, double rcp_w = 0.0, double rcp_h = 0.0,
+                                         const int* mv_raw = nullptr) {
     PosRec r; r.w = make_float4(0.f, 0.f, 0.f, 0.f); r.info = -1;
     if (fy < 0 || fy >= p.H || fx < 0 || fx >= p.W) return r;
     float ix = (float)fx, iy = (float)fy;
     if (p.flow) {
         double u, v;
-        mflow_at(p, n, fy, fx, u, v);
-        warp_source_pos(fx, fy, u, v, p.W, p.H, ix, iy);
+        if (mv_raw) {   // dataset/camvid.py:625: int16 / 4.0; evaluation.py:177: * Hf/Hm (= 1 here)
+            u = (double)(short)(*mv_raw & 0xffff) / 4.0;
+            v = (double)(short)(*mv_raw >> 16) / 4.0;
+        } else {
+            mflow_at(p, n, fy, fx, u, v);
+        }
+        if (rcp_w > 0.0) {
+            const float gx = (float)(((double)(float)fx + u) * rcp_w - 1.0), gy = (float)(((double)(float)fy + v) * rcp_h - 1.0);
+            ix = ((gx + 1.f) * (float)p.W - 1.f) / 2.f;
+            iy = ((gy + 1.f) * (float)p.H - 1.f) / 2.f;
+        } else {
+            warp_source_pos(fx, fy, u, v, p.W, p.H, ix, iy);
+        }
     }
     if (!(ix > -1.5f && ix < (float)p.W + 0.5f && iy > -1.5f && iy < (float)p.H + 0.5f)) return r;  // all taps outside
     const float fxn = floorf(ix), fyn = floorf(iy);

@@ -23,10 +23,13 @@ def main():
     ap.add_argument("--engine", default="mma")
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--want-p", action="store_true")
+    ap.add_argument("--H", type=int, default=720)
+    ap.add_argument("--W", type=int, default=960)
+    ap.add_argument("--no-flush", action="store_true")
     a = ap.parse_args()
     torch.set_grad_enabled(False)
     dev = "cuda:0"
-    C, H, W, ncls = 64, 720, 960, 12
+    C, H, W, ncls = 64, a.H, a.W, 12
     h, w = int(H * a.scale), int(W * a.scale)
     hr = synth.synth_feature(1, C, H, W, 1).to(dev) * 0.5
     lr = synth.synth_feature(a.frames, C, h, w, 2).to(dev) * 0.5
@@ -44,7 +47,8 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     times = []
     for it in range(a.iters):
-        flush.zero_()
+        if not a.no_flush:
+            flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         ops.creff_fused(hr_in, lr_nhwc, *ws, a.k, flow=mv, wcls=wcls, bcls=bcls, log_softmax=True, lr_layout=L.NHWC,
