@@ -81,22 +81,20 @@ __device__ __forceinline__ void xbar_arrive(uint64_t* bars, int step) {
 __device__ __forceinline__ void xbar_wait(uint64_t* bars, int step) {
     const uint32_t addr = s_u32(bars + ((step + 1) & (XNB - 1)));
     const uint32_t parity = (uint32_t)(((step + 1) / XNB) & 1);
-    uint32_t ok = 0;
-    long long t0 = 0;
-    for (int spin = 0; !ok; ++spin) {
+    uint32_t ok;
+    // try_wait suspends the thread in hardware until the phase completes or a time limit expires; the poll loop is
+    // kept minimal (a spinning warp takes issue slots from the working roles) and bounded (a protocol bug must trap,
+    // not hang the GPU box)
+    for (int spin = 0; spin < (1 << 22); ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok) : "r"(addr), "r"(parity), "r"(2000u) : "memory");
-        if (!ok && (spin & 1023) == 1023) {          // bounded: a protocol bug must not hang the GPU box
-            if (t0 == 0) t0 = clock64();
-            else if (clock64() - t0 > 4000000000LL) {
-                printf("arseg creff_march: mbarrier wait timed out (block %d thread %d step %d)\n", (int)blockIdx.x, (int)threadIdx.x, step);
-                __trap();
-            }
-        }
+            : "=r"(ok) : "r"(addr), "r"(parity), "r"(100000u) : "memory");
+        if (ok) return;
     }
+    printf("arseg creff_march: mbarrier wait timed out (block %d thread %d step %d)\n", (int)blockIdx.x, (int)threadIdx.x, step);
+    __trap();
 }
 
 // byte offset of 16-byte chunk `chunk` of K/V ring position (slot row, col): the swizzle key is the column only,
