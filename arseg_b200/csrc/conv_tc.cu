@@ -14,8 +14,8 @@
 //   * Epilogue (4 warps, one TMEM lane quarter each): tcgen05.ld -> folded-BN scale/shift (+bias)
 //     -> (+residual) -> ReLU/PReLU -> NHWC store (channel slice of the destination = fused torch.cat).
 //   * Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
-//   Non-persistent: one CTA per (m-tile, n-tile); two CTAs co-reside per SM so one CTA's epilogue overlaps
-//   the other's main loop.
+//   Persistent: one CTA per SM walks the (m-tile, n-tile) list; two TMEM accumulator buffers let the epilogue of
+//   one tile overlap the main loop of the next.
 #include "common.cuh"
 #include <cuda.h>
 #include <mutex>
@@ -32,6 +32,7 @@ struct TcParams {
     int N, Ho, Wo, Cin, Cout, KH, KW, pad, dil, ocs, oco, act;
     float slope;
     int TH, TW, tiles_x, tiles_y, n_tiles, kchunks;  // kchunks = Cin / BK
+    int cout_pad;                                    // Cout rounded up to the n-tile size (scale/shift staging)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -44,6 +45,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
@@ -135,18 +139,26 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // ---------------------------------------------------------------------------------------------
-// kernel
+// kernel: persistent, warp-specialised.  One CTA per SM walks the tile list (tile = blockIdx.x + i * gridDim.x,
+// n-tile fastest so that CTAs working at the same time share A tiles in L2).  Three pipelines:
+//   smem ring   full/empty   TMA producer (warp 0)  <->  MMA issuer (warp 1)
+//   TMEM        tfull/tempty MMA issuer             <->  epilogue warps 2..5 (two accumulator buffers, so the
+//                                                        epilogue of tile i overlaps the main loop of tile i+1)
 // ---------------------------------------------------------------------------------------------
+constexpr int TC_NACC = 2;
+constexpr int TC_MAX_COUT = 2048;   // scale/shift staged in shared memory once per CTA
+
 template <typename T, int BLOCK_N, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap map_a,
-                                                             const __grid_constant__ CUtensorMap map_b, TcParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                const __grid_constant__ CUtensorMap map_b, TcParams p) {
     constexpr bool TF32 = sizeof(T) == 4;
     constexpr int BK = TC_ROW_BYTES / (int)sizeof(T);     // elements per swizzle row: 64 (bf16) / 32 (tf32)
     constexpr int UMMA_K = 32 / (int)sizeof(T);           // 16 / 8
     constexpr int B_STAGE = BLOCK_N * TC_ROW_BYTES;
     constexpr uint32_t STAGE_BYTES = TC_A_STAGE + B_STAGE;
     constexpr uint32_t IDESC = umma_idesc(TF32 ? 2 : 1, TC_BM, BLOCK_N);
-    constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+    constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+    constexpr int TMEM_COLS = TC_NACC * ACC_COLS;         // power of two >= 64
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -154,29 +166,28 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     uint8_t* smem_b = smem + STAGES * TC_A_STAGE;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full_bar = empty_bar + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    uint64_t* tfull_bar = empty_bar + STAGES;
+    uint64_t* tempty_bar = tfull_bar + TC_NACC;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + TC_NACC);
+    float* s_scale = reinterpret_cast<float*>(tmem_slot + 4);
+    float* s_shift = s_scale + p.cout_pad;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    // tile coordinates: n-tile fastest so CTAs sharing an A tile are co-scheduled (L2 reuse)
-    int b = blockIdx.x;
-    const int nt = b % p.n_tiles; b /= p.n_tiles;
-    const int txi = b % p.tiles_x; b /= p.tiles_x;
-    const int tyi = b % p.tiles_y;
-    const int img = b / p.tiles_y;
-    const int x0 = txi * p.TW, y0 = tyi * p.TH, n0 = nt * BLOCK_N;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(tmem_full_bar, 1);
+        for (int a = 0; a < TC_NACC; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 128); }
         fence_barrier_init();
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < p.cout_pad; i += TC_THREADS) {
+        s_scale[i] = (p.scale && i < p.Cout) ? __ldg(p.scale + i) : 1.f;
+        s_shift[i] = (p.shift && i < p.Cout) ? __ldg(p.shift + i) : 0.f;
     }
     tc_fence_before();
     __syncthreads();
@@ -185,91 +196,118 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
 
     const int taps = p.KH * p.KW;
     const int kiters = taps * p.kchunks;
+    const int total_tiles = p.N * p.tiles_y * p.tiles_x * p.n_tiles;
 
     if (warp == 0) {
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
-            for (int it = 0; it < kiters; ++it) {
-                const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
-                const int ky = tap / p.KW, kx = tap - ky * p.KW;
-                mbar_wait(&empty_bar[stage], phase ^ 1);
-                mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-                tma_load_4d(&map_a, &full_bar[stage], smem_a + stage * TC_A_STAGE, kc * BK, x0 - p.pad + kx * p.dil,
-                            y0 - p.pad + ky * p.dil, img);
-                tma_load_2d(&map_b, &full_bar[stage], smem_b + stage * B_STAGE, tap * p.Cin + kc * BK, n0);
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int b = tile;
+                const int nt = b % p.n_tiles; b /= p.n_tiles;
+                const int txi = b % p.tiles_x; b /= p.tiles_x;
+                const int tyi = b % p.tiles_y;
+                const int img = b / p.tiles_y;
+                const int x0 = txi * p.TW, y0 = tyi * p.TH, n0 = nt * BLOCK_N;
+                int tap = 0, kc = 0, ky = 0, kx = 0;
+                for (int it = 0; it < kiters; ++it) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+                    tma_load_4d(&map_a, &full_bar[stage], smem_a + stage * TC_A_STAGE, kc * BK, x0 - p.pad + kx * p.dil,
+                                y0 - p.pad + ky * p.dil, img);
+                    tma_load_2d(&map_b, &full_bar[stage], smem_b + stage * B_STAGE, tap * p.Cin + kc * BK, n0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++kc == p.kchunks) { kc = 0; ++tap; if (++kx == p.KW) { kx = 0; ++ky; } }
+                }
             }
         }
     } else if (warp == 1) {
         int stage = 0; uint32_t phase = 0;
-        for (int it = 0; it < kiters; ++it) {
-            mbar_wait(&full_bar[stage], phase);
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);              // the epilogue has drained this accumulator
             tc_fence_after();
-            if (elect_one()) {
-                const uint64_t da = umma_desc_sw128(smem_u32(smem_a + stage * TC_A_STAGE));
-                const uint64_t db = umma_desc_sw128(smem_u32(smem_b + stage * B_STAGE));
+            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * ACC_COLS);
+            for (int it = 0; it < kiters; ++it) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t da = umma_desc_sw128(smem_u32(smem_a + stage * TC_A_STAGE));
+                    const uint64_t db = umma_desc_sw128(smem_u32(smem_b + stage * B_STAGE));
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k)   // +32 bytes per UMMA_K step inside the swizzle row
-                    umma_ss<TF32>(da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), tmem_base, (it | k) != 0, IDESC);
-                umma_commit(&empty_bar[stage]);                       // frees the smem stage when the MMAs retire
-                if (it == kiters - 1) umma_commit(tmem_full_bar);     // accumulator complete -> epilogue
+                    for (int k = 0; k < BK / UMMA_K; ++k)   // +32 bytes per UMMA_K step inside the swizzle row
+                        umma_ss<TF32>(da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), tmem_d, (it | k) != 0, IDESC);
+                    umma_commit(&empty_bar[stage]);                       // frees the smem stage when the MMAs retire
+                    if (it == kiters - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete -> epilogue
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
-            __syncwarp();
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            if (++acc == TC_NACC) { acc = 0; acc_phase ^= 1; }
         }
     } else {
         // epilogue warps 2..5: TMEM lane quarter = warp % 4
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
-        const int gy = y0 + row / p.TW, gx = x0 + row % p.TW;
-        const bool valid = gy < p.Ho && gx < p.Wo;
-        const size_t pix = ((size_t)img * p.Ho + gy) * p.Wo + gx;
-        T* __restrict__ out = reinterpret_cast<T*>(p.out) + pix * p.ocs + p.oco;
-        const T* __restrict__ res = p.res ? reinterpret_cast<const T*>(p.res) + pix * p.Cout : nullptr;
-        mbar_wait(tmem_full_bar, 0);
-        tc_fence_after();
+        const int ry = row / p.TW, rx = row % p.TW;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int b = tile;
+            const int nt = b % p.n_tiles; b /= p.n_tiles;
+            const int txi = b % p.tiles_x; b /= p.tiles_x;
+            const int tyi = b % p.tiles_y;
+            const int img = b / p.tiles_y;
+            const int n0 = nt * BLOCK_N;
+            const int gy = tyi * p.TH + ry, gx = txi * p.TW + rx;
+            const bool valid = gy < p.Ho && gx < p.Wo;
+            const size_t pix = ((size_t)img * p.Ho + gy) * p.Wo + gx;
+            T* __restrict__ out = reinterpret_cast<T*>(p.out) + pix * p.ocs + p.oco;
+            const T* __restrict__ res = p.res ? reinterpret_cast<const T*>(p.res) + pix * p.Cout : nullptr;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS);
 #pragma unroll 1
-        for (int cb = 0; cb < BLOCK_N; cb += 32) {
-            uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)cb, r);
-            tmem_ld_wait();
-            if (!valid) continue;
-            const int co0 = n0 + cb;
-            if (co0 >= p.Cout) continue;
-            float v[32];
+            for (int cb = 0; cb < BLOCK_N; cb += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_d + (uint32_t)cb, r);
+                tmem_ld_wait();
+                if (cb + 32 >= BLOCK_N) {                 // last chunk is in registers: hand the accumulator back
+                    tc_fence_before();
+                    mbar_arrive(&tempty_bar[acc]);
+                }
+                const int co0 = n0 + cb;
+                if (!valid || co0 >= p.Cout) continue;
+                float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int co = co0 + j;
-                float a = __uint_as_float(r[j]);
-                if (co < p.Cout) {
-                    a = a * (p.scale ? __ldg(p.scale + co) : 1.f) + (p.shift ? __ldg(p.shift + co) : 0.f);
-                    if (res) a += to_f32(res[co]);
+                for (int j = 0; j < 32; ++j) {
+                    float a = fmaf(__uint_as_float(r[j]), s_scale[co0 + j], s_shift[co0 + j]);
+                    if (res && co0 + j < p.Cout) a += to_f32(res[co0 + j]);
                     if (p.act == ARSEG_ACT_RELU) a = fmaxf(a, 0.f);
                     else if (p.act == ARSEG_ACT_PRELU) a = a > 0.f ? a : a * p.slope;
+                    v[j] = a;
                 }
-                v[j] = a;
-            }
-            if (co0 + 32 <= p.Cout && ((p.ocs | p.oco) % (16 / (int)sizeof(T)) == 0)) {
-                if (TF32) {
+                if (co0 + 32 <= p.Cout && ((p.ocs | p.oco) % (16 / (int)sizeof(T)) == 0)) {
+                    if (TF32) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + co0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + co0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            uint4 pk;
+                            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + co0 + j) = pk;
+                        }
+                    }
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        uint4 pk;
-                        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                        pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                        pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + co0 + j) = pk;
-                    }
+                    for (int j = 0; j < 32; ++j)
+                        if (co0 + j < p.Cout) out[co0 + j] = from_f32<T>(v[j]);
                 }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (co0 + j < p.Cout) out[co0 + j] = from_f32<T>(v[j]);
             }
+            if (++acc == TC_NACC) { acc = 0; acc_phase ^= 1; }
         }
     }
     tc_fence_before();
@@ -335,18 +373,21 @@ bool conv_tc_supported(const arseg_conv_desc* d) {
 
 template <typename T, int BLOCK_N, int STAGES>
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st) {
-    constexpr size_t smem = (size_t)STAGES * (TC_A_STAGE + BLOCK_N * TC_ROW_BYTES) + (2 * STAGES + 1) * 8 + 16 + 1024;
+    const size_t smem = (size_t)STAGES * (TC_A_STAGE + BLOCK_N * TC_ROW_BYTES) + (2 * STAGES + 2 * TC_NACC) * 8 + 16 + 2 * (size_t)p.cout_pad * 4 + 1024;
+    ARSEG_REQUIRE(smem <= 232448, "conv_tc: Cout=%d too large for the scale/shift staging", p.Cout);
     auto kern = conv_tc_kernel<T, BLOCK_N, STAGES>;
     static bool configured[64] = {false};
     int dev = 0;
     ARSEG_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !configured[dev]) {
-        ARSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ARSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
-    const long long blocks = (long long)p.N * p.tiles_y * p.tiles_x * p.n_tiles;
-    ARSEG_REQUIRE(blocks > 0 && blocks < 2147483647LL, "conv_tc: grid too large");
-    kern<<<(unsigned)blocks, TC_THREADS, smem, st>>>(ma, mb, p);
+    const long long tiles = (long long)p.N * p.tiles_y * p.tiles_x * p.n_tiles;
+    ARSEG_REQUIRE(tiles > 0 && tiles < 2147483647LL, "conv_tc: too many tiles");
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    const unsigned blocks = (unsigned)(tiles < sms ? tiles : sms);          // persistent: one CTA per SM
+    kern<<<blocks, TC_THREADS, smem, st>>>(ma, mb, p);
     ARSEG_CHECK_LAUNCH("conv_tc");
     return ARSEG_OK;
 }
@@ -365,6 +406,8 @@ int conv_tc_launch(const arseg_conv_desc* d, cudaStream_t st) {
     p.kchunks = d->Cin / bk;
     const int block_n = d->Cout >= 128 ? 128 : (d->Cout > 32 ? 64 : 32);
     p.n_tiles = ceil_div(d->Cout, block_n);
+    p.cout_pad = p.n_tiles * block_n;
+    ARSEG_REQUIRE(p.cout_pad <= TC_MAX_COUT, "conv_tc: Cout=%d > %d", d->Cout, TC_MAX_COUT);
 
     const CUtensorMapDataType dt = tf32 ? (tf32_tma_round() ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32)
                                         : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
@@ -389,13 +432,13 @@ int conv_tc_launch(const arseg_conv_desc* d, cudaStream_t st) {
         if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(B) failed (%d)", (int)r); return ARSEG_E_CUDA; }
     }
     if (tf32) {
-        if (block_n == 128) return launch_tc<float, 128, 3>(ma, mb, p, st);
-        if (block_n == 64) return launch_tc<float, 64, 4>(ma, mb, p, st);
-        return launch_tc<float, 32, 4>(ma, mb, p, st);
+        if (block_n == 128) return launch_tc<float, 128, 6>(ma, mb, p, st);
+        if (block_n == 64) return launch_tc<float, 64, 8>(ma, mb, p, st);
+        return launch_tc<float, 32, 8>(ma, mb, p, st);
     }
-    if (block_n == 128) return launch_tc<__nv_bfloat16, 128, 3>(ma, mb, p, st);
-    if (block_n == 64) return launch_tc<__nv_bfloat16, 64, 4>(ma, mb, p, st);
-    return launch_tc<__nv_bfloat16, 32, 4>(ma, mb, p, st);
+    if (block_n == 128) return launch_tc<__nv_bfloat16, 128, 6>(ma, mb, p, st);
+    if (block_n == 64) return launch_tc<__nv_bfloat16, 64, 8>(ma, mb, p, st);
+    return launch_tc<__nv_bfloat16, 32, 8>(ma, mb, p, st);
 }
 
 }  // namespace arseg
