@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <mutex>
+#include <cstdlib>
 
 namespace arseg {
 
@@ -319,6 +320,210 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 }
 
 // ---------------------------------------------------------------------------------------------
+// 3x3 kernel with operand reuse across the taps ("halo" kernel).  Same roles and pipelines as above, but the A
+// operand of a Cin chunk is loaded ONCE per tile as a (16+2d) x 16-pixel halo box (d = dilation = padding) instead
+// of nine tap-shifted 128-pixel boxes: the output tile is 16 rows x 8 pixels, so the 128 GEMM rows of tap (ky,kx)
+// are the halo rows ((ty + ky d) * 16 + tx + kx d), i.e. 8-row groups at a constant stride of 16 halo rows --
+// a K-major SWIZZLE_128B operand with SBO = 2048 B whose start address is simply advanced by the tap offset.
+// A traffic drops from 9 x 16 KB to 36-48 KB per Cin chunk; B (weights) is streamed per tap as before.
+// The 128-byte swizzle is a function of the shared-memory address bits in both the TMA write and the UMMA read,
+// so a start address that is 128-byte but not 1024-byte aligned addresses the same bytes with the descriptor's
+// base-offset field left 0 (verified on B200: setting it to (addr >> 7) & 7 gives wrong results).
+// ---------------------------------------------------------------------------------------------
+constexpr int TCH_TW = 8, TCH_TH = 16, TCH_WH = 16;      // output tile, halo box width (pixels)
+
+struct TchParams {
+    TcParams c;
+    int sa, sb;             // A-halo stages, B stages
+    int a_stage;            // bytes per A-halo stage
+};
+
+__device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo, uint32_t base_off) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) | ((uint64_t)(base_off & 7) << 49) | (2ull << 61);
+}
+
+template <typename T, int BLOCK_N>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                     const __grid_constant__ CUtensorMap map_b, TchParams hp) {
+    const TcParams& p = hp.c;
+    constexpr bool TF32 = sizeof(T) == 4;
+    constexpr int BK = TC_ROW_BYTES / (int)sizeof(T);
+    constexpr int UMMA_K = 32 / (int)sizeof(T);
+    constexpr int B_STAGE = BLOCK_N * TC_ROW_BYTES;
+    constexpr uint32_t IDESC = umma_idesc(TF32 ? 2 : 1, TC_BM, BLOCK_N);
+    constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+    constexpr int TMEM_COLS = TC_NACC * ACC_COLS;
+    constexpr int MAXS = 8;
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + hp.sa * hp.a_stage;
+    uint64_t* fulla = reinterpret_cast<uint64_t*>(smem_b + hp.sb * B_STAGE);
+    uint64_t* emptya = fulla + MAXS;
+    uint64_t* fullb = emptya + MAXS;
+    uint64_t* emptyb = fullb + MAXS;
+    uint64_t* tfull_bar = emptyb + MAXS;
+    uint64_t* tempty_bar = tfull_bar + TC_NACC;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + TC_NACC);
+    float* s_scale = reinterpret_cast<float*>(tmem_slot + 4);
+    float* s_shift = s_scale + p.cout_pad;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+        for (int s = 0; s < MAXS; ++s) { mbar_init(&fulla[s], 1); mbar_init(&emptya[s], 1); mbar_init(&fullb[s], 1); mbar_init(&emptyb[s], 1); }
+        for (int a = 0; a < TC_NACC; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 128); }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < p.cout_pad; i += TC_THREADS) {
+        s_scale[i] = (p.scale && i < p.Cout) ? __ldg(p.scale + i) : 1.f;
+        s_shift[i] = (p.shift && i < p.Cout) ? __ldg(p.shift + i) : 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int total_tiles = p.N * p.tiles_y * p.tiles_x * p.n_tiles;
+    const int d = p.dil;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int b = tile;
+                const int nt = b % p.n_tiles; b /= p.n_tiles;
+                const int txi = b % p.tiles_x; b /= p.tiles_x;
+                const int tyi = b % p.tiles_y;
+                const int img = b / p.tiles_y;
+                const int x0 = txi * TCH_TW, y0 = tyi * TCH_TH, n0 = nt * BLOCK_N;
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    mbar_wait(&emptya[sa], pa ^ 1);
+                    mbar_expect_tx(&fulla[sa], (uint32_t)hp.a_stage);
+                    tma_load_4d(&map_a, &fulla[sa], smem_a + sa * hp.a_stage, kc * BK, x0 - d, y0 - d, img);
+                    if (++sa == hp.sa) { sa = 0; pa ^= 1; }
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(&emptyb[sb], pb ^ 1);
+                        mbar_expect_tx(&fullb[sb], B_STAGE);
+                        tma_load_2d(&map_b, &fullb[sb], smem_b + sb * B_STAGE, tap * p.Cin + kc * BK, n0);
+                        if (++sb == hp.sb) { sb = 0; pb ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * ACC_COLS);
+            for (int kc = 0; kc < p.kchunks; ++kc) {
+                mbar_wait(&fulla[sa], pa);
+                const uint32_t a_base = smem_u32(smem_a + sa * hp.a_stage);
+                for (int tap = 0; tap < 9; ++tap) {
+                    mbar_wait(&fullb[sb], pb);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const int ky = tap / 3, kx = tap - 3 * ky;
+                        const uint32_t a_addr = a_base + (uint32_t)(((ky * d) * TCH_WH + kx * d) * TC_ROW_BYTES);
+                        const uint64_t da = umma_desc_sw128_sbo(a_addr, TCH_WH * TC_ROW_BYTES, 0u);
+                        const uint64_t db = umma_desc_sw128(smem_u32(smem_b + sb * B_STAGE));
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k)
+                            umma_ss<TF32>(da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), tmem_d, (kc | tap | k) != 0, IDESC);
+                        umma_commit(&emptyb[sb]);
+                        if (tap == 8) {
+                            umma_commit(&emptya[sa]);
+                            if (kc == p.kchunks - 1) umma_commit(&tfull_bar[acc]);
+                        }
+                    }
+                    __syncwarp();
+                    if (++sb == hp.sb) { sb = 0; pb ^= 1; }
+                }
+                if (++sa == hp.sa) { sa = 0; pa ^= 1; }
+            }
+            if (++acc == TC_NACC) { acc = 0; acc_phase ^= 1; }
+        }
+    } else {
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const int ry = row / TCH_TW, rx = row % TCH_TW;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int b = tile;
+            const int nt = b % p.n_tiles; b /= p.n_tiles;
+            const int txi = b % p.tiles_x; b /= p.tiles_x;
+            const int tyi = b % p.tiles_y;
+            const int img = b / p.tiles_y;
+            const int n0 = nt * BLOCK_N;
+            const int gy = tyi * TCH_TH + ry, gx = txi * TCH_TW + rx;
+            const bool valid = gy < p.Ho && gx < p.Wo;
+            const size_t pix = ((size_t)img * p.Ho + gy) * p.Wo + gx;
+            T* __restrict__ out = reinterpret_cast<T*>(p.out) + pix * p.ocs + p.oco;
+            const T* __restrict__ res = p.res ? reinterpret_cast<const T*>(p.res) + pix * p.Cout : nullptr;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS);
+#pragma unroll 1
+            for (int cb = 0; cb < BLOCK_N; cb += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_d + (uint32_t)cb, r);
+                tmem_ld_wait();
+                if (cb + 32 >= BLOCK_N) {
+                    tc_fence_before();
+                    mbar_arrive(&tempty_bar[acc]);
+                }
+                const int co0 = n0 + cb;
+                if (!valid || co0 >= p.Cout) continue;
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float a = fmaf(__uint_as_float(r[j]), s_scale[co0 + j], s_shift[co0 + j]);
+                    if (res && co0 + j < p.Cout) a += to_f32(res[co0 + j]);
+                    if (p.act == ARSEG_ACT_RELU) a = fmaxf(a, 0.f);
+                    else if (p.act == ARSEG_ACT_PRELU) a = a > 0.f ? a : a * p.slope;
+                    v[j] = a;
+                }
+                if (co0 + 32 <= p.Cout && ((p.ocs | p.oco) % (16 / (int)sizeof(T)) == 0)) {
+                    if (TF32) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + co0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            uint4 pk;
+                            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + co0 + j) = pk;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (co0 + j < p.Cout) out[co0 + j] = from_f32<T>(v[j]);
+                }
+            }
+            if (++acc == TC_NACC) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -392,6 +597,36 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParam
     return ARSEG_OK;
 }
 
+template <typename T, int BLOCK_N>
+static int launch_tch(const CUtensorMap& ma, const CUtensorMap& mb, TchParams& hp, cudaStream_t st) {
+    const TcParams& p = hp.c;
+    const size_t fixed = (4 * 8 + 2 * TC_NACC) * 8 + 16 + 2 * (size_t)p.cout_pad * 4 + 1024;
+    const size_t b_stage = (size_t)BLOCK_N * TC_ROW_BYTES;
+    hp.sa = 2;
+    long long sb = ((long long)232448 - (long long)fixed - (long long)hp.sa * hp.a_stage) / (long long)b_stage;
+    ARSEG_REQUIRE(sb >= 2, "conv_tc_halo: not enough shared memory (Cout=%d)", p.Cout);
+    hp.sb = sb > 8 ? 8 : (int)sb;
+    const size_t smem = fixed + (size_t)hp.sa * hp.a_stage + (size_t)hp.sb * b_stage;
+    auto kern = conv_tc_halo_kernel<T, BLOCK_N>;
+    static bool configured[64] = {false};
+    int dev = 0;
+    ARSEG_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        ARSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    const long long tiles = (long long)p.N * p.tiles_y * p.tiles_x * p.n_tiles;
+    ARSEG_REQUIRE(tiles > 0 && tiles < 2147483647LL, "conv_tc_halo: too many tiles");
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    const unsigned blocks = (unsigned)(tiles < sms ? tiles : sms);
+    kern<<<blocks, TC_THREADS, smem, st>>>(ma, mb, hp);
+    ARSEG_CHECK_LAUNCH("conv_tc_halo");
+    return ARSEG_OK;
+}
+
+// ARSEG_TC_HALO=0 disables the halo kernel, ARSEG_TC_N256=0 the 256-wide n-tiles (A/B measurements)
+static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+
 int conv_tc_launch(const arseg_conv_desc* d, cudaStream_t st) {
     EncodeTiledFn encode = get_encode();
     if (!encode) { set_error("conv_tc: cuTensorMapEncodeTiled entry point not available"); return ARSEG_E_CUDA; }
@@ -401,10 +636,12 @@ int conv_tc_launch(const arseg_conv_desc* d, cudaStream_t st) {
     p.scale = d->scale; p.shift = d->shift; p.res = d->residual; p.out = d->out;
     p.N = d->N; p.Ho = d->Hi; p.Wo = d->Wi; p.Cin = d->Cin; p.Cout = d->Cout; p.KH = d->KH; p.KW = d->KW;
     p.pad = d->pad; p.dil = d->dil; p.ocs = d->out_cstride; p.oco = d->out_coff; p.act = d->act; p.slope = d->prelu_slope;
-    pick_tile(p.Ho, p.Wo, p.TH, p.TW);
+    const bool halo = d->KH == 3 && d->KW == 3 && d->pad == d->dil && d->dil >= 1 && d->dil <= 8 && env_int("ARSEG_TC_HALO", 1) != 0;
+    if (halo) { p.TH = TCH_TH; p.TW = TCH_TW; } else pick_tile(p.Ho, p.Wo, p.TH, p.TW);
     p.tiles_x = ceil_div(p.Wo, p.TW); p.tiles_y = ceil_div(p.Ho, p.TH);
     p.kchunks = d->Cin / bk;
-    const int block_n = d->Cout >= 128 ? 128 : (d->Cout > 32 ? 64 : 32);
+    const int n256 = env_int("ARSEG_TC_N256", 1);
+    const int block_n = (d->Cout >= 256 && d->Cout % 256 == 0 && n256) ? 256 : (d->Cout >= 128 ? 128 : (d->Cout > 32 ? 64 : 32));
     p.n_tiles = ceil_div(d->Cout, block_n);
     p.cout_pad = p.n_tiles * block_n;
     ARSEG_REQUIRE(p.cout_pad <= TC_MAX_COUT, "conv_tc: Cout=%d > %d", d->Cout, TC_MAX_COUT);
@@ -415,7 +652,7 @@ int conv_tc_launch(const arseg_conv_desc* d, cudaStream_t st) {
     {
         cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->Wi, (cuuint64_t)d->Hi, (cuuint64_t)d->N};
         cuuint64_t strides[3] = {(cuuint64_t)d->Cin * es, (cuuint64_t)d->Wi * d->Cin * es, (cuuint64_t)d->Hi * d->Wi * d->Cin * es};
-        cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+        cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)(halo ? TCH_WH : p.TW), (cuuint32_t)(halo ? TCH_TH + 2 * d->dil : p.TH), 1};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = encode(&ma, dt, 4, const_cast<void*>(d->in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -431,11 +668,28 @@ int conv_tc_launch(const arseg_conv_desc* d, cudaStream_t st) {
                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(B) failed (%d)", (int)r); return ARSEG_E_CUDA; }
     }
+    if (halo) {
+        TchParams hp;
+        hp.c = p;
+        hp.a_stage = TCH_WH * (TCH_TH + 2 * d->dil) * TC_ROW_BYTES;
+        if (tf32) {
+            if (block_n == 256) return launch_tch<float, 256>(ma, mb, hp, st);
+            if (block_n == 128) return launch_tch<float, 128>(ma, mb, hp, st);
+            if (block_n == 64) return launch_tch<float, 64>(ma, mb, hp, st);
+            return launch_tch<float, 32>(ma, mb, hp, st);
+        }
+        if (block_n == 256) return launch_tch<__nv_bfloat16, 256>(ma, mb, hp, st);
+        if (block_n == 128) return launch_tch<__nv_bfloat16, 128>(ma, mb, hp, st);
+        if (block_n == 64) return launch_tch<__nv_bfloat16, 64>(ma, mb, hp, st);
+        return launch_tch<__nv_bfloat16, 32>(ma, mb, hp, st);
+    }
     if (tf32) {
+        if (block_n == 256) return launch_tc<float, 256, 4>(ma, mb, p, st);
         if (block_n == 128) return launch_tc<float, 128, 6>(ma, mb, p, st);
         if (block_n == 64) return launch_tc<float, 64, 8>(ma, mb, p, st);
         return launch_tc<float, 32, 8>(ma, mb, p, st);
     }
+    if (block_n == 256) return launch_tc<__nv_bfloat16, 256, 4>(ma, mb, p, st);
     if (block_n == 128) return launch_tc<__nv_bfloat16, 128, 6>(ma, mb, p, st);
     if (block_n == 64) return launch_tc<__nv_bfloat16, 64, 8>(ma, mb, p, st);
     return launch_tc<__nv_bfloat16, 32, 8>(ma, mb, p, st);
