@@ -336,30 +336,38 @@ struct TchParams {
     TcParams c;
     int sa, sb;             // A-halo stages, B stages
     int a_stage;            // bytes per A-halo stage
+    int tps;                // taps per B stage (1 or 3): short MMAs (narrow n-tiles) need fewer barrier round trips
+    int b_resident;         // 1: all 9 * kchunks weight tiles stay in shared memory for the whole kernel
 };
 
 __device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo, uint32_t base_off) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) | ((uint64_t)(base_off & 7) << 49) | (2ull << 61);
 }
 
+constexpr int TCH_EPI_WARPS = 8;                       // two warps per TMEM lane quarter, half the columns each
+constexpr int TCH_THREADS = 64 + 32 * TCH_EPI_WARPS;
+
 template <typename T, int BLOCK_N>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a,
-                                                                     const __grid_constant__ CUtensorMap map_b, TchParams hp) {
+__global__ void __launch_bounds__(TCH_THREADS, 1) conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                      const __grid_constant__ CUtensorMap map_b, TchParams hp) {
     const TcParams& p = hp.c;
     constexpr bool TF32 = sizeof(T) == 4;
     constexpr int BK = TC_ROW_BYTES / (int)sizeof(T);
     constexpr int UMMA_K = 32 / (int)sizeof(T);
-    constexpr int B_STAGE = BLOCK_N * TC_ROW_BYTES;
+    constexpr int B_TAP = BLOCK_N * TC_ROW_BYTES;         // bytes of one tap's weight tile
     constexpr uint32_t IDESC = umma_idesc(TF32 ? 2 : 1, TC_BM, BLOCK_N);
     constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
     constexpr int TMEM_COLS = TC_NACC * ACC_COLS;
     constexpr int MAXS = 8;
+    constexpr int CHUNKS = BLOCK_N / 32;                  // 32-column epilogue chunks
+    constexpr int CPW = CHUNKS >= 2 ? CHUNKS / 2 : 1;     // chunks per epilogue warp
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int b_stage = hp.tps * B_TAP;
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + hp.sa * hp.a_stage;
-    uint64_t* fulla = reinterpret_cast<uint64_t*>(smem_b + hp.sb * B_STAGE);
+    uint64_t* fulla = reinterpret_cast<uint64_t*>(smem_b + hp.sb * b_stage);
     uint64_t* emptya = fulla + MAXS;
     uint64_t* fullb = emptya + MAXS;
     uint64_t* emptyb = fullb + MAXS;
@@ -370,18 +378,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_halo_kernel(const __gri
     float* s_shift = s_scale + p.cout_pad;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int EPI_ARRIVALS = (CHUNKS >= 2 ? TCH_EPI_WARPS : 4) * 32;
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
         for (int s = 0; s < MAXS; ++s) { mbar_init(&fulla[s], 1); mbar_init(&emptya[s], 1); mbar_init(&fullb[s], 1); mbar_init(&emptyb[s], 1); }
-        for (int a = 0; a < TC_NACC; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 128); }
+        for (int a = 0; a < TC_NACC; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], EPI_ARRIVALS); }
         fence_barrier_init();
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < p.cout_pad; i += TC_THREADS) {
+    for (int i = threadIdx.x; i < p.cout_pad; i += TCH_THREADS) {
         s_scale[i] = (p.scale && i < p.Cout) ? __ldg(p.scale + i) : 1.f;
         s_shift[i] = (p.shift && i < p.Cout) ? __ldg(p.shift + i) : 0.f;
     }
@@ -391,11 +400,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_halo_kernel(const __gri
     const uint32_t tmem_base = *tmem_slot;
     const int total_tiles = p.N * p.tiles_y * p.tiles_x * p.n_tiles;
     const int d = p.dil;
+    const int tgroups = 9 / hp.tps;                       // B stages per Cin chunk
 
     if (warp == 0) {
         if (elect_one()) {
             int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            bool first = true;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, first = false) {
                 int b = tile;
                 const int nt = b % p.n_tiles; b /= p.n_tiles;
                 const int txi = b % p.tiles_x; b /= p.tiles_x;
@@ -407,10 +418,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_halo_kernel(const __gri
                     mbar_expect_tx(&fulla[sa], (uint32_t)hp.a_stage);
                     tma_load_4d(&map_a, &fulla[sa], smem_a + sa * hp.a_stage, kc * BK, x0 - d, y0 - d, img);
                     if (++sa == hp.sa) { sa = 0; pa ^= 1; }
-                    for (int tap = 0; tap < 9; ++tap) {
-                        mbar_wait(&emptyb[sb], pb ^ 1);
-                        mbar_expect_tx(&fullb[sb], B_STAGE);
-                        tma_load_2d(&map_b, &fullb[sb], smem_b + sb * B_STAGE, tap * p.Cin + kc * BK, n0);
+                    if (hp.b_resident && !first) continue;
+                    // resident: stage index = kc * tgroups + tg; barrier 0 is armed once with the bytes of all stages
+                    if (hp.b_resident && kc == 0) mbar_expect_tx(&fullb[0], (uint32_t)(p.kchunks * tgroups * b_stage));
+                    for (int tg = 0; tg < tgroups; ++tg) {
+                        uint64_t* fb = hp.b_resident ? &fullb[0] : &fullb[sb];
+                        if (!hp.b_resident) {
+                            mbar_wait(&emptyb[sb], pb ^ 1);
+                            mbar_expect_tx(fb, (uint32_t)b_stage);
+                        }
+                        for (int i = 0; i < hp.tps; ++i)
+                            tma_load_2d(&map_b, fb, smem_b + sb * b_stage + i * B_TAP, (tg * hp.tps + i) * p.Cin + kc * BK, n0);
                         if (++sb == hp.sb) { sb = 0; pb ^= 1; }
                     }
                 }
@@ -419,26 +437,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_halo_kernel(const __gri
     } else if (warp == 1) {
         int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        bool first = true;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, first = false) {
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + (uint32_t)(acc * ACC_COLS);
+            if (hp.b_resident) { sb = 0; if (first) { /* every weight tile has landed */ mbar_wait(&fullb[0], 0); } }
             for (int kc = 0; kc < p.kchunks; ++kc) {
                 mbar_wait(&fulla[sa], pa);
                 const uint32_t a_base = smem_u32(smem_a + sa * hp.a_stage);
-                for (int tap = 0; tap < 9; ++tap) {
-                    mbar_wait(&fullb[sb], pb);
+                for (int tg = 0; tg < tgroups; ++tg) {
+                    if (!hp.b_resident) mbar_wait(&fullb[sb], pb);
                     tc_fence_after();
                     if (elect_one()) {
-                        const int ky = tap / 3, kx = tap - 3 * ky;
-                        const uint32_t a_addr = a_base + (uint32_t)(((ky * d) * TCH_WH + kx * d) * TC_ROW_BYTES);
-                        const uint64_t da = umma_desc_sw128_sbo(a_addr, TCH_WH * TC_ROW_BYTES, 0u);
-                        const uint64_t db = umma_desc_sw128(smem_u32(smem_b + sb * B_STAGE));
+                        for (int i = 0; i < hp.tps; ++i) {
+                            const int tap = tg * hp.tps + i;
+                            const int ky = tap / 3, kx = tap - 3 * ky;
+                            const uint32_t a_addr = a_base + (uint32_t)(((ky * d) * TCH_WH + kx * d) * TC_ROW_BYTES);
+                            const uint64_t da = umma_desc_sw128_sbo(a_addr, TCH_WH * TC_ROW_BYTES, 0u);
+                            const uint64_t db = umma_desc_sw128(smem_u32(smem_b + sb * b_stage + i * B_TAP));
 #pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; ++k)
-                            umma_ss<TF32>(da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), tmem_d, (kc | tap | k) != 0, IDESC);
-                        umma_commit(&emptyb[sb]);
-                        if (tap == 8) {
+                            for (int k = 0; k < BK / UMMA_K; ++k)
+                                umma_ss<TF32>(da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), tmem_d, (kc | tap | k) != 0, IDESC);
+                        }
+                        if (!hp.b_resident) umma_commit(&emptyb[sb]);
+                        if (tg == tgroups - 1) {
                             umma_commit(&emptya[sa]);
                             if (kc == p.kchunks - 1) umma_commit(&tfull_bar[acc]);
                         }
@@ -450,8 +473,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_halo_kernel(const __gri
             }
             if (++acc == TC_NACC) { acc = 0; acc_phase ^= 1; }
         }
-    } else {
+    } else if (CHUNKS >= 2 || warp < 6) {
+        // epilogue warps 2..9: TMEM lane quarter = warp % 4; warps 2..5 take the low column half, 6..9 the high half
         const int quarter = warp & 3;
+        const int chalf = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
         const int ry = row / TCH_TW, rx = row % TCH_TW;
         int acc = 0; uint32_t acc_phase = 0;
@@ -471,11 +496,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_halo_kernel(const __gri
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS);
 #pragma unroll 1
-            for (int cb = 0; cb < BLOCK_N; cb += 32) {
+            for (int ci = 0; ci < CPW; ++ci) {
+                const int cb = (chalf * CPW + ci) * 32;
                 uint32_t r[32];
                 tmem_ld32(tmem_d + (uint32_t)cb, r);
                 tmem_ld_wait();
-                if (cb + 32 >= BLOCK_N) {
+                if (ci == CPW - 1) {                      // this warp's last chunk is in registers
                     tc_fence_before();
                     mbar_arrive(&tempty_bar[acc]);
                 }
@@ -483,14 +509,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_halo_kernel(const __gri
                 if (!valid || co0 >= p.Cout) continue;
                 float v[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float a = fmaf(__uint_as_float(r[j]), s_scale[co0 + j], s_shift[co0 + j]);
-                    if (res && co0 + j < p.Cout) a += to_f32(res[co0 + j]);
-                    if (p.act == ARSEG_ACT_RELU) a = fmaxf(a, 0.f);
-                    else if (p.act == ARSEG_ACT_PRELU) a = a > 0.f ? a : a * p.slope;
-                    v[j] = a;
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 sc = *reinterpret_cast<const float4*>(s_scale + co0 + j);
+                    const float4 sh = *reinterpret_cast<const float4*>(s_shift + co0 + j);
+                    v[j] = fmaf(__uint_as_float(r[j]), sc.x, sh.x); v[j + 1] = fmaf(__uint_as_float(r[j + 1]), sc.y, sh.y);
+                    v[j + 2] = fmaf(__uint_as_float(r[j + 2]), sc.z, sh.z); v[j + 3] = fmaf(__uint_as_float(r[j + 3]), sc.w, sh.w);
                 }
-                if (co0 + 32 <= p.Cout && ((p.ocs | p.oco) % (16 / (int)sizeof(T)) == 0)) {
+                const bool vec = co0 + 32 <= p.Cout && ((p.ocs | p.oco) % (16 / (int)sizeof(T)) == 0);
+                if (res) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (co0 + j < p.Cout) v[j] += to_f32(res[co0 + j]);
+                }
+                if (p.act == ARSEG_ACT_RELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                } else if (p.act == ARSEG_ACT_PRELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
+                }
+                if (vec) {
                     if (TF32) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4)
@@ -597,15 +635,26 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParam
     return ARSEG_OK;
 }
 
+static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+
 template <typename T, int BLOCK_N>
 static int launch_tch(const CUtensorMap& ma, const CUtensorMap& mb, TchParams& hp, cudaStream_t st) {
     const TcParams& p = hp.c;
     const size_t fixed = (4 * 8 + 2 * TC_NACC) * 8 + 16 + 2 * (size_t)p.cout_pad * 4 + 1024;
-    const size_t b_stage = (size_t)BLOCK_N * TC_ROW_BYTES;
+    const size_t b_tap = (size_t)BLOCK_N * TC_ROW_BYTES;
+    const long long budget = 232448 - (long long)fixed;
     hp.sa = 2;
-    long long sb = ((long long)232448 - (long long)fixed - (long long)hp.sa * hp.a_stage) / (long long)b_stage;
-    ARSEG_REQUIRE(sb >= 2, "conv_tc_halo: not enough shared memory (Cout=%d)", p.Cout);
-    hp.sb = sb > 8 ? 8 : (int)sb;
+    // weights that fit next to two A stages stay resident (64 -> 64 layers: 147 KB in tf32)
+    const long long w_bytes = 9LL * p.kchunks * (long long)b_tap;
+    hp.b_resident = p.n_tiles == 1 && w_bytes + 2LL * hp.a_stage <= budget && env_int("ARSEG_TC_BRES", 1) != 0;
+    hp.tps = (BLOCK_N <= 64 && env_int("ARSEG_TC_TPS", 3) == 3) ? 3 : 1;
+    const size_t b_stage = hp.tps * b_tap;
+    if (hp.b_resident) hp.sb = (9 / hp.tps) * p.kchunks;
+    else {
+        long long sb = (budget - (long long)hp.sa * hp.a_stage) / (long long)b_stage;
+        ARSEG_REQUIRE(sb >= 2, "conv_tc_halo: not enough shared memory (Cout=%d)", p.Cout);
+        hp.sb = sb > 8 ? 8 : (int)sb;
+    }
     const size_t smem = fixed + (size_t)hp.sa * hp.a_stage + (size_t)hp.sb * b_stage;
     auto kern = conv_tc_halo_kernel<T, BLOCK_N>;
     static bool configured[64] = {false};
@@ -619,13 +668,13 @@ static int launch_tch(const CUtensorMap& ma, const CUtensorMap& mb, TchParams& h
     ARSEG_REQUIRE(tiles > 0 && tiles < 2147483647LL, "conv_tc_halo: too many tiles");
     const int sms = sm_count() > 0 ? sm_count() : 148;
     const unsigned blocks = (unsigned)(tiles < sms ? tiles : sms);
-    kern<<<blocks, TC_THREADS, smem, st>>>(ma, mb, hp);
+    kern<<<blocks, TCH_THREADS, smem, st>>>(ma, mb, hp);
     ARSEG_CHECK_LAUNCH("conv_tc_halo");
     return ARSEG_OK;
 }
 
-// ARSEG_TC_HALO=0 disables the halo kernel, ARSEG_TC_N256=0 the 256-wide n-tiles (A/B measurements)
-static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+// ARSEG_TC_HALO=0 disables the halo kernel, ARSEG_TC_N256=0 the 256-wide n-tiles, ARSEG_TC_BRES=0 resident weights,
+// ARSEG_TC_TPS=1 the three-tap weight stages (A/B measurements)
 
 int conv_tc_launch(const arseg_conv_desc* d, cudaStream_t st) {
     EncodeTiledFn encode = get_encode();
