@@ -12,11 +12,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_build", "libarseg_sm100a.so")
 
 OK, E_BADARG, E_UNSUPPORTED, E_CUDA = 0, -1, -2, -3
-F32, BF16, F64, I16 = 0, 1, 2, 3
+F32, BF16, F64, I16, F16 = 0, 1, 2, 3, 4
 ACT_NONE, ACT_RELU, ACT_PRELU = 0, 1, 2
 RESIZE_BILINEAR, RESIZE_BILINEAR_AC, RESIZE_NEAREST = 0, 1, 2
 NCHW, NHWC = 0, 1
-CONV_SIMT_F32, CONV_TC_TF32, CONV_TC_BF16 = 1, 2, 3
+CONV_SIMT_F32, CONV_TC_TF32, CONV_TC_BF16, CONV_TC_F16 = 1, 2, 3, 4
 CREFF_EXACT_F32, CREFF_MMA_F16 = 0, 1
 ABI_VERSION = 2
 

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
@@ -56,6 +57,13 @@ __device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162flo
 template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+// fp16 storage (11-bit significand, the same as TF32): round to nearest, saturate to +-65504 instead of overflowing to inf
+__device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) {
+    unsigned short r;
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(v));
+    return __ushort_as_half(r);
+}
 
 // ---- ATen-compatible resampling index math (aten/src/ATen/native/UpSample.h semantics) --------
 // mode: ARSEG_RESIZE_BILINEAR (align_corners=False), ARSEG_RESIZE_BILINEAR_AC (True)

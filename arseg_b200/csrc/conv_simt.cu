@@ -14,6 +14,7 @@ constexpr int BM = 128, BN = 64, BK = 16, LDA = BM + 4, LDB = BN + 4;
 template <typename T> struct Vec4 { T v[4]; };
 template <> struct alignas(16) Vec4<float> { float v[4]; };
 template <> struct alignas(8) Vec4<__nv_bfloat16> { __nv_bfloat16 v[4]; };
+template <> struct alignas(8) Vec4<__half> { __half v[4]; };
 
 struct ConvParams {
     const void* in; const void* w; const float* scale; const float* shift; const void* res; void* out;
@@ -149,6 +150,7 @@ int conv_simt_launch(const arseg_conv_desc* d, cudaStream_t st) {
     ARSEG_REQUIRE(grid.y <= 65535, "conv_simt: Cout too large");
     if (d->dtype == ARSEG_F32) conv_simt_kernel<float><<<grid, 256, 0, st>>>(p);
     else if (d->dtype == ARSEG_BF16) conv_simt_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p);
+    else if (d->dtype == ARSEG_F16) conv_simt_kernel<__half><<<grid, 256, 0, st>>>(p);
     else ARSEG_UNSUPPORTED("conv_simt: dtype %d", d->dtype);
     ARSEG_CHECK_LAUNCH("conv_simt");
     return ARSEG_OK;
@@ -174,6 +176,7 @@ extern "C" int arseg_conv2d_nhwc(const arseg_conv_desc* d, arseg_stream_t stream
             return conv_simt_launch(d, as_stream(stream));
         case ARSEG_CONV_TC_TF32:
         case ARSEG_CONV_TC_BF16:
+        case ARSEG_CONV_TC_F16:
             if (!conv_tc_supported(d))
                 ARSEG_UNSUPPORTED("conv2d: tcgen05 engine does not take this shape (Cin=%d Cout=%d stride=%d k=%dx%d)",
                                   d->Cin, d->Cout, d->stride, d->KH, d->KW);

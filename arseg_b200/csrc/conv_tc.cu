@@ -18,6 +18,7 @@
 //   one tile overlap the main loop of the next.
 #include "common.cuh"
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <mutex>
 #include <cstdlib>
 
@@ -101,6 +102,12 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t umma_idesc(int fmt, int M, int N) {
     return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// cute::UMMA::F16F32Format: F16 = 0, BF16 = 1, TF32 = 2
+template <typename T> struct UmmaFmt;
+template <> struct UmmaFmt<float> { static constexpr int v = 2; };
+template <> struct UmmaFmt<__nv_bfloat16> { static constexpr int v = 1; };
+template <> struct UmmaFmt<__half> { static constexpr int v = 0; };
+
 template <bool TF32>
 __device__ __forceinline__ void umma_ss(uint64_t da, uint64_t db, uint32_t tmem_d, uint32_t accumulate, uint32_t idesc) {
     if (TF32)
@@ -129,6 +136,26 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// eight fp32 -> eight 16-bit values (bf16: round to nearest; fp16: round to nearest, saturate)
+template <typename T> __device__ __forceinline__ uint4 pack8(const float* v);
+template <> __device__ __forceinline__ uint4 pack8<__nv_bfloat16>(const float* v) {
+    uint4 pk;
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+    pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+    pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+    return pk;
+}
+template <> __device__ __forceinline__ uint4 pack8<__half>(const float* v) {
+    uint4 pk;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk.x) : "f"(v[1]), "f"(v[0]));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk.y) : "f"(v[3]), "f"(v[2]));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk.z) : "f"(v[5]), "f"(v[4]));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk.w) : "f"(v[7]), "f"(v[6]));
+    return pk;
+}
+template <> __device__ __forceinline__ uint4 pack8<float>(const float*) { return make_uint4(0, 0, 0, 0); }
+
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(
@@ -157,7 +184,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     constexpr int UMMA_K = 32 / (int)sizeof(T);           // 16 / 8
     constexpr int B_STAGE = BLOCK_N * TC_ROW_BYTES;
     constexpr uint32_t STAGE_BYTES = TC_A_STAGE + B_STAGE;
-    constexpr uint32_t IDESC = umma_idesc(TF32 ? 2 : 1, TC_BM, BLOCK_N);
+    constexpr uint32_t IDESC = umma_idesc(UmmaFmt<T>::v, TC_BM, BLOCK_N);
     constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
     constexpr int TMEM_COLS = TC_NACC * ACC_COLS;         // power of two >= 64
 
@@ -293,14 +320,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                             *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + co0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            uint4 pk;
-                            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + co0 + j) = pk;
-                        }
+                        for (int j = 0; j < 32; j += 8)
+                            *reinterpret_cast<uint4*>(reinterpret_cast<T*>(out) + co0 + j) = pack8<T>(v + j);
                     }
                 } else {
 #pragma unroll
@@ -355,7 +376,7 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv_tc_halo_kernel(const __gr
     constexpr int BK = TC_ROW_BYTES / (int)sizeof(T);
     constexpr int UMMA_K = 32 / (int)sizeof(T);
     constexpr int B_TAP = BLOCK_N * TC_ROW_BYTES;         // bytes of one tap's weight tile
-    constexpr uint32_t IDESC = umma_idesc(TF32 ? 2 : 1, TC_BM, BLOCK_N);
+    constexpr uint32_t IDESC = umma_idesc(UmmaFmt<T>::v, TC_BM, BLOCK_N);
     constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
     constexpr int TMEM_COLS = TC_NACC * ACC_COLS;
     constexpr int MAXS = 8;
@@ -535,14 +556,8 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv_tc_halo_kernel(const __gr
                             *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + co0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            uint4 pk;
-                            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + co0 + j) = pk;
-                        }
+                        for (int j = 0; j < 32; j += 8)
+                            *reinterpret_cast<uint4*>(reinterpret_cast<T*>(out) + co0 + j) = pack8<T>(v + j);
                     }
                 } else {
 #pragma unroll
@@ -605,6 +620,7 @@ bool conv_tc_supported(const arseg_conv_desc* d) {
     const int bk = 128 / es;
     if (d->engine == ARSEG_CONV_TC_TF32 && d->dtype != ARSEG_F32) return false;
     if (d->engine == ARSEG_CONV_TC_BF16 && d->dtype != ARSEG_BF16) return false;
+    if (d->engine == ARSEG_CONV_TC_F16 && d->dtype != ARSEG_F16) return false;
     if (d->stride != 1) return false;
     if (d->Cin % bk != 0) return false;
     if (d->Cout < 16) return false;
@@ -695,8 +711,9 @@ int conv_tc_launch(const arseg_conv_desc* d, cudaStream_t st) {
     p.cout_pad = p.n_tiles * block_n;
     ARSEG_REQUIRE(p.cout_pad <= TC_MAX_COUT, "conv_tc: Cout=%d > %d", d->Cout, TC_MAX_COUT);
 
+    const bool f16 = d->engine == ARSEG_CONV_TC_F16;
     const CUtensorMapDataType dt = tf32 ? (tf32_tma_round() ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32)
-                                        : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+                                        : (f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
     CUtensorMap ma, mb;
     {
         cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->Wi, (cuuint64_t)d->Hi, (cuuint64_t)d->N};
@@ -727,6 +744,12 @@ int conv_tc_launch(const arseg_conv_desc* d, cudaStream_t st) {
             if (block_n == 64) return launch_tch<float, 64>(ma, mb, hp, st);
             return launch_tch<float, 32>(ma, mb, hp, st);
         }
+        if (f16) {
+            if (block_n == 256) return launch_tch<__half, 256>(ma, mb, hp, st);
+            if (block_n == 128) return launch_tch<__half, 128>(ma, mb, hp, st);
+            if (block_n == 64) return launch_tch<__half, 64>(ma, mb, hp, st);
+            return launch_tch<__half, 32>(ma, mb, hp, st);
+        }
         if (block_n == 256) return launch_tch<__nv_bfloat16, 256>(ma, mb, hp, st);
         if (block_n == 128) return launch_tch<__nv_bfloat16, 128>(ma, mb, hp, st);
         if (block_n == 64) return launch_tch<__nv_bfloat16, 64>(ma, mb, hp, st);
@@ -737,6 +760,12 @@ int conv_tc_launch(const arseg_conv_desc* d, cudaStream_t st) {
         if (block_n == 128) return launch_tc<float, 128, 6>(ma, mb, p, st);
         if (block_n == 64) return launch_tc<float, 64, 8>(ma, mb, p, st);
         return launch_tc<float, 32, 8>(ma, mb, p, st);
+    }
+    if (f16) {
+        if (block_n == 256) return launch_tc<__half, 256, 4>(ma, mb, p, st);
+        if (block_n == 128) return launch_tc<__half, 128, 6>(ma, mb, p, st);
+        if (block_n == 64) return launch_tc<__half, 64, 8>(ma, mb, p, st);
+        return launch_tc<__half, 32, 8>(ma, mb, p, st);
     }
     if (block_n == 256) return launch_tc<__nv_bfloat16, 256, 4>(ma, mb, p, st);
     if (block_n == 128) return launch_tc<__nv_bfloat16, 128, 6>(ma, mb, p, st);

@@ -313,6 +313,7 @@ template <int K>
 static int creff_launch_k(const CreffParams& p, int layout, int dtype, cudaStream_t st) {
     if (layout == ARSEG_NCHW) return creff_launch_t<K, ARSEG_NCHW, float>(p, st);
     if (dtype == ARSEG_F32) return creff_launch_t<K, ARSEG_NHWC, float>(p, st);
+    if (dtype == ARSEG_F16) return creff_launch_t<K, ARSEG_NHWC, __half>(p, st);
     return creff_launch_t<K, ARSEG_NHWC, __nv_bfloat16>(p, st);
 }
 
@@ -338,7 +339,7 @@ extern "C" int arseg_creff_fused_fwd(const arseg_creff_args* a, arseg_stream_t s
     }
     ARSEG_REQUIRE(a->lr_layout == ARSEG_NCHW || a->lr_layout == ARSEG_NHWC, "creff: lr layout %d", a->lr_layout);
     if (a->lr_layout == ARSEG_NCHW) ARSEG_REQUIRE(a->lr_dtype == ARSEG_F32, "creff: NCHW lr must be fp32");
-    else ARSEG_REQUIRE(a->lr_dtype == ARSEG_F32 || a->lr_dtype == ARSEG_BF16, "creff: lr dtype %d", a->lr_dtype);
+    else ARSEG_REQUIRE(a->lr_dtype == ARSEG_F32 || a->lr_dtype == ARSEG_BF16 || a->lr_dtype == ARSEG_F16, "creff: lr dtype %d", a->lr_dtype);
     cudaStream_t st = as_stream(stream);
     if (a->engine == ARSEG_CREFF_MMA_F16) {
         if (!creff_mma_supported(a))

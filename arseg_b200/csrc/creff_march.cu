@@ -794,18 +794,24 @@ static int creff_march_launch_t(CreffMmaParams& p, cudaStream_t st) {
     return creff_march_launch_n<K, TLR, 4>(p, st);
 }
 
-int creff_march_launch(CreffMmaParams& p, int k, bool lr_bf16, cudaStream_t st) {
+template <int K>
+static int creff_march_launch_k(CreffMmaParams& p, int lr_dtype, cudaStream_t st) {
+    if (lr_dtype == ARSEG_BF16) return creff_march_launch_t<K, __nv_bfloat16>(p, st);
+    if (lr_dtype == ARSEG_F16) return creff_march_launch_t<K, __half>(p, st);
+    return creff_march_launch_t<K, float>(p, st);
+}
+
+int creff_march_launch(CreffMmaParams& p, int k, int lr_dtype, cudaStream_t st) {
     switch (k) {
-        case 3: return lr_bf16 ? creff_march_launch_t<3, __nv_bfloat16>(p, st) : creff_march_launch_t<3, float>(p, st);
-        case 5: return lr_bf16 ? creff_march_launch_t<5, __nv_bfloat16>(p, st) : creff_march_launch_t<5, float>(p, st);
-        case 7: return lr_bf16 ? creff_march_launch_t<7, __nv_bfloat16>(p, st) : creff_march_launch_t<7, float>(p, st);
-        case 9: return lr_bf16 ? creff_march_launch_t<9, __nv_bfloat16>(p, st) : creff_march_launch_t<9, float>(p, st);
+        case 3: return creff_march_launch_k<3>(p, lr_dtype, st);
+        case 5: return creff_march_launch_k<5>(p, lr_dtype, st);
+        case 7: return creff_march_launch_k<7>(p, lr_dtype, st);
+        case 9: return creff_march_launch_k<9>(p, lr_dtype, st);
         default: ARSEG_UNSUPPORTED("creff_march: window k=%d", k);
     }
 }
 
 }  // namespace arseg
-
 #ifdef ARSEG_XTRACE
 extern "C" int arseg_debug_creff_trace(long long* host, int cap) {
     const int n = cap < arseg::XTRACE_N ? cap : arseg::XTRACE_N;

@@ -545,7 +545,7 @@ bool creff_mma_supported(const arseg_creff_args* a) {
            (!a->wcls || a->ncls <= 32) && ((size_t)a->H * a->W < (1u << 29)) && ((size_t)a->h * a->w < (1u << 29));
 }
 
-int creff_march_launch(CreffMmaParams& p, int k, bool lr_bf16, cudaStream_t st);   // creff_march.cu
+int creff_march_launch(CreffMmaParams& p, int k, int lr_dtype, cudaStream_t st);   // creff_march.cu
 
 // ARSEG_CREFF_MMA_F16 runs the column-marching engine (creff_march.cu); ARSEG_CREFF_TILE=1 selects the older
 // square-tile engine of this file (kept for A/B measurements).
@@ -562,7 +562,7 @@ int creff_mma_launch(const arseg_creff_args* a, cudaStream_t st) {
     p.ncls = a->ncls; p.log_softmax = a->log_softmax; p.out_p = a->out_p; p.out_logits = a->out_logits;
     p.out_argmax = a->out_argmax; p.N = a->N; p.C = a->C; p.H = a->H; p.W = a->W;
     const bool bf = a->lr_dtype == ARSEG_BF16;
-    if (!use_tile_engine()) return creff_march_launch(p, a->k, bf, st);
+    if (!use_tile_engine() || a->lr_dtype == ARSEG_F16) return creff_march_launch(p, a->k, a->lr_dtype, st);
     switch (a->k) {
         case 3: return bf ? creff_mma_launch_t<3, __nv_bfloat16>(p, st) : creff_mma_launch_t<3, float>(p, st);
         case 5: return bf ? creff_mma_launch_t<5, __nv_bfloat16>(p, st) : creff_mma_launch_t<5, float>(p, st);

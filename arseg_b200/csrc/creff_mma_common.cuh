@@ -156,6 +156,15 @@ __device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
     return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
                        __uint_as_float(u.y & 0xffff0000u));
 }
+__device__ __forceinline__ float4 ld4(const __half* p) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ float2 ld2(const __half* p) {
+    const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(p));
+    return __half22float2(*reinterpret_cast<const __half2*>(&u));
+}
 // (lo, hi) -> packed f16x2 with saturation to +-65504 (one F2FP.SATFINITE)
 __device__ __forceinline__ uint32_t pack_h2_sat(float lo, float hi) {
     uint32_t r;

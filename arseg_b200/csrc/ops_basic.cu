@@ -313,6 +313,8 @@ int arseg_nchw_to_nhwc(const float* src, void* dst, int dst_dtype, int N, int C,
         transpose_kernel<float, float><<<grid, block, 0, as_stream(stream)>>>(src, (float*)dst, C, H * W);
     else if (dst_dtype == ARSEG_BF16)
         transpose_kernel<float, __nv_bfloat16><<<grid, block, 0, as_stream(stream)>>>(src, (__nv_bfloat16*)dst, C, H * W);
+    else if (dst_dtype == ARSEG_F16)
+        transpose_kernel<float, __half><<<grid, block, 0, as_stream(stream)>>>(src, (__half*)dst, C, H * W);
     else ARSEG_UNSUPPORTED("nchw_to_nhwc: dtype %d", dst_dtype);
     ARSEG_CHECK_LAUNCH("nchw_to_nhwc");
     return ARSEG_OK;
@@ -326,6 +328,8 @@ int arseg_nhwc_to_nchw(const void* src, int src_dtype, float* dst, int N, int C,
         transpose_kernel<float, float><<<grid, block, 0, as_stream(stream)>>>((const float*)src, dst, H * W, C);
     else if (src_dtype == ARSEG_BF16)
         transpose_kernel<__nv_bfloat16, float><<<grid, block, 0, as_stream(stream)>>>((const __nv_bfloat16*)src, dst, H * W, C);
+    else if (src_dtype == ARSEG_F16)
+        transpose_kernel<__half, float><<<grid, block, 0, as_stream(stream)>>>((const __half*)src, dst, H * W, C);
     else ARSEG_UNSUPPORTED("nhwc_to_nchw: dtype %d", src_dtype);
     ARSEG_CHECK_LAUNCH("nhwc_to_nchw");
     return ARSEG_OK;
@@ -366,6 +370,15 @@ int arseg_resize_nhwc(const void* src, void* dst, int dtype, int N, int Hi, int 
             long long total = (long long)N * Ho * Wo * C;
             resize_nhwc_kernel<__nv_bfloat16, 1><<<grid_1d(total, 256), 256, 0, st>>>(s, d, N, Hi, Wi, C, Ho, Wo, dcs, dco, mode, sh, sw);
         }
+    } else if (dtype == ARSEG_F16) {
+        const __half* s = (const __half*)src; __half* d = (__half*)dst;
+        if (C % 8 == 0 && dcs % 8 == 0 && dco % 8 == 0 && ((uintptr_t)s % 16 == 0) && ((uintptr_t)d % 16 == 0)) {
+            long long total = (long long)N * Ho * Wo * (C / 8);
+            resize_nhwc_kernel<__half, 8><<<grid_1d(total, 256), 256, 0, st>>>(s, d, N, Hi, Wi, C, Ho, Wo, dcs, dco, mode, sh, sw);
+        } else {
+            long long total = (long long)N * Ho * Wo * C;
+            resize_nhwc_kernel<__half, 1><<<grid_1d(total, 256), 256, 0, st>>>(s, d, N, Hi, Wi, C, Ho, Wo, dcs, dco, mode, sh, sw);
+        }
     } else ARSEG_UNSUPPORTED("resize_nhwc: dtype %d", dtype);
     ARSEG_CHECK_LAUNCH("resize_nhwc");
     return ARSEG_OK;
@@ -381,6 +394,8 @@ int arseg_adaptive_avgpool_nhwc(const void* in, void* out, int dtype, int out_dt
         adaptive_pool_kernel<float, false><<<grid, block, 0, as_stream(stream)>>>((const float*)in, out, N, H, W, C, Ho, Wo, of32);
     else if (dtype == ARSEG_BF16)
         adaptive_pool_kernel<__nv_bfloat16, false><<<grid, block, 0, as_stream(stream)>>>((const __nv_bfloat16*)in, out, N, H, W, C, Ho, Wo, of32);
+    else if (dtype == ARSEG_F16)
+        adaptive_pool_kernel<__half, false><<<grid, block, 0, as_stream(stream)>>>((const __half*)in, out, N, H, W, C, Ho, Wo, of32);
     else ARSEG_UNSUPPORTED("adaptive_avgpool: dtype %d", dtype);
     ARSEG_CHECK_LAUNCH("adaptive_avgpool");
     return ARSEG_OK;
@@ -393,6 +408,8 @@ int arseg_global_maxpool_nhwc(const void* in, float* out, int dtype, int N, int 
         adaptive_pool_kernel<float, true><<<grid, block, 0, as_stream(stream)>>>((const float*)in, out, N, H, W, C, 1, 1, 1);
     else if (dtype == ARSEG_BF16)
         adaptive_pool_kernel<__nv_bfloat16, true><<<grid, block, 0, as_stream(stream)>>>((const __nv_bfloat16*)in, out, N, H, W, C, 1, 1, 1);
+    else if (dtype == ARSEG_F16)
+        adaptive_pool_kernel<__half, true><<<grid, block, 0, as_stream(stream)>>>((const __half*)in, out, N, H, W, C, 1, 1, 1);
     else ARSEG_UNSUPPORTED("global_maxpool: dtype %d", dtype);
     ARSEG_CHECK_LAUNCH("global_maxpool");
     return ARSEG_OK;
@@ -419,6 +436,10 @@ int arseg_gate_nhwc(const void* feat, const float* gate, const float* gs, const 
         gate_kernel<__nv_bfloat16><<<grid_1d(total, 256), 256, 0, as_stream(stream)>>>(
             (const __nv_bfloat16*)feat, gate, gs, gb, add_identity, add_chan, (const __nv_bfloat16*)add_pix,
             (__nv_bfloat16*)out, N, (long long)H * W, C);
+    else if (dtype == ARSEG_F16)
+        gate_kernel<__half><<<grid_1d(total, 256), 256, 0, as_stream(stream)>>>(
+            (const __half*)feat, gate, gs, gb, add_identity, add_chan, (const __half*)add_pix,
+            (__half*)out, N, (long long)H * W, C);
     else ARSEG_UNSUPPORTED("gate: dtype %d", dtype);
     ARSEG_CHECK_LAUNCH("gate");
     return ARSEG_OK;
@@ -444,6 +465,14 @@ int arseg_maxpool3x3s2_nhwc(const void* in, void* out, int dtype, int N, int H, 
             long long total = (long long)N * Ho * Wo * C;
             maxpool_kernel<__nv_bfloat16, 1><<<grid_1d(total, 256), 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, N, H, W, C, Ho, Wo);
         }
+    } else if (dtype == ARSEG_F16) {
+        if (C % 8 == 0) {
+            long long total = (long long)N * Ho * Wo * (C / 8);
+            maxpool_kernel<__half, 8><<<grid_1d(total, 256), 256, 0, st>>>((const __half*)in, (__half*)out, N, H, W, C, Ho, Wo);
+        } else {
+            long long total = (long long)N * Ho * Wo * C;
+            maxpool_kernel<__half, 1><<<grid_1d(total, 256), 256, 0, st>>>((const __half*)in, (__half*)out, N, H, W, C, Ho, Wo);
+        }
     } else ARSEG_UNSUPPORTED("maxpool: dtype %d", dtype);
     ARSEG_CHECK_LAUNCH("maxpool");
     return ARSEG_OK;
@@ -459,6 +488,8 @@ int arseg_conv_stem7x7s2(const float* in, const float* w, const float* scale, co
         stem_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(in, w, scale, shift, (float*)out, H, W, Ho, Wo, Cout);
     else if (out_dtype == ARSEG_BF16)
         stem_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(in, w, scale, shift, (__nv_bfloat16*)out, H, W, Ho, Wo, Cout);
+    else if (out_dtype == ARSEG_F16)
+        stem_kernel<__half><<<grid, 256, 0, as_stream(stream)>>>(in, w, scale, shift, (__half*)out, H, W, Ho, Wo, Cout);
     else ARSEG_UNSUPPORTED("stem: dtype %d", out_dtype);
     ARSEG_CHECK_LAUNCH("stem");
     return ARSEG_OK;

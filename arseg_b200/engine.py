@@ -8,6 +8,8 @@ and records the launches as pre-bound ctypes calls.  `Plan.run()` replays them o
 Precision modes
   'fp32' : fp32 NHWC activations, SIMT implicit-GEMM convs (exact fp32 FMA; the parity gate)
   'tf32' : fp32 NHWC activations, tcgen05 kind::tf32 convs (what cuDNN does for the reference on Ampere+)
+  'f16'  : fp16 NHWC activations and weights (11-bit significand = TF32's, saturating at +-65504), tcgen05 kind::f16
+           convs at twice the TF32 rate, fp32 accumulate / epilogue
   'bf16' : bf16 NHWC activations, tcgen05 kind::f16 convs, fp32 accumulate / epilogue
 Layers the tcgen05 engine does not take (stride 2, Cout < 16, tiny spatial extents) run on the SIMT engine
 in the same dtype.
@@ -31,6 +33,7 @@ SD = Dict[str, torch.Tensor]
 _PRECISIONS = {
     "fp32": (torch.float32, L.CONV_SIMT_F32),
     "tf32": (torch.float32, L.CONV_TC_TF32),
+    "f16": (torch.float16, L.CONV_TC_F16),
     "bf16": (torch.bfloat16, L.CONV_TC_BF16),
 }
 
@@ -105,7 +108,7 @@ class Plan:
                        out.shape[-1], coff, act, float(slope), engine)
         self.keep.append(d)
         fn = self.lib.arseg_conv2d_nhwc
-        self._add("%s[%s %dx%d %d->%d @%dx%d]" % (name, {1: "simt", 2: "tf32", 3: "bf16"}[engine], KH, KW, Cin, Cout, Ho, Wo),
+        self._add("%s[%s %dx%d %d->%d @%dx%d]" % (name, {1: "simt", 2: "tf32", 3: "bf16", 4: "f16"}[engine], KH, KW, Cin, Cout, Ho, Wo),
                   lambda s, d=d: fn(C.byref(d), s))
         self.conv_flops += 2 * N * Ho * Wo * Cout * Cin * KH * KW
         return out

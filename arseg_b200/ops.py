@@ -9,7 +9,7 @@ import torch
 
 from . import _lib as L
 
-_TORCH2ARSEG = {torch.float32: L.F32, torch.bfloat16: L.BF16, torch.float64: L.F64, torch.int16: L.I16}
+_TORCH2ARSEG = {torch.float32: L.F32, torch.bfloat16: L.BF16, torch.float64: L.F64, torch.int16: L.I16, torch.float16: L.F16}
 
 
 def _stream() -> int:

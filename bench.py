@@ -131,7 +131,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("ARSEG_PRECISION", "tf32"), choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("ARSEG_PRECISION", "tf32"), choices=["fp32", "tf32", "f16", "bf16"])
     ap.add_argument("--shard", default="gop", choices=["gop", "frame"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="also print the per-kernel time table to stderr")
@@ -243,9 +243,9 @@ def main():
     hbm_peak, tc_burst, tc_sust, peak_src = peaks()
     t_all = sum(t for _, t in prof)
     creff_ms = sum(t for n, t in prof if n.startswith("creff"))
-    tc_ms = sum(t for n, t in prof if "[tf32" in n or "[bf16" in n)
+    tc_ms = sum(t for n, t in prof if "[tf32" in n or "[bf16" in n or "[f16" in n)
     simt_ms = sum(t for n, t in prof if "[simt" in n)
-    lr_bytes = 2 if args.precision == "bf16" else 4
+    lr_bytes = 2 if args.precision in ("bf16", "f16") else 4
     cbytes = creff_bytes(lr_bytes, write_p=False, write_logits=True) * n_local
     creff_gbs = cbytes / (creff_ms * 1e-3) / 1e9 if creff_ms > 0 else 0.0
     creff_gbs_full = CREFF_BYTES_FULL * n_local / (creff_ms * 1e-3) / 1e9 if creff_ms > 0 else 0.0
@@ -274,7 +274,7 @@ def main():
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
         "scaling": "strong" if args.shard == "frame" else "weak", "vs_baseline": None,
-        "dtype": {"fp32": "f32", "tf32": "tf32 (fp32 storage, fp32 accumulate)", "bf16": "bf16 (fp32 accumulate)"}[args.precision],
+        "dtype": {"fp32": "f32", "tf32": "tf32 (fp32 storage, fp32 accumulate)", "f16": "f16 (fp16 storage: 11-bit significand as TF32, fp32 accumulate)", "bf16": "bf16 (fp32 accumulate)"}[args.precision],
         "data": "synthetic (seeded randn frames, block-constant int16 quarter-pel MV fields, name-keyed random weights)",
         "config": {"workload": "CamVid 720x960 GOP-12 PSPNet-18 AR-0.5x, k=7: 11 non-keyframes per step per rank (BASELINE configs[1])",
                    "frames_per_step_per_rank": n_local, "shard": args.shard, "precision": args.precision,

@@ -13,7 +13,7 @@
  *   - Return value: 0 = ARSEG_OK, negative = error; arseg_last_error() returns a thread-local message.
  *     Nothing throws across the boundary.
  *   - "NCHW" tensors are the reference's API layout (fp32, contiguous); "NHWC" tensors are the internal
- *     activation layout (`dtype` = ARSEG_F32 or ARSEG_BF16).
+ *     activation layout (`dtype` = ARSEG_F32, ARSEG_F16 or ARSEG_BF16).
  */
 #ifndef ARSEG_H_
 #define ARSEG_H_
@@ -27,13 +27,13 @@ extern "C" {
 #define ARSEG_ABI_VERSION 2
 
 enum { ARSEG_OK = 0, ARSEG_E_BADARG = -1, ARSEG_E_UNSUPPORTED = -2, ARSEG_E_CUDA = -3 };
-enum { ARSEG_F32 = 0, ARSEG_BF16 = 1, ARSEG_F64 = 2, ARSEG_I16 = 3 };
+enum { ARSEG_F32 = 0, ARSEG_BF16 = 1, ARSEG_F64 = 2, ARSEG_I16 = 3, ARSEG_F16 = 4 };
 enum { ARSEG_ACT_NONE = 0, ARSEG_ACT_RELU = 1, ARSEG_ACT_PRELU = 2 };
 /* resize modes: bilinear align_corners=False / True, legacy nearest */
 enum { ARSEG_RESIZE_BILINEAR = 0, ARSEG_RESIZE_BILINEAR_AC = 1, ARSEG_RESIZE_NEAREST = 2 };
 enum { ARSEG_NCHW = 0, ARSEG_NHWC = 1 };
 /* convolution engines: SIMT fp32 (exact-order fp32 FMA), tcgen05 kind::tf32, tcgen05 kind::f16 (bf16) */
-enum { ARSEG_CONV_SIMT_F32 = 1, ARSEG_CONV_TC_TF32 = 2, ARSEG_CONV_TC_BF16 = 3 };
+enum { ARSEG_CONV_SIMT_F32 = 1, ARSEG_CONV_TC_TF32 = 2, ARSEG_CONV_TC_BF16 = 3, ARSEG_CONV_TC_F16 = 4 };
 /* CReFF engines: exact fp32 SIMT (any C, NCHW hr), or tensor-core window attention (mma.sync f16 operands with
  * fp32 accumulate -- TF32-class error; C = 64, NHWC hr and lr) */
 enum { ARSEG_CREFF_EXACT_F32 = 0, ARSEG_CREFF_MMA_F16 = 1 };
@@ -104,12 +104,12 @@ int arseg_maxpool3x3s2_nhwc(const void* in, void* out, int dtype, int N, int H, 
 
 typedef struct arseg_conv_desc {
     const void* in;        /* NHWC [N,Hi,Wi,Cin], dtype `dtype` */
-    const void* w;         /* [Cout][KH][KW][Cin], same dtype as `in` (fp32 for SIMT/TF32, bf16 for BF16) */
+    const void* w;         /* [Cout][KH][KW][Cin], same dtype as `in` (fp32 for SIMT/TF32, fp16 / bf16 for F16 / BF16) */
     const float* scale;    /* [Cout] folded BN scale, or NULL (=1) */
     const float* shift;    /* [Cout] folded BN shift + bias, or NULL (=0) */
     const void* residual;  /* NHWC [N,Ho,Wo,Cout] (dense), added before the activation, or NULL */
     void* out;             /* NHWC [N,Ho,Wo,out_cstride] written at channel offset out_coff */
-    int dtype;             /* ARSEG_F32 | ARSEG_BF16 (in, w, residual, out) */
+    int dtype;             /* ARSEG_F32 | ARSEG_F16 | ARSEG_BF16 (in, w, residual, out) */
     int N, Hi, Wi, Cin, Cout, KH, KW, stride, pad, dil;
     int out_cstride, out_coff;
     int act;               /* ARSEG_ACT_* */

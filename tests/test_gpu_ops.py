@@ -163,15 +163,16 @@ TC_CASES = [c for c in CONV_CASES if c[6] == 1 and c[2] >= 16] + [
 
 
 @pytest.mark.parametrize("case", TC_CASES)
-@pytest.mark.parametrize("engine,dtype,tol", [(L.CONV_TC_TF32, torch.float32, 2e-3), (L.CONV_TC_BF16, torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("engine,dtype,tol", [(L.CONV_TC_TF32, torch.float32, 2e-3), (L.CONV_TC_F16, torch.float16, 2e-3),
+                                              (L.CONV_TC_BF16, torch.bfloat16, 2e-2)])
 def test_conv_tcgen05(case, engine, dtype, tol):
     N, Ci, Co, H, W, k, s, p, d, has_res, act = case
     x, w = rnd(N, Ci, H, W, seed=30), rnd(Co, Ci, k, k, seed=31) * (1.0 / (Ci * k * k) ** 0.5)
     scale, shift = torch.rand(Co) + 0.5, rnd(Co, seed=32) * 0.1
     res = rnd(N, Co, H, W, seed=33) if has_res else None
-    if dtype == torch.bfloat16:   # reference on the bf16-rounded operands: isolates accumulation error
-        x, w = x.bfloat16().float(), w.bfloat16().float()
-        res = res.bfloat16().float() if res is not None else None
+    if dtype != torch.float32:    # reference on the 16-bit-rounded operands: isolates accumulation error
+        x, w = x.to(dtype).float(), w.to(dtype).float()
+        res = res.to(dtype).float() if res is not None else None
     ref = conv_ref(x, w, scale, shift, res, s, p, d, act, 0.25)
     got = run_conv(x, w, scale, shift, res, s, p, d, act, 0.25, engine, dtype)
     assert got.shape == ref.shape
@@ -298,7 +299,7 @@ def test_creff_mma_prewarped(k, H, W, h, w):
 
 @pytest.mark.parametrize("flow_kind", ["i16", "f64"])
 @pytest.mark.parametrize("stride", [1, 8])
-@pytest.mark.parametrize("lr_dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("lr_dtype", [torch.float32, torch.bfloat16, torch.float16])
 def test_creff_mma_with_mv_warp_and_classifier(flow_kind, stride, lr_dtype):
     from arseg_b200 import synth
     C, ncls, k = 64, 12, 7
@@ -306,8 +307,8 @@ def test_creff_mma_with_mv_warp_and_classifier(flow_kind, stride, lr_dtype):
     H, W, h, w = Hm // stride, Wm // stride, Hm // stride // 2, Wm // stride // 2
     sd = creff_sd(C)
     hr, lr = rnd(1, C, H, W, seed=53) * 0.6, rnd(2, C, h, w, seed=54) * 0.4
-    if lr_dtype == torch.bfloat16:
-        lr = lr.bfloat16().float()
+    if lr_dtype != torch.float32:
+        lr = lr.to(lr_dtype).float()
     wcls, bcls = rnd(ncls, C, seed=55) * 0.2, rnd(ncls, seed=56) * 0.1
     mvs = np.stack([synth.synth_mv_int16(Hm, Wm, 60 + i, distance=5 + 3 * i) for i in range(2)])
     flow64 = torch.from_numpy(mvs.astype(np.float64) / 4.0)
