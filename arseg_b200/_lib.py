@@ -18,7 +18,7 @@ RESIZE_BILINEAR, RESIZE_BILINEAR_AC, RESIZE_NEAREST = 0, 1, 2
 NCHW, NHWC = 0, 1
 CONV_SIMT_F32, CONV_TC_TF32, CONV_TC_BF16, CONV_TC_F16 = 1, 2, 3, 4
 CREFF_EXACT_F32, CREFF_MMA_F16 = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 vp, ci, cf = C.c_void_p, C.c_int, C.c_float
 
@@ -27,7 +27,7 @@ class ConvDesc(C.Structure):
     _fields_ = [("inp", vp), ("w", vp), ("scale", vp), ("shift", vp), ("residual", vp), ("out", vp),
                 ("dtype", ci), ("N", ci), ("Hi", ci), ("Wi", ci), ("Cin", ci), ("Cout", ci), ("KH", ci), ("KW", ci),
                 ("stride", ci), ("pad", ci), ("dil", ci), ("out_cstride", ci), ("out_coff", ci), ("act", ci),
-                ("prelu_slope", cf), ("engine", ci)]
+                ("prelu_slope", cf), ("engine", ci), ("out_f32", ci)]
 
 
 class CreffArgs(C.Structure):

@@ -171,6 +171,7 @@ extern "C" int arseg_conv2d_nhwc(const arseg_conv_desc* d, arseg_stream_t stream
     ARSEG_REQUIRE(d->out_cstride >= d->Cout && d->out_coff >= 0 && d->out_coff + d->Cout <= d->out_cstride,
                   "conv2d: bad output slice (cstride=%d coff=%d Cout=%d)", d->out_cstride, d->out_coff, d->Cout);
     ARSEG_REQUIRE(d->act >= ARSEG_ACT_NONE && d->act <= ARSEG_ACT_PRELU, "conv2d: bad act %d", d->act);
+    ARSEG_REQUIRE(!d->out_f32 || d->dtype == ARSEG_F32 || d->engine != ARSEG_CONV_SIMT_F32, "conv2d: out_f32 needs a tcgen05 engine");
     switch (d->engine) {
         case ARSEG_CONV_SIMT_F32:
             return conv_simt_launch(d, as_stream(stream));

@@ -35,6 +35,7 @@ struct TcParams {
     float slope;
     int TH, TW, tiles_x, tiles_y, n_tiles, kchunks;  // kchunks = Cin / BK
     int cout_pad;                                    // Cout rounded up to the n-tile size (scale/shift staging)
+    int out_f32;                                     // fp32 output from 16-bit operands
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -289,6 +290,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const bool valid = gy < p.Ho && gx < p.Wo;
             const size_t pix = ((size_t)img * p.Ho + gy) * p.Wo + gx;
             T* __restrict__ out = reinterpret_cast<T*>(p.out) + pix * p.ocs + p.oco;
+            float* __restrict__ outf = reinterpret_cast<float*>(p.out) + pix * p.ocs + p.oco;   // p.out_f32
             const T* __restrict__ res = p.res ? reinterpret_cast<const T*>(p.res) + pix * p.Cout : nullptr;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
@@ -313,7 +315,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     else if (p.act == ARSEG_ACT_PRELU) a = a > 0.f ? a : a * p.slope;
                     v[j] = a;
                 }
-                if (co0 + 32 <= p.Cout && ((p.ocs | p.oco) % (16 / (int)sizeof(T)) == 0)) {
+                if (!TF32 && p.out_f32) {
+                    if (co0 + 32 <= p.Cout && ((p.ocs | p.oco) % 4 == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(outf + co0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (co0 + j < p.Cout) outf[co0 + j] = v[j];
+                    }
+                } else if (co0 + 32 <= p.Cout && ((p.ocs | p.oco) % (16 / (int)sizeof(T)) == 0)) {
                     if (TF32) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4)
@@ -512,6 +523,7 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv_tc_halo_kernel(const __gr
             const bool valid = gy < p.Ho && gx < p.Wo;
             const size_t pix = ((size_t)img * p.Ho + gy) * p.Wo + gx;
             T* __restrict__ out = reinterpret_cast<T*>(p.out) + pix * p.ocs + p.oco;
+            float* __restrict__ outf = reinterpret_cast<float*>(p.out) + pix * p.ocs + p.oco;   // p.out_f32
             const T* __restrict__ res = p.res ? reinterpret_cast<const T*>(p.res) + pix * p.Cout : nullptr;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
@@ -549,7 +561,16 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv_tc_halo_kernel(const __gr
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
                 }
-                if (vec) {
+                if (!TF32 && p.out_f32) {
+                    if (co0 + 32 <= p.Cout && ((p.ocs | p.oco) % 4 == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(outf + co0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (co0 + j < p.Cout) outf[co0 + j] = v[j];
+                    }
+                } else if (vec) {
                     if (TF32) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4)
@@ -700,6 +721,7 @@ int conv_tc_launch(const arseg_conv_desc* d, cudaStream_t st) {
     TcParams p;
     p.scale = d->scale; p.shift = d->shift; p.res = d->residual; p.out = d->out;
     p.N = d->N; p.Ho = d->Hi; p.Wo = d->Wi; p.Cin = d->Cin; p.Cout = d->Cout; p.KH = d->KH; p.KW = d->KW;
+    p.out_f32 = (d->out_f32 && d->dtype != ARSEG_F32) ? 1 : 0;
     p.pad = d->pad; p.dil = d->dil; p.ocs = d->out_cstride; p.oco = d->out_coff; p.act = d->act; p.slope = d->prelu_slope;
     const bool halo = d->KH == 3 && d->KW == 3 && d->pad == d->dil && d->dil >= 1 && d->dil <= 8 && env_int("ARSEG_TC_HALO", 1) != 0;
     if (halo) { p.TH = TCH_TH; p.TW = TCH_TW; } else pick_tile(p.Ho, p.Wo, p.TH, p.TW);

@@ -86,7 +86,7 @@ class Plan:
 
     # -- ops -----------------------------------------------------------------------------------
     def conv(self, x: torch.Tensor, w_oihw: torch.Tensor, scale=None, shift=None, *, stride=1, pad=0, dil=1,
-             act=L.ACT_NONE, slope=0.0, residual=None, out=None, coff=0, name="conv") -> torch.Tensor:
+             act=L.ACT_NONE, slope=0.0, residual=None, out=None, coff=0, name="conv", out_f32=False) -> torch.Tensor:
         N, Hi, Wi, Cin = x.shape
         Cout, _, KH, KW = w_oihw.shape
         Ho = (Hi + 2 * pad - dil * (KH - 1) - 1) // stride + 1
@@ -94,18 +94,20 @@ class Plan:
         w = self.conv_weight(w_oihw)
         sc = self.dev(scale, torch.float32) if scale is not None else None
         sh = self.dev(shift, torch.float32) if shift is not None else None
-        if out is None:
-            out = self.empty((N, Ho, Wo, Cout))
         engine = self.engine
         es = 4 if self.act_dtype == torch.float32 else 2
         tc_ok = (engine != L.CONV_SIMT_F32 and stride == 1 and Cin % (128 // es) == 0 and Cout >= 16
                  and Ho == Hi and Wo == Wi and Hi * Wi >= 64)
         if not tc_ok:
             engine = L.CONV_SIMT_F32
+        # out_f32: fp32 output from a 16-bit plan (tcgen05 engines only; other plans / engines ignore the request)
+        out_f32 = bool(out_f32 and tc_ok and self.act_dtype != torch.float32)
+        if out is None:
+            out = self.empty((N, Ho, Wo, Cout), torch.float32 if out_f32 else None)
         d = L.ConvDesc(x.data_ptr(), w.data_ptr(), sc.data_ptr() if sc is not None else None,
                        sh.data_ptr() if sh is not None else None, residual.data_ptr() if residual is not None else None,
                        out.data_ptr(), dtype_code(self.act_dtype), N, Hi, Wi, Cin, Cout, KH, KW, stride, pad, dil,
-                       out.shape[-1], coff, act, float(slope), engine)
+                       out.shape[-1], coff, act, float(slope), engine, 1 if out_f32 else 0)
         self.keep.append(d)
         fn = self.lib.arseg_conv2d_nhwc
         self._add("%s[%s %dx%d %d->%d @%dx%d]" % (name, {1: "simt", 2: "tf32", 3: "bf16", 4: "f16"}[engine], KH, KW, Cin, Cout, Ho, Wo),
@@ -379,8 +381,9 @@ def build_psp_phase1(pl: Plan, sd: SD, x_nchw: torch.Tensor, p: str = "", sizes=
         Nn, hh, ww, _ = t.shape
         t = pl.resize(t, 2 * hh, 2 * ww, L.RESIZE_BILINEAR, name=u + "upsample")
         sc, sh = fold_bn(sd, p + u + "conv.1.", sd[p + u + "conv.0.bias"])
+        # up_3 produces the LR feature p: kept fp32 in 16-bit plans (it is the residual of the CReFF kernel)
         t = pl.conv(t, sd[p + u + "conv.0.weight"], sc, sh, pad=1, act=L.ACT_PRELU,
-                    slope=float(sd[p + u + "conv.2.weight"].reshape(-1)[0]), name=u + "conv")
+                    slope=float(sd[p + u + "conv.2.weight"].reshape(-1)[0]), name=u + "conv", out_f32=(u == "up_3."))
     cls = None
     if aux:                                                         # model/pspnet.py:215-217
         a = pl.gmaxpool(x3)

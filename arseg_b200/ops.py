@@ -179,7 +179,8 @@ def conv2d_nhwc(x, w, scale=None, shift=None, residual=None, stride=1, pad=0, di
     if out is None:
         out = torch.empty((N, Ho, Wo, Cout), dtype=x.dtype, device=x.device)
     d = L.ConvDesc(_p(x), _p(w), _p(scale), _p(shift), _p(residual), _p(out), dtype_code(x.dtype), N, Hi, Wi, Cin, Cout,
-                   KH, KW, stride, pad, dil, out.shape[-1], out_coff, act, float(slope), engine)
+                   KH, KW, stride, pad, dil, out.shape[-1], out_coff, act, float(slope), engine,
+                   1 if (out.dtype == torch.float32 and x.dtype != torch.float32) else 0)
     with torch.cuda.device(x.device):
         L.check(L.load().arseg_conv2d_nhwc(C.byref(d), _stream()), "conv2d_nhwc")
     return out

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define ARSEG_ABI_VERSION 2
+#define ARSEG_ABI_VERSION 3
 
 enum { ARSEG_OK = 0, ARSEG_E_BADARG = -1, ARSEG_E_UNSUPPORTED = -2, ARSEG_E_CUDA = -3 };
 enum { ARSEG_F32 = 0, ARSEG_BF16 = 1, ARSEG_F64 = 2, ARSEG_I16 = 3, ARSEG_F16 = 4 };
@@ -115,6 +115,8 @@ typedef struct arseg_conv_desc {
     int act;               /* ARSEG_ACT_* */
     float prelu_slope;
     int engine;            /* ARSEG_CONV_* */
+    int out_f32;           /* 1: `out` is fp32 although dtype is a 16-bit type (the LR feature p handed to the CReFF
+                              kernel stays fp32: it is the residual of model/attention.py:210); tcgen05 engines only */
 } arseg_conv_desc;
 /* nn.Conv2d (+BatchNorm2d eval) (+residual) (+ReLU/PReLU) as one implicit-GEMM kernel */
 int arseg_conv2d_nhwc(const arseg_conv_desc* d, arseg_stream_t stream);
