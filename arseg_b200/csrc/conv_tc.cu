@@ -34,6 +34,7 @@ struct TcParams {
     int N, Ho, Wo, Cin, Cout, KH, KW, pad, dil, ocs, oco, act;
     float slope;
     int TH, TW, tiles_x, tiles_y, n_tiles, kchunks;  // kchunks = Cin / BK
+    int stride;                                      // 1 or 2 (tap-box kernel only: TMA element strides)
     int cout_pad;                                    // Cout rounded up to the n-tile size (scale/shift staging)
     int out_f32;                                     // fp32 output from 16-bit operands
 };
@@ -241,8 +242,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 for (int it = 0; it < kiters; ++it) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-                    tma_load_4d(&map_a, &full_bar[stage], smem_a + stage * TC_A_STAGE, kc * BK, x0 - p.pad + kx * p.dil,
-                                y0 - p.pad + ky * p.dil, img);
+                    tma_load_4d(&map_a, &full_bar[stage], smem_a + stage * TC_A_STAGE, kc * BK, x0 * p.stride - p.pad + kx * p.dil,
+                                y0 * p.stride - p.pad + ky * p.dil, img);
                     tma_load_2d(&map_b, &full_bar[stage], smem_b + stage * B_STAGE, tap * p.Cin + kc * BK, n0);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     if (++kc == p.kchunks) { kc = 0; ++tap; if (++kx == p.KW) { kx = 0; ++ky; } }
@@ -642,11 +643,11 @@ bool conv_tc_supported(const arseg_conv_desc* d) {
     if (d->engine == ARSEG_CONV_TC_TF32 && d->dtype != ARSEG_F32) return false;
     if (d->engine == ARSEG_CONV_TC_BF16 && d->dtype != ARSEG_BF16) return false;
     if (d->engine == ARSEG_CONV_TC_F16 && d->dtype != ARSEG_F16) return false;
-    if (d->stride != 1) return false;
+    if (d->stride != 1 && d->stride != 2) return false;
     if (d->Cin % bk != 0) return false;
     if (d->Cout < 16) return false;
-    const int Ho = d->Hi + 2 * d->pad - d->dil * (d->KH - 1), Wo = d->Wi + 2 * d->pad - d->dil * (d->KW - 1);
-    if (Ho != d->Hi || Wo != d->Wi) return false;   // "same" convs only (all stride-1 convs on the path)
+    // "same" convs (every stride-1 conv on the path) and their stride-2 versions (ResNet down-sampling blocks)
+    if (2 * d->pad != d->dil * (d->KH - 1) || 2 * d->pad != d->dil * (d->KW - 1)) return false;
     if ((uintptr_t)d->in % 16 || (uintptr_t)d->w % 16) return false;
     return true;
 }
@@ -720,10 +721,11 @@ int conv_tc_launch(const arseg_conv_desc* d, cudaStream_t st) {
     const int es = tf32 ? 4 : 2, bk = 128 / es;
     TcParams p;
     p.scale = d->scale; p.shift = d->shift; p.res = d->residual; p.out = d->out;
-    p.N = d->N; p.Ho = d->Hi; p.Wo = d->Wi; p.Cin = d->Cin; p.Cout = d->Cout; p.KH = d->KH; p.KW = d->KW;
+    p.stride = d->stride;
+    p.N = d->N; p.Ho = (d->Hi - 1) / d->stride + 1; p.Wo = (d->Wi - 1) / d->stride + 1; p.Cin = d->Cin; p.Cout = d->Cout; p.KH = d->KH; p.KW = d->KW;
     p.out_f32 = (d->out_f32 && d->dtype != ARSEG_F32) ? 1 : 0;
     p.pad = d->pad; p.dil = d->dil; p.ocs = d->out_cstride; p.oco = d->out_coff; p.act = d->act; p.slope = d->prelu_slope;
-    const bool halo = d->KH == 3 && d->KW == 3 && d->pad == d->dil && d->dil >= 1 && d->dil <= 8 && env_int("ARSEG_TC_HALO", 1) != 0;
+    const bool halo = d->stride == 1 && d->KH == 3 && d->KW == 3 && d->pad == d->dil && d->dil >= 1 && d->dil <= 8 && env_int("ARSEG_TC_HALO", 1) != 0;
     if (halo) { p.TH = TCH_TH; p.TW = TCH_TW; } else pick_tile(p.Ho, p.Wo, p.TH, p.TW);
     p.tiles_x = ceil_div(p.Wo, p.TW); p.tiles_y = ceil_div(p.Ho, p.TH);
     p.kchunks = d->Cin / bk;
@@ -740,8 +742,9 @@ int conv_tc_launch(const arseg_conv_desc* d, cudaStream_t st) {
     {
         cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->Wi, (cuuint64_t)d->Hi, (cuuint64_t)d->N};
         cuuint64_t strides[3] = {(cuuint64_t)d->Cin * es, (cuuint64_t)d->Wi * d->Cin * es, (cuuint64_t)d->Hi * d->Wi * d->Cin * es};
-        cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)(halo ? TCH_WH : p.TW), (cuuint32_t)(halo ? TCH_TH + 2 * d->dil : p.TH), 1};
-        cuuint32_t estr[4] = {1, 1, 1, 1};
+        // stride 2: the box spans stride * T input pixels and is traversed with element stride 2 (T pixels land in smem)
+        cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)(halo ? TCH_WH : p.TW * d->stride), (cuuint32_t)(halo ? TCH_TH + 2 * d->dil : p.TH * d->stride), 1};
+        cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
         CUresult r = encode(&ma, dt, 4, const_cast<void*>(d->in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(A) failed (%d)", (int)r); return ARSEG_E_CUDA; }

@@ -77,40 +77,49 @@ __global__ void resize_nchw_kernel(const float* __restrict__ src, float* __restr
 template <typename T, int VEC>
 struct alignas(sizeof(T) * VEC) Pack { T v[VEC]; };
 
+// One CTA per output row (grid-stride over N*Ho rows): the row's vertical taps / weights are computed once and the
+// per-element index math is 32-bit (64-bit div/mod per element made the previous flat version ALU-bound).
 template <typename T, int VEC>
-__global__ void resize_nhwc_kernel(const T* __restrict__ src, T* __restrict__ dst, int N, int Hi, int Wi, int C,
-                                   int Ho, int Wo, int dcs, int dco, int mode, float sh, float sw) {
+__global__ void __launch_bounds__(256) resize_nhwc_kernel(const T* __restrict__ src, T* __restrict__ dst, int N, int Hi, int Wi, int C,
+                                                          int Ho, int Wo, int dcs, int dco, int mode, float sh, float sw) {
     const int cv = C / VEC;
-    const long long total = (long long)N * Ho * Wo * cv;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(idx % cv) * VEC;
-        long long p = idx / cv;
-        const int x = (int)(p % Wo); p /= Wo;
-        const int y = (int)(p % Ho);
-        const int n = (int)(p / Ho);
-        const T* s = src + (size_t)n * Hi * Wi * C + c;
-        Pack<T, VEC> o;
+    const int row_elems = Wo * cv;
+    for (int row = blockIdx.x; row < N * Ho; row += gridDim.x) {
+        const int n = row / Ho, y = row - n * Ho;
+        const T* s = src + (size_t)n * Hi * Wi * C;
+        T* drow = dst + ((size_t)row * Wo) * dcs + dco;
         if (mode == ARSEG_RESIZE_NEAREST) {
-            const int ys = nearest_src(sh, y, Hi), xs = nearest_src(sw, x, Wi);
-            o = *reinterpret_cast<const Pack<T, VEC>*>(s + ((size_t)ys * Wi + xs) * C);
+            const T* srow = s + (size_t)nearest_src(sh, y, Hi) * Wi * C;
+            for (int i = threadIdx.x; i < row_elems; i += blockDim.x) {
+                const int x = i / cv, c = (i - x * cv) * VEC;
+                *reinterpret_cast<Pack<T, VEC>*>(drow + (size_t)x * dcs + c) =
+                    *reinterpret_cast<const Pack<T, VEC>*>(srow + (size_t)nearest_src(sw, x, Wi) * C + c);
+            }
         } else {
-            int y0, y1, x0, x1;
-            float ly0, ly1, lx0, lx1;
+            int y0, y1;
+            float ly0, ly1;
             bilinear_src(sh, y, Hi, mode, y0, y1, ly0, ly1);
-            bilinear_src(sw, x, Wi, mode, x0, x1, lx0, lx1);
-            const Pack<T, VEC> a = *reinterpret_cast<const Pack<T, VEC>*>(s + ((size_t)y0 * Wi + x0) * C);
-            const Pack<T, VEC> b = *reinterpret_cast<const Pack<T, VEC>*>(s + ((size_t)y0 * Wi + x1) * C);
-            const Pack<T, VEC> cc = *reinterpret_cast<const Pack<T, VEC>*>(s + ((size_t)y1 * Wi + x0) * C);
-            const Pack<T, VEC> d = *reinterpret_cast<const Pack<T, VEC>*>(s + ((size_t)y1 * Wi + x1) * C);
+            const T* r0 = s + (size_t)y0 * Wi * C;
+            const T* r1 = s + (size_t)y1 * Wi * C;
+            for (int i = threadIdx.x; i < row_elems; i += blockDim.x) {
+                const int x = i / cv, c = (i - x * cv) * VEC;
+                int x0, x1;
+                float lx0, lx1;
+                bilinear_src(sw, x, Wi, mode, x0, x1, lx0, lx1);
+                const Pack<T, VEC> a = *reinterpret_cast<const Pack<T, VEC>*>(r0 + (size_t)x0 * C + c);
+                const Pack<T, VEC> b = *reinterpret_cast<const Pack<T, VEC>*>(r0 + (size_t)x1 * C + c);
+                const Pack<T, VEC> cc = *reinterpret_cast<const Pack<T, VEC>*>(r1 + (size_t)x0 * C + c);
+                const Pack<T, VEC> d = *reinterpret_cast<const Pack<T, VEC>*>(r1 + (size_t)x1 * C + c);
+                Pack<T, VEC> o;
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-                float v = ly0 * (lx0 * to_f32(a.v[i]) + lx1 * to_f32(b.v[i])) +
-                          ly1 * (lx0 * to_f32(cc.v[i]) + lx1 * to_f32(d.v[i]));
-                o.v[i] = from_f32<T>(v);
+                for (int k = 0; k < VEC; ++k) {
+                    float v = ly0 * (lx0 * to_f32(a.v[k]) + lx1 * to_f32(b.v[k])) +
+                              ly1 * (lx0 * to_f32(cc.v[k]) + lx1 * to_f32(d.v[k]));
+                    o.v[k] = from_f32<T>(v);
+                }
+                *reinterpret_cast<Pack<T, VEC>*>(drow + (size_t)x * dcs + c) = o;
             }
         }
-        *reinterpret_cast<Pack<T, VEC>*>(dst + (((size_t)n * Ho + y) * Wo + x) * dcs + dco + c) = o;
     }
 }
 
@@ -230,61 +239,93 @@ __global__ void maxpool_kernel(const T* __restrict__ in, T* __restrict__ out, in
 // Block = 16x16 output pixels; weights for a 32-channel half live in smem as [tap][32] and are read
 // as broadcast float4; each thread keeps 32 accumulators for its pixel.
 // ------------------------------------------------------------------------------------------
-constexpr int STEM_T = 16;
-constexpr int STEM_IN = STEM_T * 2 + 5;  // 37
+// Register-tiled direct convolution: a CTA computes a 4-row x 64-column output tile for all 64 channels; a thread owns
+// 4 output pixels of one row (columns tx, tx+16, tx+32, tx+48) x 16 channels, so every weight vector read from shared
+// memory (LDS.128, warp-broadcast) feeds 16 FMAs and every input value 16.  Input tile 13 x 133 x 3 fp32 and the
+// [147][64] weights live in shared memory (57 KB).
+constexpr int STEM_TW = 64, STEM_TH = 4, STEM_CG = 16;
+constexpr int STEM_IW = STEM_TW * 2 + 5, STEM_IH = STEM_TH * 2 + 5;     // 133 x 13
+constexpr int STEM_IWP = STEM_IW + 1;
+constexpr int STEM_IN_FLOATS = (3 * STEM_IH * STEM_IWP + 3) / 4 * 4;                // keeps s_w 16-byte aligned
+constexpr size_t STEM_SMEM = (size_t)(STEM_IN_FLOATS + 147 * 64) * 4;
 template <typename T>
 __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                    const float* __restrict__ scale, const float* __restrict__ shift,
                                                    T* __restrict__ out, int H, int W, int Ho, int Wo, int Cout) {
-    __shared__ float s_in[3][STEM_IN][STEM_IN + 1];
-    __shared__ __align__(16) float s_w[147][32];
+    extern __shared__ __align__(16) float stem_sm[];
+    float* s_in = stem_sm;                                   // [3][STEM_IH][STEM_IWP]
+    float* s_w = stem_sm + STEM_IN_FLOATS;                   // [147][64]
     const int n = blockIdx.z;
-    const int ox0 = blockIdx.x * STEM_T, oy0 = blockIdx.y * STEM_T;
+    const int ox0 = blockIdx.x * STEM_TW, oy0 = blockIdx.y * STEM_TH;
     const int tid = threadIdx.x;
     const int ix0 = ox0 * 2 - 3, iy0 = oy0 * 2 - 3;
-    for (int i = tid; i < 3 * STEM_IN * STEM_IN; i += 256) {
-        const int c = i / (STEM_IN * STEM_IN), r = (i / STEM_IN) % STEM_IN, q = i % STEM_IN;
+    for (int i = tid; i < 3 * STEM_IH * STEM_IW; i += 256) {
+        const int c = i / (STEM_IH * STEM_IW), r = (i / STEM_IW) % STEM_IH, q = i % STEM_IW;
         const int y = iy0 + r, x = ix0 + q;
         float v = 0.f;
-        if (y >= 0 && y < H && x >= 0 && x < W) v = in[(((size_t)n * 3 + c) * H + y) * W + x];
-        s_in[c][r][q] = v;
+        if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(in + (((size_t)n * 3 + c) * H + y) * W + x);
+        s_in[(c * STEM_IH + r) * STEM_IWP + q] = v;
     }
-    const int tx = tid % STEM_T, ty = tid / STEM_T;
-    const int ox = ox0 + tx, oy = oy0 + ty;
-    for (int co0 = 0; co0 < Cout; co0 += 32) {
-        __syncthreads();
-        // w: [Cout][7][7][3] -> s_w[tap*3+c][co]
-        for (int i = tid; i < 147 * 32; i += 256) {
-            const int co = i / 147, t = i % 147;
-            s_w[t][co] = (co0 + co < Cout) ? w[(size_t)(co0 + co) * 147 + t] : 0.f;
+    // w: [Cout][7][7][3] -> s_w[tap*3+c][co]  (Cout <= 64; missing channels zero)
+    for (int i = tid; i < 147 * 64; i += 256) {
+        const int co = i / 147, t = i % 147;
+        s_w[t * 64 + co] = co < Cout ? __ldg(w + (size_t)co * 147 + t) : 0.f;
+    }
+    __syncthreads();
+    const int tx = tid & 15, ty = (tid >> 4) & 3, cg = tid >> 6;       // a warp = 2 rows x 16 columns of one channel group
+    float acc[4][STEM_CG];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int i = 0; i < STEM_CG; ++i) acc[p][i] = 0.f;
+#pragma unroll 1
+    for (int ky = 0; ky < 7; ++ky) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float* row = s_in + (c * STEM_IH + ty * 2 + ky) * STEM_IWP + tx * 2;
+#pragma unroll
+            for (int kx = 0; kx < 7; ++kx) {
+                const float4* wp = reinterpret_cast<const float4*>(s_w + ((ky * 7 + kx) * 3 + c) * 64 + cg * STEM_CG);
+                const float4 w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const float v = row[p * 32 + kx];
+                    acc[p][0] = fmaf(v, w0.x, acc[p][0]); acc[p][1] = fmaf(v, w0.y, acc[p][1]);
+                    acc[p][2] = fmaf(v, w0.z, acc[p][2]); acc[p][3] = fmaf(v, w0.w, acc[p][3]);
+                    acc[p][4] = fmaf(v, w1.x, acc[p][4]); acc[p][5] = fmaf(v, w1.y, acc[p][5]);
+                    acc[p][6] = fmaf(v, w1.z, acc[p][6]); acc[p][7] = fmaf(v, w1.w, acc[p][7]);
+                    acc[p][8] = fmaf(v, w2.x, acc[p][8]); acc[p][9] = fmaf(v, w2.y, acc[p][9]);
+                    acc[p][10] = fmaf(v, w2.z, acc[p][10]); acc[p][11] = fmaf(v, w2.w, acc[p][11]);
+                    acc[p][12] = fmaf(v, w3.x, acc[p][12]); acc[p][13] = fmaf(v, w3.y, acc[p][13]);
+                    acc[p][14] = fmaf(v, w3.z, acc[p][14]); acc[p][15] = fmaf(v, w3.w, acc[p][15]);
+                }
+            }
         }
-        __syncthreads();
-        float acc[32];
+    }
+    const int oy = oy0 + ty, co0 = cg * STEM_CG;
+    if (oy < Ho && co0 < Cout) {
+        float sc[STEM_CG], sh[STEM_CG];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-        for (int ky = 0; ky < 7; ++ky)
-            for (int kx = 0; kx < 7; ++kx)
+        for (int i = 0; i < STEM_CG; ++i) {
+            sc[i] = co0 + i < Cout ? __ldg(scale + co0 + i) : 0.f;
+            sh[i] = co0 + i < Cout ? __ldg(shift + co0 + i) : 0.f;
+        }
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float v = s_in[c][ty * 2 + ky][tx * 2 + kx];
-                    const float4* wp = reinterpret_cast<const float4*>(&s_w[(ky * 7 + kx) * 3 + c][0]);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 ww = wp[j];
-                        acc[j * 4 + 0] = fmaf(v, ww.x, acc[j * 4 + 0]);
-                        acc[j * 4 + 1] = fmaf(v, ww.y, acc[j * 4 + 1]);
-                        acc[j * 4 + 2] = fmaf(v, ww.z, acc[j * 4 + 2]);
-                        acc[j * 4 + 3] = fmaf(v, ww.w, acc[j * 4 + 3]);
-                    }
-                }
-        if (ox < Wo && oy < Ho) {
+        for (int p = 0; p < 4; ++p) {
+            const int ox = ox0 + tx + 16 * p;
+            if (ox >= Wo) continue;
             T* o = out + (((size_t)n * Ho + oy) * Wo + ox) * Cout + co0;
+            if (co0 + STEM_CG <= Cout && Cout % 8 == 0) {
+                alignas(16) T v[STEM_CG];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                if (co0 + i < Cout) {
-                    float v = acc[i] * scale[co0 + i] + shift[co0 + i];
-                    o[i] = from_f32<T>(fmaxf(v, 0.f));
-                }
+                for (int i = 0; i < STEM_CG; ++i) v[i] = from_f32<T>(fmaxf(fmaf(acc[p][i], sc[i], sh[i]), 0.f));
+                constexpr int NV = (int)(STEM_CG * sizeof(T) / 16);
+#pragma unroll
+                for (int q = 0; q < NV; ++q) reinterpret_cast<uint4*>(o)[q] = reinterpret_cast<const uint4*>(v)[q];
+            } else {
+#pragma unroll
+                for (int i = 0; i < STEM_CG; ++i)
+                    if (co0 + i < Cout) o[i] = from_f32<T>(fmaxf(fmaf(acc[p][i], sc[i], sh[i]), 0.f));
             }
         }
     }
@@ -346,6 +387,8 @@ int arseg_resize_nchw_f32(const float* src, float* dst, int planes, int Hi, int 
     return ARSEG_OK;
 }
 
+static inline int resize_grid(int N, int Ho) { const long long r = (long long)N * Ho, cap = (long long)sm_count() * 32; return (int)(r < cap ? r : cap); }
+
 int arseg_resize_nhwc(const void* src, void* dst, int dtype, int N, int Hi, int Wi, int C, int Ho, int Wo,
                       int dcs, int dco, int mode, arseg_stream_t stream) {
     ARSEG_REQUIRE(src && dst && N > 0 && Hi > 0 && Wi > 0 && C > 0 && Ho > 0 && Wo > 0, "resize_nhwc: bad args");
@@ -355,29 +398,23 @@ int arseg_resize_nhwc(const void* src, void* dst, int dtype, int N, int Hi, int 
     if (dtype == ARSEG_F32) {
         const float* s = (const float*)src; float* d = (float*)dst;
         if (C % 4 == 0 && dcs % 4 == 0 && dco % 4 == 0 && ((uintptr_t)s % 16 == 0) && ((uintptr_t)d % 16 == 0)) {
-            long long total = (long long)N * Ho * Wo * (C / 4);
-            resize_nhwc_kernel<float, 4><<<grid_1d(total, 256), 256, 0, st>>>(s, d, N, Hi, Wi, C, Ho, Wo, dcs, dco, mode, sh, sw);
+            resize_nhwc_kernel<float, 4><<<resize_grid(N, Ho), 256, 0, st>>>(s, d, N, Hi, Wi, C, Ho, Wo, dcs, dco, mode, sh, sw);
         } else {
-            long long total = (long long)N * Ho * Wo * C;
-            resize_nhwc_kernel<float, 1><<<grid_1d(total, 256), 256, 0, st>>>(s, d, N, Hi, Wi, C, Ho, Wo, dcs, dco, mode, sh, sw);
+            resize_nhwc_kernel<float, 1><<<resize_grid(N, Ho), 256, 0, st>>>(s, d, N, Hi, Wi, C, Ho, Wo, dcs, dco, mode, sh, sw);
         }
     } else if (dtype == ARSEG_BF16) {
         const __nv_bfloat16* s = (const __nv_bfloat16*)src; __nv_bfloat16* d = (__nv_bfloat16*)dst;
         if (C % 8 == 0 && dcs % 8 == 0 && dco % 8 == 0 && ((uintptr_t)s % 16 == 0) && ((uintptr_t)d % 16 == 0)) {
-            long long total = (long long)N * Ho * Wo * (C / 8);
-            resize_nhwc_kernel<__nv_bfloat16, 8><<<grid_1d(total, 256), 256, 0, st>>>(s, d, N, Hi, Wi, C, Ho, Wo, dcs, dco, mode, sh, sw);
+            resize_nhwc_kernel<__nv_bfloat16, 8><<<resize_grid(N, Ho), 256, 0, st>>>(s, d, N, Hi, Wi, C, Ho, Wo, dcs, dco, mode, sh, sw);
         } else {
-            long long total = (long long)N * Ho * Wo * C;
-            resize_nhwc_kernel<__nv_bfloat16, 1><<<grid_1d(total, 256), 256, 0, st>>>(s, d, N, Hi, Wi, C, Ho, Wo, dcs, dco, mode, sh, sw);
+            resize_nhwc_kernel<__nv_bfloat16, 1><<<resize_grid(N, Ho), 256, 0, st>>>(s, d, N, Hi, Wi, C, Ho, Wo, dcs, dco, mode, sh, sw);
         }
     } else if (dtype == ARSEG_F16) {
         const __half* s = (const __half*)src; __half* d = (__half*)dst;
         if (C % 8 == 0 && dcs % 8 == 0 && dco % 8 == 0 && ((uintptr_t)s % 16 == 0) && ((uintptr_t)d % 16 == 0)) {
-            long long total = (long long)N * Ho * Wo * (C / 8);
-            resize_nhwc_kernel<__half, 8><<<grid_1d(total, 256), 256, 0, st>>>(s, d, N, Hi, Wi, C, Ho, Wo, dcs, dco, mode, sh, sw);
+            resize_nhwc_kernel<__half, 8><<<resize_grid(N, Ho), 256, 0, st>>>(s, d, N, Hi, Wi, C, Ho, Wo, dcs, dco, mode, sh, sw);
         } else {
-            long long total = (long long)N * Ho * Wo * C;
-            resize_nhwc_kernel<__half, 1><<<grid_1d(total, 256), 256, 0, st>>>(s, d, N, Hi, Wi, C, Ho, Wo, dcs, dco, mode, sh, sw);
+            resize_nhwc_kernel<__half, 1><<<resize_grid(N, Ho), 256, 0, st>>>(s, d, N, Hi, Wi, C, Ho, Wo, dcs, dco, mode, sh, sw);
         }
     } else ARSEG_UNSUPPORTED("resize_nhwc: dtype %d", dtype);
     ARSEG_CHECK_LAUNCH("resize_nhwc");
@@ -481,15 +518,25 @@ int arseg_maxpool3x3s2_nhwc(const void* in, void* out, int dtype, int N, int H, 
 int arseg_conv_stem7x7s2(const float* in, const float* w, const float* scale, const float* shift, void* out,
                          int out_dtype, int N, int H, int W, int Cout, arseg_stream_t stream) {
     ARSEG_REQUIRE(in && w && scale && shift && out && N > 0 && H > 0 && W > 0 && Cout > 0, "stem: bad args");
+    ARSEG_REQUIRE(Cout <= 64, "stem: Cout=%d > 64", Cout);
     const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
-    dim3 grid(ceil_div(Wo, STEM_T), ceil_div(Ho, STEM_T), N);
+    dim3 grid(ceil_div(Wo, STEM_TW), ceil_div(Ho, STEM_TH), N);
     ARSEG_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "stem: dims too large");
+    static bool configured[64] = {false};
+    int dev = 0;
+    ARSEG_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        ARSEG_CUDA(cudaFuncSetAttribute(stem_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEM_SMEM));
+        ARSEG_CUDA(cudaFuncSetAttribute(stem_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEM_SMEM));
+        ARSEG_CUDA(cudaFuncSetAttribute(stem_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEM_SMEM));
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
     if (out_dtype == ARSEG_F32)
-        stem_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(in, w, scale, shift, (float*)out, H, W, Ho, Wo, Cout);
+        stem_kernel<float><<<grid, 256, STEM_SMEM, as_stream(stream)>>>(in, w, scale, shift, (float*)out, H, W, Ho, Wo, Cout);
     else if (out_dtype == ARSEG_BF16)
-        stem_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(in, w, scale, shift, (__nv_bfloat16*)out, H, W, Ho, Wo, Cout);
+        stem_kernel<__nv_bfloat16><<<grid, 256, STEM_SMEM, as_stream(stream)>>>(in, w, scale, shift, (__nv_bfloat16*)out, H, W, Ho, Wo, Cout);
     else if (out_dtype == ARSEG_F16)
-        stem_kernel<__half><<<grid, 256, 0, as_stream(stream)>>>(in, w, scale, shift, (__half*)out, H, W, Ho, Wo, Cout);
+        stem_kernel<__half><<<grid, 256, STEM_SMEM, as_stream(stream)>>>(in, w, scale, shift, (__half*)out, H, W, Ho, Wo, Cout);
     else ARSEG_UNSUPPORTED("stem: dtype %d", out_dtype);
     ARSEG_CHECK_LAUNCH("stem");
     return ARSEG_OK;

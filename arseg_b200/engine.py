@@ -96,8 +96,8 @@ class Plan:
         sh = self.dev(shift, torch.float32) if shift is not None else None
         engine = self.engine
         es = 4 if self.act_dtype == torch.float32 else 2
-        tc_ok = (engine != L.CONV_SIMT_F32 and stride == 1 and Cin % (128 // es) == 0 and Cout >= 16
-                 and Ho == Hi and Wo == Wi and Hi * Wi >= 64)
+        tc_ok = (engine != L.CONV_SIMT_F32 and stride in (1, 2) and Cin % (128 // es) == 0 and Cout >= 16
+                 and 2 * pad == dil * (KH - 1) and 2 * pad == dil * (KW - 1) and Ho * Wo >= 64)
         if not tc_ok:
             engine = L.CONV_SIMT_F32
         # out_f32: fp32 output from a 16-bit plan (tcgen05 engines only; other plans / engines ignore the request)

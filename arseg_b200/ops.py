@@ -186,6 +186,21 @@ def conv2d_nhwc(x, w, scale=None, shift=None, residual=None, stride=1, pad=0, di
     return out
 
 
+def conv_stem(x_nchw, w_oihw, scale, shift, dtype=torch.float32):
+    """conv1 7x7 s2 p3 + folded BN + ReLU (model/extractors.py:112-114): NCHW fp32 [N,3,H,W] -> NHWC [N,Ho,Wo,Cout]."""
+    _chk_cuda("conv_stem", x_nchw, w_oihw, scale, shift)
+    N, Ci, H, W = x_nchw.shape
+    Cout = w_oihw.shape[0]
+    assert Ci == 3 and tuple(w_oihw.shape[1:]) == (3, 7, 7)
+    Ho, Wo = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+    w = w_oihw.permute(0, 2, 3, 1).contiguous()
+    out = torch.empty((N, Ho, Wo, Cout), dtype=dtype, device=x_nchw.device)
+    with torch.cuda.device(x_nchw.device):
+        L.check(L.load().arseg_conv_stem7x7s2(_p(x_nchw), _p(w), _p(scale), _p(shift), _p(out), dtype_code(dtype), N, H, W, Cout,
+                                              _stream()), "conv_stem")
+    return out
+
+
 def creff_fused(hr, lr, wq, bq, wk, bk, wv, bv, k, flow=None, flow_hw=None, wcls=None, bcls=None, log_softmax=False,
                 lr_layout=L.NCHW, want_p=True, want_logits=True, want_argmax=False, hr_shared=False, n_frames=None,
                 engine=L.CREFF_EXACT_F32, hr_layout=L.NCHW):

@@ -155,7 +155,9 @@ def test_conv_simt_fp32(case):
     assert rel_err(got, ref) < FP32_TOL
 
 
-TC_CASES = [c for c in CONV_CASES if c[6] == 1 and c[2] >= 16] + [
+TC_CASES = [c for c in CONV_CASES if c[2] >= 16] + [
+    (2, 64, 128, 45, 61, 3, 2, 1, 1, False, L.ACT_RELU),       # stride 2 with odd extents (TMA element strides)
+    (1, 128, 256, 23, 30, 1, 2, 0, 1, False, L.ACT_NONE),
     (2, 64, 64, 45, 60, 3, 1, 1, 1, True, L.ACT_RELU),
     (1, 1024, 256, 18, 24, 3, 1, 1, 1, False, L.ACT_PRELU),
     (1, 2560, 1024, 9, 12, 1, 1, 0, 1, False, L.ACT_RELU),
@@ -169,7 +171,8 @@ def test_conv_tcgen05(case, engine, dtype, tol):
     N, Ci, Co, H, W, k, s, p, d, has_res, act = case
     x, w = rnd(N, Ci, H, W, seed=30), rnd(Co, Ci, k, k, seed=31) * (1.0 / (Ci * k * k) ** 0.5)
     scale, shift = torch.rand(Co) + 0.5, rnd(Co, seed=32) * 0.1
-    res = rnd(N, Co, H, W, seed=33) if has_res else None
+    Ho, Wo = (H + 2 * p - d * (k - 1) - 1) // s + 1, (W + 2 * p - d * (k - 1) - 1) // s + 1
+    res = rnd(N, Co, Ho, Wo, seed=33) if has_res else None
     if dtype != torch.float32:    # reference on the 16-bit-rounded operands: isolates accumulation error
         x, w = x.to(dtype).float(), w.to(dtype).float()
         res = res.to(dtype).float() if res is not None else None
@@ -178,6 +181,18 @@ def test_conv_tcgen05(case, engine, dtype, tol):
     assert got.shape == ref.shape
     assert rel_err(got, ref) < tol, (rel_err(got, ref), rms_err(got, ref))
     assert rms_err(got, ref) < tol / 4
+
+
+@pytest.mark.parametrize("N,H,W,Cout", [(2, 37, 53, 64), (1, 64, 130, 64), (1, 23, 18, 40)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, FP32_TOL), (torch.float16, 2e-3)])
+def test_conv_stem(N, H, W, Cout, dtype, tol):
+    """conv1 7x7 stride 2 pad 3 (no bias) + BN(eval) + ReLU, model/extractors.py:112-114,148-150."""
+    x, w = rnd(N, 3, H, W, seed=40), rnd(Cout, 3, 7, 7, seed=41) * (1.0 / 147 ** 0.5)
+    scale, shift = torch.rand(Cout) + 0.5, rnd(Cout, seed=42) * 0.1
+    ref = F.relu(F.conv2d(x.double(), w.double(), None, 2, 3) * scale.double().view(1, -1, 1, 1) + shift.double().view(1, -1, 1, 1)).float()
+    got = ops.nhwc_to_nchw(ops.conv_stem(x.to(DEV), w.to(DEV), scale.to(DEV), shift.to(DEV), dtype)).cpu()
+    assert got.shape == ref.shape
+    assert rel_err(got, ref) < tol
 
 
 def test_conv_output_channel_slice():
