@@ -61,6 +61,9 @@ _PROTOS = {
     "arseg_global_maxpool_nhwc": ([vp, vp] + [ci] * 5 + [vp], ci),
     "arseg_linear_f32": ([vp, vp, vp, vp, ci, ci, ci, ci, vp], ci),
     "arseg_gate_nhwc": ([vp, vp, vp, vp, ci, vp, vp, vp, ci, ci, ci, ci, ci, vp], ci),
+    "arseg_pyramid_pool_nhwc": ([vp, vp, ci, ci, ci, ci, ci, vp, ci, vp], ci),
+    "arseg_pyramid_conv1x1": ([vp, vp, vp, vp, ci, vp, ci, ci, ci, vp, ci, vp], ci),
+    "arseg_pyramid_upsample_concat": ([vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp, ci, vp], ci),
     "arseg_creff_fused_fwd": ([C.POINTER(CreffArgs), vp], ci),
 }
 

@@ -163,6 +163,34 @@ class Plan:
         self._add("avgpool%dx%d" % (Ho, Wo), lambda s: fn(*args, s))
         return out
 
+    def pyramid(self, f: torch.Tensor, bins: Sequence[int], weights: Sequence[torch.Tensor], scales=None, shifts=None,
+                relu: bool = False, mode: int = L.RESIZE_BILINEAR, stages_first: bool = True, name: str = "psp") -> torch.Tensor:
+        """Pyramid pooling module as three launches: all levels of AdaptiveAvgPool2d, the per-level 1x1 convolutions
+        (+ folded BN, + ReLU) and bilinear up-sampling + concat with `f` (PSPModule model/pspnet.py:14-31 puts the
+        stages first, PPM model/pspnet_semseg.py:12-30 puts x first)."""
+        N, H, W, Cf = f.shape
+        nlev, Cout = len(bins), weights[0].shape[0]
+        B = sum(b * b for b in bins)
+        cbins = (C.c_int * nlev)(*bins)
+        self.keep.append(cbins)
+        pooled = self.empty((N, B, Cf), torch.float32)
+        stage = self.empty((N, B, Cout), torch.float32)
+        w = self.dev(torch.stack([x.detach().reshape(Cout, Cf) for x in weights]).contiguous(), torch.float32)
+        sc = self.dev(torch.stack(list(scales)).contiguous(), torch.float32) if scales is not None else None
+        sh = self.dev(torch.stack(list(shifts)).contiguous(), torch.float32) if shifts is not None else None
+        out = self.empty((N, H, W, nlev * Cout + Cf))
+        f1, f2, f3 = self.lib.arseg_pyramid_pool_nhwc, self.lib.arseg_pyramid_conv1x1, self.lib.arseg_pyramid_upsample_concat
+        a1 = (f.data_ptr(), pooled.data_ptr(), dtype_code(f.dtype), N, H, W, Cf, cbins, nlev)
+        a2 = (pooled.data_ptr(), w.data_ptr(), sc.data_ptr() if sc is not None else None, sh.data_ptr() if sh is not None else None,
+              int(relu), stage.data_ptr(), N, Cf, Cout, cbins, nlev)
+        s_off, f_off = (0, nlev * Cout) if stages_first else (Cf, 0)
+        a3 = (stage.data_ptr(), f.data_ptr(), out.data_ptr(), dtype_code(f.dtype), N, H, W, Cout, Cf, s_off, f_off, mode, cbins, nlev)
+        self._add(name + ".pool", lambda s: f1(*a1, s))
+        self._add(name + ".conv1x1", lambda s: f2(*a2, s))
+        self._add(name + ".upsample_concat", lambda s: f3(*a3, s))
+        self.conv_flops += 2 * N * B * Cout * Cf
+        return out
+
     def gmaxpool(self, x: torch.Tensor) -> torch.Tensor:
         N, H, W, Cc = x.shape
         out = self.empty((N, Cc), torch.float32)
@@ -370,12 +398,9 @@ def build_psp_phase1(pl: Plan, sd: SD, x_nchw: torch.Tensor, p: str = "", sizes=
     """PSPNetWithFuse.forward_phase1 (model/pspnet.py:198-217) -> (cls fp32 [N,ncls] | None, p NHWC [N,h,w,64])."""
     f, x3 = _resnet_os8(pl, sd, p, x_nchw, semseg=False)
     N, h, w, Cf = f.shape
-    cat = pl.empty((N, h, w, Cf * (len(sizes) + 1)))
-    for i, s in enumerate(sizes):                                   # PSPModule stages (model/pspnet.py:22-30)
-        t = pl.avgpool(f, s, s)
-        t = pl.conv(t, sd[p + "psp.stages.%d.1.weight" % i], name="psp.stage%d" % i)
-        pl.resize(t, h, w, L.RESIZE_BILINEAR, out=cat, coff=i * Cf, name="psp.up%d" % i)
-    pl.resize(f, h, w, L.RESIZE_NEAREST, out=cat, coff=len(sizes) * Cf, name="psp.cat_feats")
+    # PSPModule stages + concat (model/pspnet.py:22-30)
+    cat = pl.pyramid(f, sizes, [sd[p + "psp.stages.%d.1.weight" % i] for i in range(len(sizes))], mode=L.RESIZE_BILINEAR,
+                     stages_first=True, name="psp")
     t = pl.conv(cat, sd[p + "psp.bottleneck.weight"], None, sd[p + "psp.bottleneck.bias"], act=L.ACT_RELU, name="psp.bottleneck")
     for u in ("up_1.", "up_2.", "up_3."):                           # PSPUpsample (model/pspnet.py:34-46)
         Nn, hh, ww, _ = t.shape
@@ -397,13 +422,9 @@ def build_semseg_phase1(pl: Plan, sd: SD, x_nchw: torch.Tensor, p: str = "", bin
     x4, x3 = _resnet_os8(pl, sd, p, x_nchw, semseg=True)
     N, h, w, Cf = x4.shape
     red = Cf // len(bins)
-    cat = pl.empty((N, h, w, 2 * Cf))
-    pl.resize(x4, h, w, L.RESIZE_NEAREST, out=cat, coff=0, name="ppm.cat_x")          # x first (:27)
-    for i, b in enumerate(bins):
-        t = pl.avgpool(x4, b, b)
-        sc, sh = fold_bn(sd, p + "ppm.features.%d.2." % i)
-        t = pl.conv(t, sd[p + "ppm.features.%d.1.weight" % i], sc, sh, act=L.ACT_RELU, name="ppm.branch%d" % i)
-        pl.resize(t, h, w, L.RESIZE_BILINEAR_AC, out=cat, coff=Cf + i * red, name="ppm.up%d" % i)
+    folded = [fold_bn(sd, p + "ppm.features.%d.2." % i) for i in range(len(bins))]
+    cat = pl.pyramid(x4, bins, [sd[p + "ppm.features.%d.1.weight" % i] for i in range(len(bins))], [f_[0] for f_ in folded],
+                     [f_[1] for f_ in folded], relu=True, mode=L.RESIZE_BILINEAR_AC, stages_first=False, name="ppm")   # x first (:27)
     sc, sh = fold_bn(sd, p + "cls.1.")
     t = pl.conv(cat, sd[p + "cls.0.weight"], sc, sh, pad=1, act=L.ACT_RELU, name="cls.0")
     return x3, t

@@ -142,6 +142,21 @@ int arseg_gate_nhwc(const void* feat, const float* gate, const float* gate_scale
                     int add_identity, const float* add_chan, const void* add_pix, void* out, int dtype,
                     int N, int H, int W, int C, arseg_stream_t stream);
 
+/* Pyramid pooling module in three launches (PSPModule model/pspnet.py:14-31; PPM model/pspnet_semseg.py:12-30).
+ * bins[nlev] = pooled sizes (1,2,3,6); B = sum bins^2.  Host array, read during the call.
+ *   pool:   NHWC `in` -> fp32 [N][B][C], level-major, every level's bins row-major (nn.AdaptiveAvgPool2d windows)
+ *   conv:   per-level 1x1 conv w [nlev][Cout][C] fp32 (+ folded BN scale/shift [nlev][Cout] or NULL, + ReLU)
+ *           on the pooled map -> fp32 [N][B][Cout]
+ *   upsample_concat: out[..., stage_coff + l*Cout + c] = bilinear(level l, mode)[c]; out[..., feats_coff + c] = feats;
+ *           out NHWC [N,H,W,nlev*Cout+Cf] of `dtype` (the two slices must tile the channel axis) */
+int arseg_pyramid_pool_nhwc(const void* in, float* out, int dtype, int N, int H, int W, int C, const int* bins, int nlev,
+                            arseg_stream_t stream);
+int arseg_pyramid_conv1x1(const float* pooled, const float* w, const float* scale, const float* shift, int relu, float* out,
+                          int N, int C, int Cout, const int* bins, int nlev, arseg_stream_t stream);
+int arseg_pyramid_upsample_concat(const float* stage, const void* feats, void* out, int dtype, int N, int H, int W, int Cout,
+                                  int Cf, int stage_coff, int feats_coff, int mode, const int* bins, int nlev,
+                                  arseg_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * 5. Fused MV-warp + CReFF + classifier (evaluation.py:177-183 + model/attention.py:184-213 +
  *    final_conv/log-softmax of model/pspnet.py:226-229, + argmax of evaluation.py:204)

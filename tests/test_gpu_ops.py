@@ -195,6 +195,36 @@ def test_conv_stem(N, H, W, Cout, dtype, tol):
     assert rel_err(got, ref) < tol
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, FP32_TOL), (torch.float16, 2e-3)])
+@pytest.mark.parametrize("semseg", [False, True])
+def test_pyramid_pooling_module(dtype, tol, semseg):
+    """PSPModule (model/pspnet.py:14-31) / PPM (model/pspnet_semseg.py:12-30) as three launches."""
+    from arseg_b200 import engine as E
+    N, Cf, H, W, bins = 2, 64, 23, 30, (1, 2, 3, 6)
+    Cout = Cf // 4 if semseg else Cf
+    x = rnd(N, Cf, H, W, seed=80)
+    ws = [rnd(Cout, Cf, 1, 1, seed=81 + i) * (1.0 / Cf ** 0.5) for i in range(4)]
+    scs = [torch.rand(Cout) + 0.5 for _ in range(4)] if semseg else None
+    shs = [rnd(Cout, seed=90 + i) * 0.1 for i in range(4)] if semseg else None
+    xr = x.to(dtype).float()
+    branches = []
+    for i, b in enumerate(bins):
+        t = F.conv2d(F.adaptive_avg_pool2d(xr, b), ws[i])
+        if semseg:
+            t = F.relu(t * scs[i].view(1, -1, 1, 1) + shs[i].view(1, -1, 1, 1))
+        branches.append(F.interpolate(t, size=(H, W), mode="bilinear", align_corners=semseg))
+    ref = torch.cat([xr] + branches, 1) if semseg else torch.cat(branches + [xr], 1)
+    pl = E.Plan(torch.device(DEV), {torch.float32: "fp32", torch.float16: "f16"}[dtype])
+    f = ops.nchw_to_nhwc(x.to(DEV), dtype)
+    cat = pl.pyramid(f, bins, ws, scs, shs, relu=semseg, mode=L.RESIZE_BILINEAR_AC if semseg else L.RESIZE_BILINEAR,
+                     stages_first=not semseg)
+    pl.launch()
+    torch.cuda.synchronize()
+    got = ops.nhwc_to_nchw(cat).cpu()
+    assert got.shape == ref.shape
+    assert rel_err(got, ref) < tol, rel_err(got, ref)
+
+
 def test_conv_output_channel_slice():
     """out_cstride / out_coff: the conv writes a channel slice of a wider tensor (fused torch.cat)."""
     x, w = rnd(1, 64, 10, 12, seed=40), rnd(32, 64, 1, 1, seed=41) * 0.1
