@@ -58,7 +58,7 @@ template <int K> struct XCfg {
     static constexpr size_t LR_BYTES = (size_t)XLR_RING * LC * 256;
     static constexpr size_t Q_BYTES = 64 * 128;
     static constexpr size_t RES_BYTES = 64 * XRES_LD * 4;
-    static constexpr size_t POS_BYTES = (size_t)PMAX * 24;
+    static constexpr size_t POS_BYTES = (size_t)PMAX * 32;
     static constexpr size_t CLS_BYTES = 32 * XCLS_LD * 2 + 32 * 4;
     static constexpr size_t SCRATCH_BYTES = 256;                  // ring-like slot the no-op gather records write to
     static constexpr size_t DWW_BYTES = 3 * 10 * 32 * 8;          // depthwise weights + bias, float2 per lane
@@ -75,8 +75,13 @@ template <int K> struct XCfg {
 __device__ __forceinline__ void xbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count));
 }
+// one arrival per WARP (barrier counts = warps of the producing role): a waiter parked in try_wait is woken by every
+// arrival on its barrier, so per-thread arrivals make every waiting warp spin through 32x more wake-ups.  __syncwarp
+// orders the lanes' shared-memory accesses before the elected lane's release-arrive.
 __device__ __forceinline__ void xbar_arrive(uint64_t* bars, int step) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(bars + ((step + 1) & (XNB - 1)))) : "memory");
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0)
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(bars + ((step + 1) & (XNB - 1)))) : "memory");
 }
 __device__ __forceinline__ void xbar_wait(uint64_t* bars, int step) {
     const uint32_t addr = s_u32(bars + ((step + 1) & (XNB - 1)));
@@ -85,6 +90,7 @@ __device__ __forceinline__ void xbar_wait(uint64_t* bars, int step) {
     // try_wait suspends the thread in hardware until the phase completes or a time limit expires; the poll loop is
     // kept minimal (a spinning warp takes issue slots from the working roles) and bounded (a protocol bug must trap,
     // not hang the GPU box)
+#pragma unroll 1
     for (int spin = 0; spin < (1 << 22); ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -123,7 +129,7 @@ struct XSmem {
     uint8_t *sK, *sV, *rings, *sQ;
     float* sRes;
     float4* posw;
-    int2* posid;
+    uint4* posa;
     __half* s_wc;
     float* s_bc;
     float2* s_dw;     // [3 convs: k, v, q][9 taps + bias][32 lanes] (channels 2*lane, 2*lane+1)
@@ -144,91 +150,132 @@ __device__ __forceinline__ void x_step_geom(int t, int& h0, int& nh, int& l0, in
     }
 }
 
+// A gather record names a 2x2 source block that lies INSIDE the image (top-left pixel clamped to [0, W-2] x [0, H-2]) plus
+// the four weights of its pixels, so the taps are base, base + one pixel, base + one row, base + one row + one pixel:
+// three of the four addresses are immediates / one add.  PosRec (pos_hr / pos_lr) names the taps by a clamped NW
+// tap and dx / dy flags instead; where a flag is 0 both taps of that direction read the same pixel (image border), and
+// their weights are merged onto whichever block column / row holds it (at most one of the two is non-zero for the
+// warp, grid_sample zero padding; for lr_up the two add up to the same bilinear weight).
+__device__ __forceinline__ void x_block_of(const PosRec& r, int Wimg, int Himg, float4& w, int& bx, int& by) {
+    w = r.w; bx = r.cx; by = r.cy;
+    if (!((r.info >> 1) & 1)) {
+        const float nn = w.x + w.y, ss = w.z + w.w;
+        if (bx > 0 && bx == Wimg - 1) { bx -= 1; w.x = 0.f; w.y = nn; w.z = 0.f; w.w = ss; }
+        else { w.x = nn; w.y = 0.f; w.z = ss; w.w = 0.f; }
+    }
+    if (!(r.info & 1)) {
+        const float ww = w.x + w.z, ee = w.y + w.w;
+        if (by > 0 && by == Himg - 1) { by -= 1; w.x = 0.f; w.y = 0.f; w.z = ww; w.w = ee; }
+        else { w.x = ww; w.y = ee; w.z = 0.f; w.w = 0.f; }
+    }
+}
+
+__device__ __forceinline__ void sts_f4(uint32_t a, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 template <int K, typename TLR>
 __device__ __forceinline__ void x_g_role(const CreffMmaParams& p, const XSmem& sm, int n, int x0, int ya, int S) {
     using Cf = XCfg<K>;
     constexpr int NHW = XNHW;                             // half-warps: one gather position each
     constexpr int LR_ES = (int)sizeof(TLR);
-    constexpr int SCRATCH_IDX = (int)((Cf::HR_BYTES + Cf::LR_BYTES) / 256);
+    constexpr uint32_t SCRATCH_OFF = (uint32_t)(Cf::HR_BYTES + Cf::LR_BYTES);
     const int gt = threadIdx.x, lane = gt & 31, hw = gt >> 4, cl = lane & 15;
     const float lsh = resize_scale(p.h, p.H, ARSEG_RESIZE_BILINEAR_AC), lsw = resize_scale(p.w, p.W, ARSEG_RESIZE_BILINEAR_AC);
-    // this lane's 4 channels of a source pixel; tap byte offsets come from the position records
-    const char* const hrb = reinterpret_cast<const char*>(p.hr + (p.hr_shared ? 0 : (size_t)n * p.H * p.W * MC) + 4 * cl);
-    const char* const lrb = reinterpret_cast<const char*>(reinterpret_cast<const TLR*>(p.lr) + (size_t)n * p.h * p.w * MC + 4 * cl);
+    const char* const hrb = reinterpret_cast<const char*>(p.hr + (p.hr_shared ? 0 : (size_t)n * p.H * p.W * MC));
+    const char* const lrb = reinterpret_cast<const char*>(reinterpret_cast<const TLR*>(p.lr) + (size_t)n * p.h * p.w * MC);
     const double rcp_w = 2.0 / (double)max(p.W - 1, 1), rcp_h = 2.0 / (double)max(p.H - 1, 1);
+    const uint32_t hr_rs = (uint32_t)p.W * MC * 4, lr_rs = (uint32_t)p.w * MC * LR_ES;
+    const uint32_t ring_st = s_u32(sm.rings) + 16 * cl;   // this lane's 4 channels of ring position 0
 
-    // position record q of a step (one per G thread): bilinear weights (invalid taps zeroed) + {byte offset of the NW
-    // tap, flags}: flags = ring offset / 256 | dx << 12 | dy << 13 | lr << 14 | all-zero << 15.  The record list is
-    // padded to a multiple of NHW * XJA with no-op records (zero weights, scratch destination), so the gather loop
-    // is branch-free.  Single-buffered: the records of step t+1 are written after the last use of those of step t.
+    // position record q of a step (one per G thread): posw = the block's four weights; posa = {block address (64 bit),
+    // row stride in bytes, byte offset of the destination ring position | lr << 31}.  The record list is padded to a
+    // multiple of NHW * XJA with no-op records (zero weights, scratch destination), so the gather loop is branch-free.
+    // Positions outside the image are zero-weight records onto a valid address (exact zeros for finite inputs).
+    // Single-buffered: the records of step t+1 are written after the last use of those of step t.
     const bool mv_fast = p.flow && p.flow_dtype == ARSEG_I16 && p.Hm == p.H && p.Wm == p.W;
     const int* const mvp = reinterpret_cast<const int*>(p.flow) + (size_t)n * p.H * p.W;
     auto padded = [](int npos) { return ((npos + NHW * XJA - 1) / (NHW * XJA)) * (NHW * XJA); };
-    auto compute_pos = [&](int t) {
+    // the int16 MV pair of this thread's hr position of step t (loaded one step ahead of compute_pos)
+    auto mv_of = [&](int t) -> int {
+        int h0, nh, l0, nl;
+        x_step_geom<K>(t, h0, nh, l0, nl);
+        if (!mv_fast || gt >= nh * Cf::HC) return 0;
+        const int rr = gt / Cf::HC, cc = gt - rr * Cf::HC;
+        const int fy = ya - Cf::R - 1 + h0 + rr, fx = x0 - Cf::R - 1 + cc;
+        return (fy >= 0 && fy < p.H && fx >= 0 && fx < p.W) ? __ldg(mvp + (size_t)fy * p.W + fx) : 0;
+    };
+    auto compute_pos = [&](int t, int mv) {
         int h0, nh, l0, nl;
         x_step_geom<K>(t, h0, nh, l0, nl);
         const int nhp = nh * Cf::HC, npos = nhp + nl * Cf::LC;
         const int q = gt;
         if (q >= padded(npos)) return;
-        PosRec r; r.w = make_float4(0.f, 0.f, 0.f, 0.f); r.info = -1;
-        int fl = SCRATCH_IDX, off = 0;
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+        const char* src = hrb;
+        uint32_t rs = hr_rs, dst = SCRATCH_OFF;
         if (q < nhp) {
             const int rr = q / Cf::HC, cc = q - rr * Cf::HC, row = h0 + rr;
             const int fy = ya - Cf::R - 1 + row, fx = x0 - Cf::R - 1 + cc;
-            int mv = 0;
-            if (mv_fast && fy >= 0 && fy < p.H && fx >= 0 && fx < p.W) mv = __ldg(mvp + (size_t)fy * p.W + fx);
-            r = pos_hr(p, n, fy, fx, rcp_w, rcp_h, mv_fast ? &mv : nullptr);
-            fl = (row % XHR_RING) * Cf::HC + cc;
-            off = (r.info >> 2) * (MC * 4);
+            const PosRec r = pos_hr(p, n, fy, fx, rcp_w, rcp_h, mv_fast ? &mv : nullptr);
+            dst = (uint32_t)(((row % XHR_RING) * Cf::HC + cc) * 256);
+            if (r.info >= 0) {
+                int bx, by;
+                x_block_of(r, p.W, p.H, w, bx, by);
+                src = hrb + ((size_t)by * p.W + bx) * (MC * 4);
+            }
         } else if (q < npos) {
             const int q2 = q - nhp, rr = q2 / Cf::LC, cc = q2 - rr * Cf::LC, row = l0 + rr;
-            r = pos_lr(p, lsh, lsw, ya - 1 + row, x0 - 1 + cc);
-            fl = ((int)(Cf::HR_BYTES / 256) + (row % XLR_RING) * Cf::LC + cc) | (1 << 14);
-            off = (r.info >> 2) * (MC * LR_ES);
+            const PosRec r = pos_lr(p, lsh, lsw, ya - 1 + row, x0 - 1 + cc);
+            dst = (uint32_t)(Cf::HR_BYTES + ((row % XLR_RING) * Cf::LC + cc) * 256);
+            if (r.info >= 0) {
+                int bx, by;
+                x_block_of(r, p.w, p.h, w, bx, by);
+                src = lrb + ((size_t)by * p.w + bx) * (MC * LR_ES);
+                rs = lr_rs;
+                dst |= 0x80000000u;
+            }
         }
-        if (r.info < 0) { off = 0; fl = (fl & ~(1 << 14)) | 1 << 15; }     // outside the image / padding: exact zeros
-        else fl |= ((r.info >> 1) & 1) << 12 | (r.info & 1) << 13;
-        sm.posw[q] = r.w;
-        sm.posid[q] = make_int2(off, fl);
+        sm.posw[q] = w;
+        const unsigned long long a = reinterpret_cast<unsigned long long>(src);
+        sm.posa[q] = make_uint4((uint32_t)a, (uint32_t)(a >> 32), rs, dst);
     };
-    const uint32_t hr_rs = (uint32_t)p.W * MC * 4, lr_rs = (uint32_t)p.w * MC * LR_ES;
     float4 tap[XJA][4];
     auto issue = [&](float4 (&tp)[4], int j) {
 #ifdef ARSEG_XTRACE
         if (p.dbg & 4) return;
 #endif
-        const int2 id = sm.posid[hw + NHW * j];
-        const bool islr = (id.y >> 14) & 1;
-        const uint32_t dxb = (id.y & (1 << 12)) ? (islr ? MC * LR_ES : MC * 4) : 0u;
-        const uint32_t dyb = (id.y & (1 << 13)) ? (islr ? lr_rs : hr_rs) : 0u;
-        if (LR_ES == 4 || !islr) {
-            const char* a = (islr ? lrb : hrb) + (uint32_t)id.x;
-            tp[0] = ld4(reinterpret_cast<const float*>(a));
-            tp[1] = ld4(reinterpret_cast<const float*>(a + dxb));
-            tp[2] = ld4(reinterpret_cast<const float*>(a + dyb));
-            tp[3] = ld4(reinterpret_cast<const float*>(a + dxb + dyb));
+        const uint4 id = sm.posa[hw + NHW * j];
+        const char* a0 = reinterpret_cast<const char*>(((unsigned long long)id.y << 32) | id.x);
+        if (LR_ES == 4 || !(id.w >> 31)) {
+            a0 += 16 * cl;
+            const char* a1 = a0 + id.z;
+            tp[0] = ld4(reinterpret_cast<const float*>(a0));
+            tp[1] = ld4(reinterpret_cast<const float*>(a0 + MC * 4));
+            tp[2] = ld4(reinterpret_cast<const float*>(a1));
+            tp[3] = ld4(reinterpret_cast<const float*>(a1 + MC * 4));
         } else {
-            const char* a = lrb + (uint32_t)id.x;
-            tp[0] = ld4(reinterpret_cast<const TLR*>(a));
-            tp[1] = ld4(reinterpret_cast<const TLR*>(a + dxb));
-            tp[2] = ld4(reinterpret_cast<const TLR*>(a + dyb));
-            tp[3] = ld4(reinterpret_cast<const TLR*>(a + dxb + dyb));
+            a0 += LR_ES * 4 * cl;
+            const char* a1 = a0 + id.z;
+            tp[0] = ld4(reinterpret_cast<const TLR*>(a0));
+            tp[1] = ld4(reinterpret_cast<const TLR*>(a0 + MC * LR_ES));
+            tp[2] = ld4(reinterpret_cast<const TLR*>(a1));
+            tp[3] = ld4(reinterpret_cast<const TLR*>(a1 + MC * LR_ES));
         }
     };
     auto commit = [&](const float4 (&tp)[4], int j) {
         const int i = hw + NHW * j;
         const float4 w = sm.posw[i];
-        const int fl = sm.posid[i].y;
+        const uint32_t dst = sm.posa[i].w & 0x7fffffffu;
         float4 v;
         v.x = tp[0].x * w.x + tp[1].x * w.y + tp[2].x * w.z + tp[3].x * w.w;
         v.y = tp[0].y * w.x + tp[1].y * w.y + tp[2].y * w.z + tp[3].y * w.w;
         v.z = tp[0].z * w.x + tp[1].z * w.y + tp[2].z * w.z + tp[3].z * w.w;
         v.w = tp[0].w * w.x + tp[1].w * w.y + tp[2].w * w.z + tp[3].w * w.w;
-        if (fl & (1 << 15)) v = make_float4(0.f, 0.f, 0.f, 0.f);
-        *reinterpret_cast<float4*>(sm.rings + (fl & 0xfff) * 256 + 16 * cl) = v;
+        sts_f4(ring_st + dst, v);
     };
 
-    compute_pos(-1);
+    compute_pos(-1, mv_of(-1));
     nbar_sync(XBAR_G, XG_THREADS);
 #pragma unroll 1
     for (int t = -1; t <= S; ++t) {
@@ -239,6 +286,7 @@ __device__ __forceinline__ void x_g_role(const CreffMmaParams& p, const XSmem& s
         // rolling pipeline: XJA positions' loads are always in flight while the oldest one is combined and stored
 #pragma unroll
         for (int j = 0; j < XJA; ++j) issue(tap[j], j);
+        const int mv_next = t < S ? mv_of(t + 1) : 0;     // in flight during the gather loop
         if (t >= 1) xbar_wait(sm.ddone, t - 2);           // D step t-2 done: the ring rows this step overwrites are free
         XTRACE(0, t, 1);
 #pragma unroll 1
@@ -254,7 +302,7 @@ __device__ __forceinline__ void x_g_role(const CreffMmaParams& p, const XSmem& s
         XTRACE(0, t, 2);
         xbar_arrive(sm.gfull, t);
         nbar_sync(XBAR_G, XG_THREADS);                    // every G thread is done with the records of step t
-        if (t < S) compute_pos(t + 1);
+        if (t < S) compute_pos(t + 1, mv_next);
         nbar_sync(XBAR_G, XG_THREADS);                    // records of step t+1 visible to the group
         XTRACE(0, t, 3);
     }
@@ -262,49 +310,48 @@ __device__ __forceinline__ void x_g_role(const CreffMmaParams& p, const XSmem& s
 
 // ---------------------------------------------------------------------------------------------
 // D role: depthwise 3x3 convolutions.  Warp d = 3 * rp + third owns column third `third` of rows rp and rp + 2 of
-// every 4-row strip and convolves the two rows in one loop (two independent FFMA2 streams per warp).
-//   NOUT = 2: K/V rows from the hr ring (input rows kr..kr+2, columns x..x+2); NOUT = 1: Q rows + residual from lr ring.
+// every 4-row strip and convolves the two rows in one pass (the two rows share input row 2 of the five they read).
+// Everything is addressed with 32-bit shared-window addresses whose per-column parts are compile-time immediates:
+// the column loop is fully unrolled, the 3-column register window rotates by renaming.
 // ---------------------------------------------------------------------------------------------
-template <int NOUT, typename Store>
-__device__ __forceinline__ void x_dw_rows2(const float* ra0, const float* ra1, const float* ra2, const float* rb0, const float* rb1,
-                                           const float* rb2, const int c_lo, const int OUTC, const float2 (&w1)[10], const float2 (&w2)[10],
-                                           Store&& store) {
-    ra0 += c_lo * MC; ra1 += c_lo * MC; ra2 += c_lo * MC;     // columns c_lo .. c_lo + OUTC - 1 (x below is relative to c_lo)
-    rb0 += c_lo * MC; rb1 += c_lo * MC; rb2 += c_lo * MC;
-    float2 wa[3][3], wb[3][3];   // [input row][slot]; slot (x + d) % 3 holds input column x + d
+__device__ __forceinline__ float2 lds_f2(uint32_t a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_f2(uint32_t a, float2 v) { asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory"); }
+
+// one 3x3 depthwise output (two channels): three independent row chains (shorter dependency chains than one 9-deep chain)
+__device__ __forceinline__ float2 x_dw9(const float2 (&w)[10], const float2 (&r0)[3], const float2 (&r1)[3], const float2 (&r2)[3],
+                                        int sa, int sb, int sc) {
+    float2 a0 = __ffma2_rn(w[0], r0[sa], w[9]), a1 = __fmul2_rn(w[3], r1[sa]), a2 = __fmul2_rn(w[6], r2[sa]);
+    a0 = __ffma2_rn(w[1], r0[sb], a0); a1 = __ffma2_rn(w[4], r1[sb], a1); a2 = __ffma2_rn(w[7], r2[sb], a2);
+    a0 = __ffma2_rn(w[2], r0[sc], a0); a1 = __ffma2_rn(w[5], r1[sc], a1); a2 = __ffma2_rn(w[8], r2[sc], a2);
+    return __fadd2_rn(__fadd2_rn(a0, a1), a2);
+}
+
+// Two output rows A (input rows 0..2) and B (input rows 2..4) x NC columns; ra[i] = shared address of this lane's channel
+// pair at input column 0 of input row i.  Columns >= NMIN are computed only when `full` (warp-uniform).
+// emit(x, a1, a2, b1, b2, centreA, centreB): conv 1 / conv 2 results of rows A / B at output column x (a compile-time
+// constant after unrolling), centre = the input sample under the kernel centre.
+template <int NOUT, int NC, int NMIN, typename Emit>
+__device__ __forceinline__ void x_dw_rows5(const uint32_t (&ra)[5], bool full, const float2 (&w1)[10], const float2 (&w2)[10], Emit&& emit) {
+    float2 win[5][3];   // [input row][slot]; slot (x + d) % 3 holds input column x + d
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        wa[0][c] = *reinterpret_cast<const float2*>(ra0 + c * MC); wa[1][c] = *reinterpret_cast<const float2*>(ra1 + c * MC);
-        wa[2][c] = *reinterpret_cast<const float2*>(ra2 + c * MC);
-        wb[0][c] = *reinterpret_cast<const float2*>(rb0 + c * MC); wb[1][c] = *reinterpret_cast<const float2*>(rb1 + c * MC);
-        wb[2][c] = *reinterpret_cast<const float2*>(rb2 + c * MC);
-    }
-    auto conv = [](const float2 (&w)[10], const float2 (&win)[3][3], int sa, int sb, int sc) {
-        // three independent row chains per output (shorter dependency chains than one 9-deep chain)
-        float2 a0 = __ffma2_rn(w[0], win[0][sa], w[9]), a1 = __fmul2_rn(w[3], win[1][sa]), a2 = __fmul2_rn(w[6], win[2][sa]);
-        a0 = __ffma2_rn(w[1], win[0][sb], a0); a1 = __ffma2_rn(w[4], win[1][sb], a1); a2 = __ffma2_rn(w[7], win[2][sb], a2);
-        a0 = __ffma2_rn(w[2], win[0][sc], a0); a1 = __ffma2_rn(w[5], win[1][sc], a1); a2 = __ffma2_rn(w[8], win[2][sc], a2);
-        return __fadd2_rn(__fadd2_rn(a0, a1), a2);
-    };
-#pragma unroll 1
-    for (int xb = 0; xb < OUTC; xb += 3) {
+    for (int c = 0; c < 2; ++c)
 #pragma unroll
-        for (int u = 0; u < 3; ++u) {
-            const int x = xb + u;
-            if (x < OUTC) {
-                const int sa = u, sb = (u + 1) % 3, sc = (u + 2) % 3;     // slots of columns x, x+1, x+2
-                wa[0][sc] = *reinterpret_cast<const float2*>(ra0 + (x + 2) * MC);
-                wa[1][sc] = *reinterpret_cast<const float2*>(ra1 + (x + 2) * MC);
-                wa[2][sc] = *reinterpret_cast<const float2*>(ra2 + (x + 2) * MC);
-                wb[0][sc] = *reinterpret_cast<const float2*>(rb0 + (x + 2) * MC);
-                wb[1][sc] = *reinterpret_cast<const float2*>(rb1 + (x + 2) * MC);
-                wb[2][sc] = *reinterpret_cast<const float2*>(rb2 + (x + 2) * MC);
-                const float2 a1 = conv(w1, wa, sa, sb, sc), b1 = conv(w1, wb, sa, sb, sc);
-                float2 a2 = make_float2(0.f, 0.f), b2 = a2;
-                if (NOUT == 2) { a2 = conv(w2, wa, sa, sb, sc); b2 = conv(w2, wb, sa, sb, sc); }
-                store(0, c_lo + x, a1, a2, wa[1][sb]);
-                store(1, c_lo + x, b1, b2, wb[1][sb]);
-            }
+        for (int i = 0; i < 5; ++i) win[i][c] = lds_f2(ra[i] + c * (MC * 4));
+#pragma unroll
+    for (int x = 0; x < NC; ++x) {
+        if (x < NMIN || full) {
+            const int sa = x % 3, sb = (x + 1) % 3, sc = (x + 2) % 3;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) win[i][sc] = lds_f2(ra[i] + (x + 2) * (MC * 4));
+            const float2 a1 = x_dw9(w1, win[0], win[1], win[2], sa, sb, sc), b1 = x_dw9(w1, win[2], win[3], win[4], sa, sb, sc);
+            float2 a2 = make_float2(0.f, 0.f), b2 = a2;
+            if (NOUT == 2) { a2 = x_dw9(w2, win[0], win[1], win[2], sa, sb, sc); b2 = x_dw9(w2, win[2], win[3], win[4], sa, sb, sc); }
+            emit(x, a1, a2, b1, b2, win[1][sb], win[3][sb]);
         }
     }
 }
@@ -314,13 +361,29 @@ __device__ __forceinline__ void x_d_role(const CreffMmaParams& p, const XSmem& s
     using Cf = XCfg<K>;
     const int lane = threadIdx.x & 31, d = (threadIdx.x >> 5) - XG_WARPS, third = d % 3, rp = d / 3;
     constexpr int KV3 = (Cf::KVC + 2) / 3, Q3 = (XSW + 2) / 3;              // columns per third
-    const int kv_lo = third * KV3, kv_n = min(Cf::KVC - kv_lo, KV3);
-    const int q_lo = third * Q3, q_n = min(XSW - q_lo, Q3);
-    const float* hring = reinterpret_cast<const float*>(sm.rings) + 2 * lane;
-    const float* lring = reinterpret_cast<const float*>(sm.rings + Cf::HR_BYTES) + 2 * lane;
+    constexpr int KVL = Cf::KVC - 2 * KV3, QL = XSW - 2 * Q3;               // columns of the last third
+    static_assert(KVL > 0 && KVL <= KV3 && QL > 0 && QL <= Q3, "column thirds");
+    const int kv_lo = third * KV3, q_lo = third * Q3;
+    const bool full = third != 2;
     const int lane_chunk = lane >> 2;
     const uint32_t lane_off = (uint32_t)((lane & 3) * 4);
     const float2* const swl = sm.s_dw + lane;
+    // shared-window addresses: this lane's channel pair at the first input column of its third, ring row 0
+    const uint32_t hring = s_u32(sm.rings) + (uint32_t)(kv_lo * (MC * 4) + lane * 8);
+    const uint32_t lring = s_u32(sm.rings) + (uint32_t)(Cf::HR_BYTES + q_lo * (MC * 4) + lane * 8);
+    const uint32_t kbase = s_u32(sm.sK), qbase = s_u32(sm.sQ);
+    const uint32_t resbase = s_u32(sm.sRes) + (uint32_t)(((rp * XSW + q_lo) * XRES_LD + 2 * lane) * 4);
+    // per-column store offsets inside a K/V ring row / the Q tile (the swizzle key depends on the column)
+    uint32_t kst[KV3], qst[Q3];
+#pragma unroll
+    for (int x = 0; x < KV3; ++x) kst[x] = kv_off(kv_lo + x, kv_lo + x, lane_chunk) + lane_off;
+#pragma unroll
+    for (int x = 0; x < Q3; ++x) qst[x] = q_off(rp, q_lo + x, lane_chunk) + lane_off;      // row rp + 2: + 2 * XSW * 128 (same key)
+    // columns of this third inside the image (constant over the march)
+    const int fx_lo = x0 - Cf::R + kv_lo, kv_n = full ? KV3 : KVL;
+    const bool cols_ok = fx_lo >= 0 && fx_lo + kv_n <= p.W;
+    // ring slots of the first row of a step (advance by 4 per step)
+    int hs = rp, ks = rp, ls = rp;          // hr ring slot of K/V row krA, K/V ring slot of krA, lr ring slot of Q row qr
 #pragma unroll 1
     for (int t = -1; t <= S; ++t) {
         XTRACE(1, t, 0);
@@ -333,29 +396,48 @@ __device__ __forceinline__ void x_d_role(const CreffMmaParams& p, const XSmem& s
         if (!(p.dbg & 1))
 #endif
         if (t >= 0 || rp < Cf::P0) {
-            const int krA = (t < 0 ? 0 : Cf::P0 + 4 * t) + rp, krB = krA + 2;
+            const int krA = (t < 0 ? 0 : Cf::P0 + 4 * t) + rp;
             const bool haveB = t >= 0 || rp + 2 < Cf::P0;          // initial step: only P0 rows exist
             float2 wk[10], wv[10];
 #pragma unroll
             for (int i = 0; i < 10; ++i) { wk[i] = swl[i * 32]; wv[i] = swl[(10 + i) * 32]; }
-            const float* ra0 = hring + ((krA) % XHR_RING) * (Cf::HC * MC);
-            const float* ra1 = hring + ((krA + 1) % XHR_RING) * (Cf::HC * MC);
-            const float* ra2 = hring + ((krA + 2) % XHR_RING) * (Cf::HC * MC);
-            const float* rb1 = hring + ((krA + 3) % XHR_RING) * (Cf::HC * MC);
-            const float* rb2 = hring + ((krA + 4) % XHR_RING) * (Cf::HC * MC);
+            uint32_t ra[5];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                int slot = hs + i;
+                slot = slot >= XHR_RING ? slot - XHR_RING : slot;
+                ra[i] = hring + (uint32_t)(slot * (Cf::HC * MC * 4));
+            }
+            int ksB = ks + 2;
+            ksB = ksB >= Cf::KVR ? ksB - Cf::KVR : ksB;
+            const uint32_t kA = kbase + (uint32_t)(ks * (Cf::KVC * 128)), kB = kbase + (uint32_t)(ksB * (Cf::KVC * 128));
+            x_dw_rows5<2, KV3, KVL>(ra, full, wk, wv, [&](int x, float2 a1, float2 a2, float2 b1, float2 b2, float2, float2) {
+                sts_u32(kA + kst[x], pack_h2_sat(a1.x, a1.y));
+                sts_u32(kA + kst[x] + (uint32_t)Cf::KV_BYTES, pack_h2_sat(a2.x, a2.y));
+                if (haveB) {
+                    sts_u32(kB + kst[x], pack_h2_sat(b1.x, b1.y));
+                    sts_u32(kB + kst[x] + (uint32_t)Cf::KV_BYTES, pack_h2_sat(b2.x, b2.y));
+                }
+            });
+            // K / V are exactly 0 outside the image (attention zero padding, model/attention.py:199,207): border strips and
+            // the first / last rows overwrite what the convolution (bias included) produced there
             const int fyA = ya - Cf::R + krA;
             const bool okA = fyA >= 0 && fyA < p.H, okB = fyA + 2 >= 0 && fyA + 2 < p.H;
-            const int posA = (krA % Cf::KVR) * Cf::KVC, posB = (krB % Cf::KVR) * Cf::KVC;
-            const int fx0 = x0 - Cf::R;
-            x_dw_rows2<2>(ra0, ra1, ra2, ra2, rb1, rb2, kv_lo, kv_n, wk, wv, [&](int which, int x, float2 a1, float2 a2, float2) {
-                // K / V are exactly 0 outside the image (attention zero padding, model/attention.py:199,207)
-                const int fx = fx0 + x;
-                if (!((which ? okB : okA) && fx >= 0 && fx < p.W)) { a1 = make_float2(0.f, 0.f); a2 = make_float2(0.f, 0.f); }
-                if (which && !haveB) return;
-                const uint32_t off = kv_off((which ? posB : posA) + x, x, lane_chunk) + lane_off;
-                *reinterpret_cast<uint32_t*>(sm.sK + off) = pack_h2_sat(a1.x, a1.y);
-                *reinterpret_cast<uint32_t*>(sm.sV + off) = pack_h2_sat(a2.x, a2.y);
-            });
+            if (!(cols_ok && okA && (okB || !haveB))) {
+#pragma unroll 1
+                for (int x = 0; x < kv_n; ++x) {
+                    const bool okx = fx_lo + x >= 0 && fx_lo + x < p.W;
+                    const uint32_t o = kv_off(kv_lo + x, kv_lo + x, lane_chunk) + lane_off;
+                    if (!(okA && okx)) { sts_u32(kA + o, 0u); sts_u32(kA + o + (uint32_t)Cf::KV_BYTES, 0u); }
+                    if (haveB && !(okB && okx)) { sts_u32(kB + o, 0u); sts_u32(kB + o + (uint32_t)Cf::KV_BYTES, 0u); }
+                }
+            }
+        }
+        if (t >= 0) {
+            hs += 4; hs = hs >= XHR_RING ? hs - XHR_RING : hs;
+            ks += 4; ks = ks >= Cf::KVR ? ks - Cf::KVR : ks;
+        } else {
+            hs = (Cf::P0 + rp) % XHR_RING; ks = (Cf::P0 + rp) % Cf::KVR;
         }
         // ---- Q rows qr, qr+2 (qr = 4(t-1)+rp, relative to ya) from the lr ring; residual = lr_up centre ----
         XTRACE(1, t, 3);
@@ -369,18 +451,21 @@ __device__ __forceinline__ void x_d_role(const CreffMmaParams& p, const XSmem& s
                 float2 wq[10];
 #pragma unroll
                 for (int i = 0; i < 10; ++i) wq[i] = swl[(20 + i) * 32];
-                const int qr = 4 * (t - 1) + rp;
-                const float* ra0 = lring + ((qr) % XLR_RING) * (Cf::LC * MC);
-                const float* ra1 = lring + ((qr + 1) % XLR_RING) * (Cf::LC * MC);
-                const float* ra2 = lring + ((qr + 2) % XLR_RING) * (Cf::LC * MC);
-                const float* rb1 = lring + ((qr + 3) % XLR_RING) * (Cf::LC * MC);
-                const float* rb2 = lring + ((qr + 4) % XLR_RING) * (Cf::LC * MC);
-                x_dw_rows2<1>(ra0, ra1, ra2, ra2, rb1, rb2, q_lo, q_n, wq, wq, [&](int which, int x, float2 a1, float2, float2 centre) {
-                    const int row = rp + 2 * which;
-                    *reinterpret_cast<uint32_t*>(sm.sQ + q_off(row, x, lane_chunk) + lane_off) = pack_h2_sat(a1.x, a1.y);
-                    *reinterpret_cast<float2*>(sm.sRes + (row * XSW + x) * XRES_LD + 2 * lane) = centre;
+                uint32_t ra[5];
+#pragma unroll
+                for (int i = 0; i < 5; ++i) {
+                    int slot = ls + i;
+                    slot = slot >= XLR_RING ? slot - XLR_RING : slot;
+                    ra[i] = lring + (uint32_t)(slot * (Cf::LC * MC * 4));
+                }
+                x_dw_rows5<1, Q3, QL>(ra, full, wq, wq, [&](int x, float2 a1, float2, float2 b1, float2, float2 ca, float2 cb) {
+                    sts_u32(qbase + qst[x], pack_h2_sat(a1.x, a1.y));
+                    sts_u32(qbase + qst[x] + 2 * XSW * 128, pack_h2_sat(b1.x, b1.y));
+                    sts_f2(resbase + (uint32_t)(x * XRES_LD * 4), ca);
+                    sts_f2(resbase + (uint32_t)((2 * XSW + x) * XRES_LD * 4), cb);
                 });
             }
+            ls += 4; ls = ls >= XLR_RING ? ls - XLR_RING : ls;
         }
         xbar_arrive(sm.ddone, t);
         XTRACE(1, t, 5);
@@ -702,12 +787,12 @@ __global__ void __launch_bounds__(XTHREADS, 1) creff_march_kernel(CreffMmaParams
     sm.sQ = sm.rings + Cf::HR_BYTES + Cf::LR_BYTES + Cf::SCRATCH_BYTES;
     sm.sRes = reinterpret_cast<float*>(sm.sQ + Cf::Q_BYTES);
     sm.posw = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(sm.sRes) + Cf::RES_BYTES);
-    sm.posid = reinterpret_cast<int2*>(sm.posw + Cf::PMAX);
+    sm.posa = reinterpret_cast<uint4*>(sm.posw + Cf::PMAX);
     // classifier weights are staged in the Q tile: C moves them to registers in its prologue, and D's first Q write
     // (step 1) waits for C's prologue arrival on qlempty(-1)
     sm.s_wc = reinterpret_cast<__half*>(sm.sQ);                             // [32][XCLS_LD]
     sm.s_bc = reinterpret_cast<float*>(sm.s_wc + 32 * XCLS_LD);             // [32]
-    sm.s_dw = reinterpret_cast<float2*>(sm.posid + Cf::PMAX);
+    sm.s_dw = reinterpret_cast<float2*>(sm.posa + Cf::PMAX);
     sm.gfull = reinterpret_cast<uint64_t*>(sm.s_dw + 3 * 10 * 32);
     sm.ddone = sm.gfull + XNB;
     sm.cdone = sm.ddone + XNB;
@@ -724,10 +809,10 @@ __global__ void __launch_bounds__(XTHREADS, 1) creff_march_kernel(CreffMmaParams
 
     if (tid == 0) {
         for (int i = 0; i < XNB; ++i) {
-            xbar_init(sm.gfull + i, XG_THREADS);
-            xbar_init(sm.ddone + i, XD_THREADS);
-            xbar_init(sm.cdone + i, XC_THREADS);
-            xbar_init(sm.qlempty + i, XC_THREADS);
+            xbar_init(sm.gfull + i, XG_WARPS);
+            xbar_init(sm.ddone + i, XD_WARPS);
+            xbar_init(sm.cdone + i, XC_WARPS);
+            xbar_init(sm.qlempty + i, XC_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -802,6 +887,7 @@ static int creff_march_launch_k(CreffMmaParams& p, int lr_dtype, cudaStream_t st
 }
 
 int creff_march_launch(CreffMmaParams& p, int k, int lr_dtype, cudaStream_t st) {
+    if (p.H < 2 || p.W < 2 || p.h < 2 || p.w < 2) ARSEG_UNSUPPORTED("creff_march: maps must be at least 2x2 (hr %dx%d, lr %dx%d)", p.H, p.W, p.h, p.w);
     switch (k) {
         case 3: return creff_march_launch_k<3>(p, lr_dtype, st);
         case 5: return creff_march_launch_k<5>(p, lr_dtype, st);

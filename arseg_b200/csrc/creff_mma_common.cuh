@@ -85,7 +85,7 @@ __device__ __forceinline__ void mflow_at(const CreffMmaParams& p, int n, int fy,
 
 // Per-position gather record: 4 tap weights (invalid taps already zeroed) + packed source address:
 // info = (pixel index of the NW tap, clamped into the image) << 2 | dx << 1 | dy, or -1 = "all zero".
-struct PosRec { float4 w; int info; };
+struct PosRec { float4 w; int info; int cx, cy; };   // (cx, cy) = the clamped NW tap (info >> 2 = cy * width + cx)
 
 // warped-hr sample (evaluation.py:61-87) at feature pixel (fy,fx); zero outside the image (depthwise padding)
 // rcp_w / rcp_h > 0: 2/(W-1), 2/(H-1) in f64 -- the grid normalisation (evaluation.py:80-81) is then a multiply
@@ -93,7 +93,7 @@ struct PosRec { float4 w; int info; };
 // mv_raw != nullptr: the position's MV was loaded by the caller (int16 quarter-pel pair at feature resolution).
 __device__ __forceinline__ PosRec pos_hr(const CreffMmaParams& p, int n, int fy, int fx, double rcp_w = 0.0, double rcp_h = 0.0,
                                          const int* mv_raw = nullptr) {
-    PosRec r; r.w = make_float4(0.f, 0.f, 0.f, 0.f); r.info = -1;
+    PosRec r; r.w = make_float4(0.f, 0.f, 0.f, 0.f); r.info = -1; r.cx = r.cy = 0;
     if (fy < 0 || fy >= p.H || fx < 0 || fx >= p.W) return r;
     float ix = (float)fx, iy = (float)fy;
     if (p.flow) {
@@ -124,17 +124,19 @@ __device__ __forceinline__ PosRec pos_hr(const CreffMmaParams& p, int n, int fy,
     const int cxa = min(max(xa, 0), p.W - 1), cxb = min(max(xb, 0), p.W - 1);
     const int cya = min(max(ya, 0), p.H - 1), cyb = min(max(yb, 0), p.H - 1);
     r.info = ((cya * p.W + cxa) << 2) | ((cxb - cxa) << 1) | (cyb - cya);
+    r.cx = cxa; r.cy = cya;
     return r;
 }
 // lr_up sample (model/attention.py:191, bilinear align_corners=True); zero outside the image
 __device__ __forceinline__ PosRec pos_lr(const CreffMmaParams& p, float lsh, float lsw, int fy, int fx) {
-    PosRec r; r.w = make_float4(0.f, 0.f, 0.f, 0.f); r.info = -1;
+    PosRec r; r.w = make_float4(0.f, 0.f, 0.f, 0.f); r.info = -1; r.cx = r.cy = 0;
     if (fy < 0 || fy >= p.H || fx < 0 || fx >= p.W) return r;
     int ya, yb, xa, xb; float lya, lyb, lxa, lxb;
     bilinear_src(lsh, fy, p.h, ARSEG_RESIZE_BILINEAR_AC, ya, yb, lya, lyb);
     bilinear_src(lsw, fx, p.w, ARSEG_RESIZE_BILINEAR_AC, xa, xb, lxa, lxb);
     r.w = make_float4(lya * lxa, lya * lxb, lyb * lxa, lyb * lxb);
     r.info = ((ya * p.w + xa) << 2) | ((xb - xa) << 1) | (yb - ya);
+    r.cx = xa; r.cy = ya;
     return r;
 }
 

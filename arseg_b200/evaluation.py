@@ -138,3 +138,62 @@ class NonKeyEngine:
         self.plan.run()
         preds_pinned.copy_(self.preds, non_blocking=True)
         return preds_pinned
+
+    def host_pipeline(self) -> "HostPipeline":
+        return HostPipeline(self)
+
+
+class HostPipeline:
+    """Streaming end-to-end path: GOP after GOP from pinned host memory (the evaluation loop of evaluation.py:161-209
+    with the DataLoader's batches already pinned).  Step i's host->device copies (frames fp32 + MV int16) run on a copy
+    stream into one of two device staging sets while step i-1 computes; the class maps of step i go back on a third
+    stream while step i+1 computes.  Every step still moves all its inputs and its result over PCIe -- only the
+    serialisation between copy and compute is removed.
+
+        pipe = eng.host_pipeline()
+        for imgs, mv, out in batches: pipe.submit(imgs, mv, out)     # asynchronous, in order
+        pipe.drain()                                                 # current stream waits for the last D2H
+    """
+
+    def __init__(self, eng: NonKeyEngine):
+        self.eng = eng
+        dev = eng.device
+        with torch.cuda.device(dev):
+            self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            self.stage = [(torch.empty_like(eng.imgs), torch.empty_like(eng.mv)) for _ in range(2)]
+            self.h2d_done = [torch.cuda.Event() for _ in range(2)]
+            self.stage_free = [torch.cuda.Event() for _ in range(2)]
+            self.computed = torch.cuda.Event()
+            self.d2h_done = torch.cuda.Event()
+        self.k = 0
+
+    def submit(self, imgs_pinned: torch.Tensor, mv_pinned: torch.Tensor, preds_pinned: torch.Tensor) -> None:
+        eng, i = self.eng, self.k & 1
+        with torch.cuda.device(eng.device):
+            main = torch.cuda.current_stream()
+            s_imgs, s_mv = self.stage[i]
+            if self.k == 0:
+                self.s_in.wait_stream(main)               # ordered after whatever the caller enqueued (timing events too)
+            else:
+                self.s_in.wait_event(self.stage_free[i])  # step k-2's staging set has been consumed
+            with torch.cuda.stream(self.s_in):
+                s_imgs.copy_(imgs_pinned, non_blocking=True)
+                s_mv.copy_(mv_pinned, non_blocking=True)
+                self.h2d_done[i].record(self.s_in)
+            main.wait_event(self.h2d_done[i])
+            eng.imgs.copy_(s_imgs, non_blocking=True)     # device-to-device into the captured graph's static inputs
+            eng.mv.copy_(s_mv, non_blocking=True)
+            self.stage_free[i].record(main)
+            if self.k > 0:
+                main.wait_event(self.d2h_done)            # the previous class maps have left eng.preds
+            eng.plan.run()
+            self.computed.record(main)
+            self.s_out.wait_event(self.computed)
+            with torch.cuda.stream(self.s_out):
+                preds_pinned.copy_(eng.preds, non_blocking=True)
+                self.d2h_done.record(self.s_out)
+        self.k += 1
+
+    def drain(self) -> None:
+        if self.k:
+            torch.cuda.current_stream(self.eng.device).wait_event(self.d2h_done)

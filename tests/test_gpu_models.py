@@ -146,3 +146,31 @@ def test_full_size_properties_camvid_psp():
         assert torch.equal(pi, p[i:i + 1]) and torch.equal(li, l[i:i + 1]) and torch.equal(ai, a[i:i + 1])
     assert torch.equal(a.long(), l.argmax(1))
     assert (l.exp().sum(1) - 1).abs().max() < 1e-4
+
+
+def test_host_pipeline_matches_resident_steps():
+    """HostPipeline (H2D of step i+1 overlapping the compute of step i, D2H on a third stream) returns, for every
+    step, exactly the class maps of the same inputs run one at a time from device-resident buffers."""
+    g = load_golden("camvid_psp18_s05")
+    arch, _, sd, imgs, ref_p, mv, flow, scale = case_setup(g)
+    H, W = imgs.shape[-2:]
+    N, STEPS = 2, 5
+    eng = ev.NonKeyEngine(arch, sd, N, H, W, scale, "f16", device=DEV)
+    batches = []
+    for s in range(STEPS):
+        fr = torch.cat([synth.synth_frame(1, H, W, 300 + 10 * s + i) for i in range(N)]).pin_memory()
+        mvs = torch.from_numpy(np.stack([synth.synth_mv_int16(H, W, 400 + 10 * s + i, distance=1 + 2 * s + i) for i in range(N)])).pin_memory()
+        batches.append((fr, mvs, torch.zeros((N, H, W), dtype=torch.uint8).pin_memory()))
+    want = []
+    for fr, mvs, _ in batches:
+        eng.set_inputs(fr.to(DEV), mvs.to(DEV), ref_p.to(DEV))
+        want.append(eng.step().cpu().clone())
+    torch.cuda.synchronize()
+    pipe = eng.host_pipeline()
+    for fr, mvs, out in batches:
+        pipe.submit(fr, mvs, out)
+    pipe.drain()
+    torch.cuda.synchronize()
+    for s in range(STEPS):
+        assert torch.equal(batches[s][2], want[s]), s
+    assert not torch.equal(want[0], want[1])
