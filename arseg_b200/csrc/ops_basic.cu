@@ -1,6 +1,7 @@
 // ops_basic.cu -- layout conversion, resampling, pooling, gating, stem conv (HBM-bound glue ops).
 // All kernels are written for sm_100a; NHWC activations, 16-byte vectorised along C where aligned.
 #include "common.cuh"
+#include <cstdlib>
 #include <mutex>
 
 namespace arseg {
@@ -341,6 +342,11 @@ static inline int grid_1d(long long total, int block) {
 
 using namespace arseg;
 
+namespace arseg {
+int stem_mma_launch(const float* in, const float* w, const float* scale, const float* shift, void* out, int out_dtype, int N, int H,
+                    int W, int Ho, int Wo, cudaStream_t st);   // stem_mma.cu
+}
+
 extern "C" {
 
 int arseg_abi_version(void) { return ARSEG_ABI_VERSION; }
@@ -520,6 +526,11 @@ int arseg_conv_stem7x7s2(const float* in, const float* w, const float* scale, co
     ARSEG_REQUIRE(in && w && scale && shift && out && N > 0 && H > 0 && W > 0 && Cout > 0, "stem: bad args");
     ARSEG_REQUIRE(Cout <= 64, "stem: Cout=%d > 64", Cout);
     const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
+    // 16-bit plans: tensor-core stem (stem_mma.cu); ARSEG_STEM_SIMT=1 keeps the CUDA-core kernel for A/B runs
+    if ((out_dtype == ARSEG_F16 || out_dtype == ARSEG_BF16) && Cout == 64) {
+        const char* e = getenv("ARSEG_STEM_SIMT");
+        if (!(e && atoi(e) != 0)) return stem_mma_launch(in, w, scale, shift, out, out_dtype, N, H, W, Ho, Wo, as_stream(stream));
+    }
     dim3 grid(ceil_div(Wo, STEM_TW), ceil_div(Ho, STEM_TH), N);
     ARSEG_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "stem: dims too large");
     static bool configured[64] = {false};

@@ -184,9 +184,10 @@ def test_conv_tcgen05(case, engine, dtype, tol):
 
 
 @pytest.mark.parametrize("N,H,W,Cout", [(2, 37, 53, 64), (1, 64, 130, 64), (1, 23, 18, 40)])
-@pytest.mark.parametrize("dtype,tol", [(torch.float32, FP32_TOL), (torch.float16, 2e-3)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, FP32_TOL), (torch.float16, 2e-3), (torch.bfloat16, 2e-2)])
 def test_conv_stem(N, H, W, Cout, dtype, tol):
-    """conv1 7x7 stride 2 pad 3 (no bias) + BN(eval) + ReLU, model/extractors.py:112-114,148-150."""
+    """conv1 7x7 stride 2 pad 3 (no bias) + BN(eval) + ReLU, model/extractors.py:112-114,148-150.
+    16-bit dtypes with Cout = 64 run the tensor-core stem (stem_mma.cu), everything else the CUDA-core kernel."""
     x, w = rnd(N, 3, H, W, seed=40), rnd(Cout, 3, 7, 7, seed=41) * (1.0 / 147 ** 0.5)
     scale, shift = torch.rand(Cout) + 0.5, rnd(Cout, seed=42) * 0.1
     ref = F.relu(F.conv2d(x.double(), w.double(), None, 2, 3) * scale.double().view(1, -1, 1, 1) + shift.double().view(1, -1, 1, 1)).float()
