@@ -507,28 +507,27 @@ __device__ __forceinline__ void x_c_role(const CreffMmaParams& p, const XSmem& s
                 if (okx && (unsigned)(ky - qy1) < (unsigned)K) mB[(2 * j + e) >> 5] |= 1u << ((2 * j + e) & 31);
             }
     }
-    // ldmatrix row addresses: key row ky and the column part of the byte offset, per n-tile (QK: 8 keys per tile,
-    // lanes 0-7 of each address group; PV: 16 keys per tile).  ky of a lane is kyq_lo[j] or kyq_lo[j]+1 (compile-time
-    // kyq_lo), selected per lane by a bit of kyq_hi; the ring slot of a key row changes every step.
-    uint32_t cq[NT8Q], cv[Cf::NT16];
-    uint32_t kyq_hi = 0, kyv_hi = 0;
+    // ldmatrix row addresses per n-tile (QK: 8 keys per tile, lanes 0-7 of each address group; PV: 16 keys per tile).
+    // Ring byte offsets of this lane's ldmatrix rows, one register per n-tile: (ring slot of the key row) * ROWB + the
+    // column part.  The column part is < ROWB, so the slot is offset / ROWB and the per-step update is "add four rows,
+    // wrap at the ring size" -- no per-step row table, no selects.
+    constexpr uint32_t ROWB = Cf::KVC * 128, RINGB = Cf::KVR * ROWB;
+    uint32_t aq[NT8Q], av[Cf::NT16];
 #pragma unroll
     for (int j = 0; j < NT8Q; ++j) {
         int nk = 8 * j + (lane & 7);
         nk = nk < Cf::NK ? nk : Cf::NK - 1;
         const int ky = nk / Cf::WN, kx = nk - ky * Cf::WN, col = 4 * cw + kx;
-        if (ky != (8 * j) / Cf::WN) kyq_hi |= 1u << j;
-        cq[j] = (uint32_t)(col * 128 + (((mi ^ col) & 7) << 4));             // chunk mi; chunk 4+mi = ^ 64
+        aq[j] = (uint32_t)ky * ROWB + (uint32_t)(col * 128 + (((mi ^ col) & 7) << 4));             // chunk mi; chunk 4+mi = ^ 64
     }
 #pragma unroll
     for (int i = 0; i < Cf::NT16; ++i) {
         int nk = 16 * i + ((mi & 1) << 3) + (lane & 7);
         nk = nk < Cf::NK ? nk : Cf::NK - 1;
         const int ky = nk / Cf::WN, kx = nk - ky * Cf::WN, col = 4 * cw + kx;
-        const int ky_lo = (16 * i < Cf::NK ? 16 * i : Cf::NK - 1) / Cf::WN;
-        kyv_hi |= (uint32_t)(ky - ky_lo) << (2 * i);                           // 0..3
-        cv[i] = (uint32_t)(col * 128 + ((((mi >> 1) ^ col) & 7) << 4));        // chunk (mi>>1) + 2cp = ^ (cp << 5)
+        av[i] = (uint32_t)ky * ROWB + (uint32_t)(col * 128 + ((((mi >> 1) ^ col) & 7) << 4));        // chunk (mi>>1) + 2cp = ^ (cp << 5)
     }
+    static_assert(Cf::WN <= Cf::KVR, "a key patch fits the ring");
     // classifier B fragments (final_conv weights, f16) and biases stay in registers for the whole march
     constexpr int NCTA = NCT > 0 ? NCT : 1;
     uint32_t wf[NCTA][4][2];
@@ -558,20 +557,11 @@ __device__ __forceinline__ void x_c_role(const CreffMmaParams& p, const XSmem& s
     float* const ol = p.out_logits ? p.out_logits + (size_t)n * p.ncls * plane + (size_t)(2 * t) * plane : nullptr;
     float* const op = p.out_p ? p.out_p + (size_t)n * MC * plane + (size_t)(2 * t) * plane : nullptr;
     uint8_t* const oa = p.out_argmax ? p.out_argmax + (size_t)n * plane : nullptr;
-    int s4 = 0;                                           // (4 s) mod KVR
     // the mbarrier phase of a step is (step+1)/XNB: C has no step -1, so arrive for it once (nobody waits on it)
     xbar_arrive(sm.cdone, -1);
     xbar_arrive(sm.qlempty, -1);
 #pragma unroll 1
     for (int s = 0; s < S; ++s, offA += 4 * (size_t)W) {
-        // byte offsets of the K/V ring rows of this step's key rows
-        uint32_t rowb[Cf::WN];
-#pragma unroll
-        for (int ky = 0; ky < Cf::WN; ++ky) {
-            int slot = s4 + ky;
-            slot = slot >= Cf::KVR ? slot - Cf::KVR : slot;
-            rowb[ky] = (uint32_t)(slot * (Cf::KVC * 128));
-        }
         XTRACE(2, s, 0);
         xbar_wait(sm.ddone, s + 1);
         XTRACE(2, s, 1);
@@ -592,10 +582,7 @@ __device__ __forceinline__ void x_c_role(const CreffMmaParams& p, const XSmem& s
                 for (int jj = 0; jj < XQG; ++jj) {
                     const int j = jg + jj;
                     if (j < NT8Q) {
-                        constexpr int dummy = 0; (void)dummy;
-                        const int ky_lo = (8 * j) / Cf::WN;
-                        const uint32_t rb = ((kyq_hi >> j) & 1u) ? rowb[ky_lo + 1 < Cf::WN ? ky_lo + 1 : ky_lo] : rowb[ky_lo];
-                        const uint32_t a0 = kb + rb + cq[j];
+                        const uint32_t a0 = kb + aq[j];
                         ldsm_x4(bf[jj][0], a0);
                         ldsm_x4(bf[jj][1], a0 ^ 64u);
                         const int b0 = 2 * j, b1 = 2 * j + 1;
@@ -657,26 +644,31 @@ __device__ __forceinline__ void x_c_role(const CreffMmaParams& p, const XSmem& s
         float O[8][4], Ssum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int c = 0; c < 8; ++c) O[c][0] = O[c][1] = O[c][2] = O[c][3] = 0.f;
+        {
+            // V fragments one key tile ahead of the MMAs that consume them (ldmatrix latency off the MMA chain)
+            uint32_t v[2][4][4];
 #pragma unroll
-        for (int i = 0; i < Cf::NT16; ++i) {
-            const int ky_lo = (16 * i < Cf::NK ? 16 * i : Cf::NK - 1) / Cf::WN;
-            const uint32_t sel = (kyv_hi >> (2 * i)) & 3u;
-            const uint32_t r0 = rowb[ky_lo], r1 = rowb[ky_lo + 1 < Cf::WN ? ky_lo + 1 : ky_lo], r2 = rowb[ky_lo + 2 < Cf::WN ? ky_lo + 2 : ky_lo];
-            uint32_t rsel = sel == 0 ? r0 : (sel == 1 ? r1 : r2);
-            if (Cf::WN < 7) rsel = sel == 3 ? rowb[ky_lo + 3 < Cf::WN ? ky_lo + 3 : ky_lo] : rsel;   // 16 keys span up to 4 rows when WN = 6
-            const uint32_t a0 = vb + rsel + cv[i];
+            for (int cp = 0; cp < 4; ++cp) ldsm_x4_t(v[0][cp], (vb + av[0]) ^ (uint32_t)(cp << 5));
 #pragma unroll
-            for (int cp = 0; cp < 4; ++cp) {
-                uint32_t v[4];
-                ldsm_x4_t(v, a0 ^ (uint32_t)(cp << 5));
-                mma16816(O[2 * cp], pa[i], v[0], v[1]);
-                mma16816(O[2 * cp + 1], pa[i], v[2], v[3]);
+            for (int i = 0; i < Cf::NT16; ++i) {
+                if (i + 1 < Cf::NT16) {
+#pragma unroll
+                    for (int cp = 0; cp < 4; ++cp) ldsm_x4_t(v[(i + 1) & 1][cp], (vb + av[i + 1]) ^ (uint32_t)(cp << 5));
+                }
+#pragma unroll
+                for (int cp = 0; cp < 4; ++cp) {
+                    mma16816(O[2 * cp], pa[i], v[i & 1][cp][0], v[i & 1][cp][1]);
+                    mma16816(O[2 * cp + 1], pa[i], v[i & 1][cp][2], v[i & 1][cp][3]);
+                }
+                mma16816(Ssum, pa[i], 0x3C003C00u, 0x3C003C00u);      // B = all ones (f16): every column = row sum of P
             }
-            mma16816(Ssum, pa[i], 0x3C003C00u, 0x3C003C00u);      // B = all ones (f16): every column = row sum of P
         }
         xbar_arrive(sm.cdone, s);
         XTRACE(2, s, 4);
-        s4 += 4; s4 = s4 >= Cf::KVR ? s4 - Cf::KVR : s4;
+#pragma unroll
+        for (int j = 0; j < NT8Q; ++j) { aq[j] += 4 * ROWB; aq[j] = aq[j] >= RINGB ? aq[j] - RINGB : aq[j]; }
+#pragma unroll
+        for (int i = 0; i < Cf::NT16; ++i) { av[i] += 4 * ROWB; av[i] = av[i] >= RINGB ? av[i] - RINGB : av[i]; }
         // fused = lr_up + O / sum (model/attention.py:210); the sum is that of the f16-rounded P the MMA consumed
         {
             const float inv0 = rcp_approx(Ssum[0]), inv1 = rcp_approx(Ssum[2]);
