@@ -125,6 +125,61 @@ __global__ void __launch_bounds__(256) resize_nhwc_kernel(const T* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------
+// Exact x2 bilinear up-sampling, align_corners=False (F.upsample(scale_factor=2), model/pspnet.py:38-41): one thread
+// per (input pixel, VEC channels) loads the clamped 3x3 neighbourhood once and writes the 2x2 output block, 2.25 loads
+// per output instead of 4.  Same arithmetic as resize_nhwc_kernel, expression for expression: for an exact factor of 2
+// the ATen source coordinates are i - 0.25 / i + 0.25, i.e. weights (0.25, 0.75) / (0.75, 0.25), and (1, 0) in row /
+// column 0 where the coordinate clamps to 0.
+// ------------------------------------------------------------------------------------------
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) upsample2x_nhwc_kernel(const T* __restrict__ src, T* __restrict__ dst, int N, int Hi, int Wi, int C,
+                                                              int dcs, int dco) {
+    const int cv = C / VEC;
+    const long long total = (long long)N * Hi * Wi * cv;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % cv) * VEC;
+        long long r = idx / cv;
+        const int j = (int)(r % Wi); r /= Wi;
+        const int i = (int)(r % Hi);
+        const int n = (int)(r / Hi);
+        const int ys[3] = {i > 0 ? i - 1 : 0, i, i < Hi - 1 ? i + 1 : i};
+        const int xs[3] = {j > 0 ? j - 1 : 0, j, j < Wi - 1 ? j + 1 : j};
+        const T* s = src + (size_t)n * Hi * Wi * C + c;
+        float v[3][3][VEC];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                const Pack<T, VEC> pk = *reinterpret_cast<const Pack<T, VEC>*>(s + ((size_t)ys[a] * Wi + xs[b]) * C);
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) v[a][b][k] = to_f32(pk.v[k]);
+            }
+        // output row 2i + dy reads input rows (dy, dy + 1) of the neighbourhood with weights wy[dy]; columns likewise
+        const float wy0[2] = {i == 0 ? 1.f : 0.25f, 0.75f}, wy1[2] = {i == 0 ? 0.f : 0.75f, 0.25f};
+        const float wx0[2] = {j == 0 ? 1.f : 0.25f, 0.75f}, wx1[2] = {j == 0 ? 0.f : 0.75f, 0.25f};
+        T* d = dst + (((size_t)n * 2 * Hi + 2 * i) * (2 * Wi) + 2 * j) * dcs + dco + c;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                Pack<T, VEC> o;
+#pragma unroll
+                for (int k = 0; k < VEC; ++k)
+                    o.v[k] = from_f32<T>(wy0[dy] * (wx0[dx] * v[dy][dx][k] + wx1[dx] * v[dy][dx + 1][k]) +
+                                         wy1[dy] * (wx0[dx] * v[dy + 1][dx][k] + wx1[dx] * v[dy + 1][dx + 1][k]));
+                *reinterpret_cast<Pack<T, VEC>*>(d + ((size_t)dy * 2 * Wi + dx) * dcs) = o;
+            }
+    }
+}
+
+template <typename T, int VEC>
+static void upsample2x_launch(const T* s, T* d, int N, int Hi, int Wi, int C, int dcs, int dco, cudaStream_t st) {
+    const long long total = (long long)N * Hi * Wi * (C / VEC);
+    const long long cap = (long long)sm_count() * 16, blocks = (total + 255) / 256;
+    upsample2x_nhwc_kernel<T, VEC><<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(s, d, N, Hi, Wi, C, dcs, dco);
+}
+
+// ------------------------------------------------------------------------------------------
 // adaptive average pool NHWC: block = (32 channel lanes, 8 window rows); grid = (N*Ho*Wo, ceil(C/32))
 // ------------------------------------------------------------------------------------------
 template <typename T, bool MAXP>
@@ -401,7 +456,14 @@ int arseg_resize_nhwc(const void* src, void* dst, int dtype, int N, int Hi, int 
     ARSEG_REQUIRE(mode >= 0 && mode <= 2 && dcs >= C && dco >= 0 && dco + C <= dcs, "resize_nhwc: bad mode/slice");
     const float sh = resize_scale(Hi, Ho, mode), sw = resize_scale(Wi, Wo, mode);
     cudaStream_t st = as_stream(stream);
-    if (dtype == ARSEG_F32) {
+    const bool x2 = mode == ARSEG_RESIZE_BILINEAR && Ho == 2 * Hi && Wo == 2 * Wi && ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0);
+    if (x2 && dtype == ARSEG_F32 && C % 4 == 0 && dcs % 4 == 0 && dco % 4 == 0) {
+        upsample2x_launch<float, 4>((const float*)src, (float*)dst, N, Hi, Wi, C, dcs, dco, st);
+    } else if (x2 && dtype == ARSEG_BF16 && C % 8 == 0 && dcs % 8 == 0 && dco % 8 == 0) {
+        upsample2x_launch<__nv_bfloat16, 8>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, N, Hi, Wi, C, dcs, dco, st);
+    } else if (x2 && dtype == ARSEG_F16 && C % 8 == 0 && dcs % 8 == 0 && dco % 8 == 0) {
+        upsample2x_launch<__half, 8>((const __half*)src, (__half*)dst, N, Hi, Wi, C, dcs, dco, st);
+    } else if (dtype == ARSEG_F32) {
         const float* s = (const float*)src; float* d = (float*)dst;
         if (C % 4 == 0 && dcs % 4 == 0 && dco % 4 == 0 && ((uintptr_t)s % 16 == 0) && ((uintptr_t)d % 16 == 0)) {
             resize_nhwc_kernel<float, 4><<<resize_grid(N, Ho), 256, 0, st>>>(s, d, N, Hi, Wi, C, Ho, Wo, dcs, dco, mode, sh, sw);

@@ -123,6 +123,19 @@ def resize_nchw(x: torch.Tensor, size, mode: int) -> torch.Tensor:
     return out
 
 
+def resize_nhwc(x: torch.Tensor, size, mode: int, out: Optional[torch.Tensor] = None, coff: int = 0) -> torch.Tensor:
+    """Resize an NHWC tensor (fp32 / fp16 / bf16) into `out[..., coff:coff+C]` (a channel slice = fused torch.cat)."""
+    _chk_cuda("resize_nhwc", x)
+    N, Hi, Wi, C = x.shape
+    Ho, Wo = int(size[0]), int(size[1])
+    if out is None:
+        out = torch.empty((N, Ho, Wo, C), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        L.check(L.load().arseg_resize_nhwc(_p(x), _p(out), dtype_code(x.dtype), N, Hi, Wi, C, Ho, Wo, out.shape[-1], coff, mode, _stream()),
+                "resize_nhwc")
+    return out
+
+
 def resize_argmax(logits: torch.Tensor, size, mode: int, want_logits: bool = False):
     logits = logits.contiguous()
     _chk_cuda("resize_argmax", logits)

@@ -95,6 +95,28 @@ def test_resize_nchw(mode, kw, sizes):
     assert rel_err(got, ref) < FP32_TOL
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, FP32_TOL), (torch.float16, 2e-3), (torch.bfloat16, 1.6e-2)])
+@pytest.mark.parametrize("hw,C", [((45, 60), 64), ((1, 7), 8), ((6, 1), 16), ((9, 12), 40)])
+def test_resize_nhwc_x2_and_generic(hw, C, dtype, tol):
+    """F.upsample(scale_factor=2, bilinear) (model/pspnet.py:38-41): the exact-x2 kernel and the generic kernel agree
+    (to fp32 rounding: the compiler may contract the two kernels' multiply-adds differently), both equal to
+    F.interpolate(align_corners=False); channel-slice destination."""
+    hi, wi = hw
+    x = rnd(2, C, hi, wi, seed=12)
+    xr = x.to(dtype).float()
+    ref = F.interpolate(xr, size=(2 * hi, 2 * wi), mode="bilinear", align_corners=False)
+    nhwc = ops.nchw_to_nhwc(x.to(DEV), dtype)
+    out = torch.zeros((2, 2 * hi, 2 * wi, C + 16), dtype=dtype, device=DEV)
+    ops.resize_nhwc(nhwc, (2 * hi, 2 * wi), L.RESIZE_BILINEAR, out=out, coff=8)            # x2 kernel (C % 8 == 0)
+    got = out[..., 8:8 + C].float().permute(0, 3, 1, 2).cpu()
+    assert rel_err(got, ref) < tol
+    assert float(out[..., :8].abs().max()) == 0 and float(out[..., 8 + C:].abs().max()) == 0
+    # generic kernel: a destination slice that is not 16-byte aligned takes the scalar path of resize_nhwc_kernel
+    out2 = torch.zeros((2, 2 * hi, 2 * wi, C + 3), dtype=dtype, device=DEV)
+    ops.resize_nhwc(nhwc, (2 * hi, 2 * wi), L.RESIZE_BILINEAR, out=out2, coff=3)
+    assert rel_err(out2[..., 3:].float(), out[..., 8:8 + C].float()) < tol
+
+
 def test_layout_roundtrip_and_resize_nhwc_slice():
     x = rnd(2, 12, 9, 14, seed=11)
     nhwc = ops.nchw_to_nhwc(x.to(DEV))
