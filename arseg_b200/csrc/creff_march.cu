@@ -174,7 +174,7 @@ __device__ __forceinline__ void sts_f4(uint32_t a, float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-template <int K, typename TLR>
+template <int K, typename TLR, bool MVF>
 __device__ __forceinline__ void x_g_role(const CreffMmaParams& p, const XSmem& sm, int n, int x0, int ya, int S) {
     using Cf = XCfg<K>;
     constexpr int NHW = XNHW;                             // half-warps: one gather position each
@@ -193,7 +193,10 @@ __device__ __forceinline__ void x_g_role(const CreffMmaParams& p, const XSmem& s
     // multiple of NHW * XJA with no-op records (zero weights, scratch destination), so the gather loop is branch-free.
     // Positions outside the image are zero-weight records onto a valid address (exact zeros for finite inputs).
     // Single-buffered: the records of step t+1 are written after the last use of those of step t.
-    const bool mv_fast = p.flow && p.flow_dtype == ARSEG_I16 && p.Hm == p.H && p.Wm == p.W;
+    // MVF (compile time): the MV field is the on-disk int16 quarter-pel map at feature resolution -- the generic MV code
+    // (f32 / f64 fields, f64 bilinear resize of the field, evaluation.py:177-180) is then not even instantiated, which keeps
+    // the once-per-step record code short (it runs cold in the instruction cache every step)
+    constexpr bool mv_fast = MVF;
     const int* const mvp = reinterpret_cast<const int*>(p.flow) + (size_t)n * p.H * p.W;
     auto padded = [](int npos) { return ((npos + NHW * XJA - 1) / (NHW * XJA)) * (NHW * XJA); };
     // the int16 MV pair of this thread's hr position of step t (loaded one step ahead of compute_pos)
@@ -768,7 +771,7 @@ __device__ __forceinline__ void x_c_role(const CreffMmaParams& p, const XSmem& s
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
-template <int K, typename TLR, int NCT>
+template <int K, typename TLR, int NCT, bool MVF>
 __global__ void __launch_bounds__(XTHREADS, 1) creff_march_kernel(CreffMmaParams p) {
     using Cf = XCfg<K>;
     extern __shared__ __align__(1024) uint8_t xsm[];
@@ -826,15 +829,15 @@ __global__ void __launch_bounds__(XTHREADS, 1) creff_march_kernel(CreffMmaParams
     // register file re-balance (warpgroup-aligned): the kernel starts with 128 per thread; G and D give 16 each to C
     if (warp < XG_WARPS + XD_WARPS) asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
     else asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
-    if (warp < XG_WARPS) x_g_role<K, TLR>(p, sm, n, x0, ya, S);
+    if (warp < XG_WARPS) x_g_role<K, TLR, MVF>(p, sm, n, x0, ya, S);
     else if (warp < XG_WARPS + XD_WARPS) x_d_role<K>(p, sm, x0, ya, S);
     else x_c_role<K, NCT>(p, sm, n, x0, ya, yb, S);
 }
 
-template <int K, typename TLR, int NCT>
+template <int K, typename TLR, int NCT, bool MVF>
 static int creff_march_launch_n(CreffMmaParams& p, cudaStream_t st) {
     using Cf = XCfg<K>;
-    auto kern = creff_march_kernel<K, TLR, NCT>;
+    auto kern = creff_march_kernel<K, TLR, NCT, MVF>;
     static bool configured[64] = {false};
     int dev = 0;
     ARSEG_CUDA(cudaGetDevice(&dev));
@@ -866,9 +869,15 @@ static int creff_march_launch_n(CreffMmaParams& p, cudaStream_t st) {
 // classifier n-tiles held in registers: none, <= 16 classes (CamVid 12), <= 32 classes (Cityscapes 19)
 template <int K, typename TLR>
 static int creff_march_launch_t(CreffMmaParams& p, cudaStream_t st) {
-    if (!p.wcls) return creff_march_launch_n<K, TLR, 0>(p, st);
-    if (p.ncls <= 16) return creff_march_launch_n<K, TLR, 2>(p, st);
-    return creff_march_launch_n<K, TLR, 4>(p, st);
+    const bool mvf = p.flow && p.flow_dtype == ARSEG_I16 && p.Hm == p.H && p.Wm == p.W;
+    if (mvf) {
+        if (!p.wcls) return creff_march_launch_n<K, TLR, 0, true>(p, st);
+        if (p.ncls <= 16) return creff_march_launch_n<K, TLR, 2, true>(p, st);
+        return creff_march_launch_n<K, TLR, 4, true>(p, st);
+    }
+    if (!p.wcls) return creff_march_launch_n<K, TLR, 0, false>(p, st);
+    if (p.ncls <= 16) return creff_march_launch_n<K, TLR, 2, false>(p, st);
+    return creff_march_launch_n<K, TLR, 4, false>(p, st);
 }
 
 template <int K>
