@@ -1,6 +1,6 @@
 #!/bin/bash
-# Session-4 GPU pass at HEAD: parity suite, smoke, default bench (f16 + tf32 alt, CPU baseline), reference arm,
-# ncu launch list, ncu --set full of the CReFF kernel from bench.py, config-5 sweep.
+# Full GPU pass at HEAD: parity suite, smoke, default bench (f16 + tf32 alt, CPU baseline), reference arm,
+# ncu launch list, ncu --set full of the CReFF kernel from bench.py, config-5 sweep, configs 2-4 table.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/smi.txt 2>&1
 nproc > gpurun_out/nproc.txt
@@ -17,5 +17,9 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 tail -2 gpurun_out/launches.csv
 echo "=== ncu full creff (f16 plan, from bench.py)"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:creff_march -c 1 -f -o gpurun_out/creff_march_f16 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --alt-precision none 2>&1 | tail -2
+echo "=== ncu full conv up_1 (f16 plan, from bench.py)"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_tc_halo_kernel -s 20 -c 1 -f -o gpurun_out/conv_halo_f16 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --alt-precision none 2>&1 | tail -2
 echo "=== sweep"
 timeout 600 python tools/sweep_creff.py --iters 3 2>&1 | tail -32
+echo "=== configs"
+timeout 600 python tools/bench_configs.py 2>&1 | tail -4

@@ -20,7 +20,8 @@ from collections import defaultdict
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT, PROF = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 
-KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+KEYS = ["gpu__time_duration.sum", "sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_subpipe_umma_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "l1tex__m_xbar2l1tex_read_bytes.sum", "lts__t_sectors_srcunit_tex_op_read.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__issue_active.avg.pct_of_peak_sustained_elapsed",
         "sm__inst_executed.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
@@ -54,7 +55,7 @@ def launches(tag):
             f.write("%6.2f%% %5d launches %11.1f us total  %s\n" % (100 * us / tot, n, us, name))
 
 
-def creff(tag, rep, key):
+def creff(tag, rep, key, cmd="-k regex:creff_march -c 1 python bench.py --steps 1 --warmup 1 (f16 plan: 11 frames per launch)"):
     p = os.path.join(OUT, rep)
     if not os.path.exists(p):
         return None
@@ -64,8 +65,7 @@ def creff(tag, rep, key):
     d = dict(zip(hdr, vals))
     u = dict(zip(hdr, units))
     with open(os.path.join(PROF, "%s_%s_ncu.txt" % (tag, key)), "w") as f:
-        f.write("# ncu --set full --clock-control none --import-source on -k regex:creff_march -c 1 python bench.py --steps 1 --warmup 1 "
-                "(f16 plan: 11 frames per launch)\n# kernel: %s\n" % d.get("Kernel Name", ""))
+        f.write("# ncu --set full --clock-control none --import-source on %s\n# kernel: %s\n" % (cmd, d.get("Kernel Name", "")))
         for k in KEYS:
             if k in d:
                 f.write("%-90s %s %s\n" % (k, d[k], u.get(k, "")))
@@ -87,6 +87,7 @@ def main():
     if os.path.exists(os.path.join(OUT, "creff_sweep.md")):
         shutil.copy(os.path.join(OUT, "creff_sweep.md"), os.path.join(PROF, tag + "_creff_sweep.md"))
     launches(tag)
+    creff(tag, "conv_halo_f16.ncu-rep", "conv_halo", "-k regex:conv_tc_halo_kernel -s 20 -c 1 python bench.py --steps 1 --warmup 1 (one 3x3 layer of the f16 plan)")
     tr = creff(tag, "creff_march_f16.ncu-rep", "creff")
     if tr:
         tp = os.path.join(PROF, "ncu_traffic.json")
