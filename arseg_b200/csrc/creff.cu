@@ -319,6 +319,9 @@ static int creff_launch_k(const CreffParams& p, int layout, int dtype, cudaStrea
 
 bool creff_mma_supported(const arseg_creff_args* a);
 int creff_mma_launch(const arseg_creff_args* a, cudaStream_t st);
+bool creff_wide_supported(const arseg_creff_args* a);                                   // creff_wide.cu
+int creff_wide_launch(const arseg_creff_args* a, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t creff_wide_workspace_bytes(int N, int C, int H, int W);
 
 }  // namespace arseg
 
@@ -342,8 +345,9 @@ extern "C" int arseg_creff_fused_fwd(const arseg_creff_args* a, arseg_stream_t s
     else ARSEG_REQUIRE(a->lr_dtype == ARSEG_F32 || a->lr_dtype == ARSEG_BF16 || a->lr_dtype == ARSEG_F16, "creff: lr dtype %d", a->lr_dtype);
     cudaStream_t st = as_stream(stream);
     if (a->engine == ARSEG_CREFF_MMA_F16) {
+        if (creff_wide_supported(a)) return creff_wide_launch(a, a->workspace, a->workspace_bytes, st);
         if (!creff_mma_supported(a))
-            ARSEG_UNSUPPORTED("creff: the MMA engine needs C=64 (got %d), NHWC hr and lr, k in {3,5,7,9}, ncls <= 32", a->C);
+            ARSEG_UNSUPPORTED("creff: the MMA engine needs C a multiple of 64 up to 1024 (got %d), NHWC hr and lr, k in {3,5,7,9}, ncls <= 32", a->C);
         return creff_mma_launch(a, st);
     }
     ARSEG_REQUIRE(a->engine == ARSEG_CREFF_EXACT_F32, "creff: unknown engine %d", a->engine);
@@ -361,4 +365,9 @@ extern "C" int arseg_creff_fused_fwd(const arseg_creff_args* a, arseg_stream_t s
         case 9: return creff_launch_k<9>(p, a->lr_layout, a->lr_dtype, st);
         default: ARSEG_UNSUPPORTED("creff: window k=%d (supported 3,5,7,9)", a->k);
     }
+}
+
+extern "C" size_t arseg_creff_workspace_bytes(const arseg_creff_args* a) {
+    if (!a || a->engine != ARSEG_CREFF_MMA_F16 || !creff_wide_supported(a)) return 0;
+    return creff_wide_workspace_bytes(a->N, a->C, a->H, a->W);
 }

@@ -238,11 +238,12 @@ class Plan:
               want_argmax=False, name="creff_fused", engine=None):
         """Fused MV-warp + CReFF (+ classifier).  hr NCHW fp32 [1|N,C,H,W]; lr [N,h,w,C] NHWC (or NCHW fp32).
         engine None: exact fp32 SIMT kernel in 'fp32' plans; tensor-core window attention (f16 operands, fp32
-        accumulate) in 'tf32'/'bf16' plans when C == 64 (hr is first converted to NHWC by one transpose launch)."""
+        accumulate) in 'tf32'/'f16'/'bf16' plans when C is a multiple of 64 (hr is first converted to NHWC by one transpose
+        launch; C = 64: column-marching engine, C > 64: the two-launch wide engine with a plan-owned workspace)."""
         _, Cc, H, W = hr.shape
         if engine is None:
-            mma_ok = (self.precision != "fp32" and Cc == 64 and lr_layout == L.NHWC and k in (3, 5, 7, 9)
-                      and (wcls is None or wcls.shape[0] <= 32))
+            mma_ok = (self.precision != "fp32" and Cc % 64 == 0 and Cc <= 1024 and lr_layout == L.NHWC and k in (3, 5, 7, 9)
+                      and (wcls is None or wcls.shape[0] <= 32) and min(H, W) >= 2)
             engine = L.CREFF_MMA_F16 if mma_ok else L.CREFF_EXACT_F32
         hr_layout = L.NCHW
         if engine == L.CREFF_MMA_F16:
@@ -276,7 +277,11 @@ class Plan:
                         wc.data_ptr() if wc is not None else None, bc.data_ptr() if bc is not None else None, ncls,
                         int(log_softmax), out_p.data_ptr() if out_p is not None else None,
                         out_l.data_ptr() if out_l is not None else None, out_a.data_ptr() if out_a is not None else None,
-                        N, Cc, H, W, k)
+                        N, Cc, H, W, k, None, 0)
+        need = int(self.lib.arseg_creff_workspace_bytes(C.byref(a)))
+        if need:
+            wsb = self.empty((need,), torch.uint8)
+            a.workspace, a.workspace_bytes = wsb.data_ptr(), need
         self.keep.append(a)
         fn = self.lib.arseg_creff_fused_fwd
         self._add(name, lambda s, a=a: fn(C.byref(a), s))

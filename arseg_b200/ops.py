@@ -219,7 +219,7 @@ def creff_fused(hr, lr, wq, bq, wk, bk, wv, bv, k, flow=None, flow_hw=None, wcls
                 engine=L.CREFF_EXACT_F32, hr_layout=L.NCHW):
     """Fused (MV warp +) CReFF (+ classifier).  hr fp32 NCHW [1|N,C,H,W] (or NHWC [1|N,H,W,C] with hr_layout=NHWC);
     lr NCHW fp32 [N,C,h,w] or NHWC [N,h,w,C].  engine: L.CREFF_EXACT_F32 (fp32 SIMT, NCHW hr) or L.CREFF_MMA_F16
-    (tensor-core window attention, TF32-class error, C=64, NHWC hr and lr)."""
+    (tensor-core window attention, TF32-class error, C = 64 m, NHWC hr and lr)."""
     _chk_cuda("creff_fused", hr, lr, wq, bq, wk, bk, wv, bv, flow, wcls, bcls)
     if hr_layout == L.NHWC:
         Nh, H, W, Cc = hr.shape
@@ -240,7 +240,11 @@ def creff_fused(hr, lr, wq, bq, wk, bk, wv, bv, k, flow=None, flow_hw=None, wcls
     Hm, Wm = (flow.shape[1], flow.shape[2]) if flow is not None else (0, 0)
     a = L.CreffArgs(_p(hr), int(hr_shared), hr_layout, engine, _p(flow), dtype_code(flow.dtype) if flow is not None else 0, Hm, Wm,
                     _p(lr), lr_layout, dtype_code(lr.dtype), h, w, _p(wq), _p(bq), _p(wk), _p(bk), _p(wv), _p(bv),
-                    _p(wcls), _p(bcls), ncls, int(log_softmax), _p(out_p), _p(out_l), _p(out_a), N, Cc, H, W, k)
+                    _p(wcls), _p(bcls), ncls, int(log_softmax), _p(out_p), _p(out_l), _p(out_a), N, Cc, H, W, k, None, 0)
     with torch.cuda.device(dev):
-        L.check(L.load().arseg_creff_fused_fwd(C.byref(a), _stream()), "creff_fused")
+        lib = L.load()
+        need = int(lib.arseg_creff_workspace_bytes(C.byref(a)))
+        ws = torch.empty(need, dtype=torch.uint8, device=dev) if need else None      # caller-owned scratch (C > 64 MMA engine)
+        a.workspace, a.workspace_bytes = _p(ws), need
+        L.check(lib.arseg_creff_fused_fwd(C.byref(a), _stream()), "creff_fused")
     return out_p, out_l, out_a

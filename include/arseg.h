@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define ARSEG_ABI_VERSION 3
+#define ARSEG_ABI_VERSION 4
 
 enum { ARSEG_OK = 0, ARSEG_E_BADARG = -1, ARSEG_E_UNSUPPORTED = -2, ARSEG_E_CUDA = -3 };
 enum { ARSEG_F32 = 0, ARSEG_BF16 = 1, ARSEG_F64 = 2, ARSEG_I16 = 3, ARSEG_F16 = 4 };
@@ -180,8 +180,14 @@ typedef struct arseg_creff_args {
     float* out_logits;      /* NCHW fp32 [N,ncls,H,W] or NULL */
     uint8_t* out_argmax;    /* [N,H,W] argmax over classes at feature resolution, or NULL */
     int N, C, H, W, k;
+    void* workspace;        /* device scratch of >= arseg_creff_workspace_bytes(a) bytes, owned by the caller; may be NULL
+                               when that function returns 0 (C = 64 and the exact engine need none) */
+    size_t workspace_bytes;
 } arseg_creff_args;
 int arseg_creff_fused_fwd(const arseg_creff_args* a, arseg_stream_t stream);
+/* Scratch the call above needs for these arguments (ARSEG_CREFF_MMA_F16 with C = 128, 192, ... 1024: Q, K, V in fp16
+ * and the lr_up residual in fp32 pass through it between the two launches of that engine); 0 otherwise. */
+size_t arseg_creff_workspace_bytes(const arseg_creff_args* a);
 
 #ifdef __cplusplus
 }

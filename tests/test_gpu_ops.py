@@ -396,6 +396,56 @@ def test_creff_mma_with_mv_warp_and_classifier(flow_kind, stride, lr_dtype):
         assert torch.equal(out_a[i:i + 1].cpu().long(), out_l[i:i + 1].cpu().argmax(1))
 
 
+@pytest.mark.parametrize("k", [3, 5, 7, 9])
+@pytest.mark.parametrize("C,H,W,h,w", [(128, 24, 40, 12, 20), (256, 17, 35, 11, 23), (512, 9, 21, 5, 11)])
+def test_creff_wide_prewarped(k, C, H, W, h, w):
+    """C = 64 m > 64 (BiSeNet 256, Cityscapes-PSP 512): the two-launch tensor-core engine (creff_wide.cu) against the
+    oracle's MyAttention.forward (model/attention.py:184-213); ragged sizes exercise the partial tiles."""
+    sd = creff_sd(C)
+    hr, lr = rnd(1, C, H, W, seed=51) * 0.6, rnd(1, C, h, w, seed=52) * 0.4
+    ref = O.creff(sd, "fuse_attention.", hr, lr, k)
+    out_p, _, _ = ops.creff_fused(ops.nchw_to_nhwc(hr.to(DEV)), ops.nchw_to_nhwc(lr.to(DEV)), *creff_args(sd), k,
+                                  want_logits=False, lr_layout=L.NHWC, hr_layout=L.NHWC, engine=L.CREFF_MMA_F16)
+    assert out_p.shape == ref.shape
+    assert rel_err(out_p, ref) < MMA_TOL, rel_err(out_p, ref)
+    assert rms_err(out_p, ref) < MMA_TOL / 4
+
+
+@pytest.mark.parametrize("flow_kind", ["i16", "f64"])
+@pytest.mark.parametrize("C,ncls,lr_dtype", [(256, 12, torch.float32), (256, 12, torch.float16), (512, 19, torch.float32), (128, 19, torch.bfloat16)])
+def test_creff_wide_with_mv_warp_and_classifier(flow_kind, C, ncls, lr_dtype):
+    """Frame-resolution MV field (stride 8, f64 bilinear resize of the field, evaluation.py:177-180), shared keyframe
+    feature, classifier with raw logits (BiSeNet / Cityscapes: no LogSoftmax) and with log-softmax, argmax."""
+    from arseg_b200 import synth
+    k, stride = 7, 8
+    Hm, Wm = 40 * stride, 56 * stride
+    H, W, h, w = Hm // stride, Wm // stride, Hm // stride // 2 + 1, Wm // stride // 2
+    sd = creff_sd(C)
+    hr, lr = rnd(1, C, H, W, seed=53) * 0.6, rnd(2, C, h, w, seed=54) * 0.4
+    if lr_dtype != torch.float32:
+        lr = lr.to(lr_dtype).float()
+    wcls, bcls = rnd(ncls, C, seed=55) * 0.1, rnd(ncls, seed=56) * 0.1
+    mvs = np.stack([synth.synth_mv_int16(Hm, Wm, 60 + i, distance=5 + 3 * i) for i in range(2)])
+    flow64 = torch.from_numpy(mvs.astype(np.float64) / 4.0)
+    flow = {"i16": torch.from_numpy(mvs), "f64": flow64}[flow_kind].to(DEV)
+    for logsm in (False, True):
+        out_p, out_l, out_a = ops.creff_fused(ops.nchw_to_nhwc(hr.to(DEV)), ops.nchw_to_nhwc(lr.to(DEV), lr_dtype), *creff_args(sd), k,
+                                              flow=flow, wcls=wcls.to(DEV), bcls=bcls.to(DEV), log_softmax=logsm, want_argmax=True,
+                                              hr_shared=True, lr_layout=L.NHWC, hr_layout=L.NHWC, engine=L.CREFF_MMA_F16)
+        for i in range(2):
+            fl = O.resize_flow(flow64[i:i + 1], H, W)
+            warped = O.warp_feature(hr, fl)
+            fused = O.creff(sd, "fuse_attention.", warped, lr[i:i + 1], k)
+            logits = F.conv2d(fused, wcls.view(ncls, C, 1, 1), bcls)
+            if logsm:
+                logits = F.log_softmax(logits, dim=1)
+            assert rel_err(out_p[i:i + 1], fused) < MMA_TOL, rel_err(out_p[i:i + 1], fused)
+            assert rel_err(out_l[i:i + 1], logits) < MMA_TOL, rel_err(out_l[i:i + 1], logits)
+            mism = (out_a[i:i + 1].cpu().long() != logits.argmax(1)).float().mean().item()
+            assert mism < 1e-2, mism
+            assert torch.equal(out_a[i:i + 1].cpu().long(), out_l[i:i + 1].cpu().argmax(1))
+
+
 @pytest.mark.parametrize("k", [3, 7, 9])
 @pytest.mark.parametrize("seg_rows", [8, 12])
 def test_creff_march_row_segments_are_seamless(k, seg_rows, monkeypatch):
