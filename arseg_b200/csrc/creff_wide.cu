@@ -34,6 +34,7 @@ struct WideParams {
 // ---------------------------------------------------------------------------------------------
 constexpr int WP_TH = 8, WP_TW = 16, WP_HH = WP_TH + 2, WP_HW = WP_TW + 2, WP_NP = WP_HH * WP_HW;   // 10 x 18 = 180 positions
 constexpr int WP_THREADS = 256;
+constexpr int WP_GJ = 3;                 // gather positions in flight per half-warp
 constexpr size_t WP_SMEM = (size_t)2 * WP_NP * 256 + (size_t)2 * WP_NP * 32 + 3 * 10 * 64 * 4;
 
 __device__ __forceinline__ void w_block_of(const PosRec& r, int Wimg, int Himg, float4& w, int& bx, int& by) {
@@ -93,59 +94,95 @@ __global__ void __launch_bounds__(WP_THREADS) creff_wide_prep_kernel(WideParams 
         s_a[i] = make_uint4((uint32_t)au, (uint32_t)(au >> 32), rs, (uint32_t)src);
     }
     __syncthreads();
-    // gather: half-warp per position, 4 channels per lane
+    // gather: half-warp per position, 4 channels per lane, WP_GJ positions' loads in flight per half-warp
     {
         const int hw = tid >> 4, cl = tid & 15;
-        for (int i = hw; i < 2 * WP_NP; i += WP_THREADS / 16) {
-            const uint4 id = s_a[i];
-            const float4 w = s_w[i];
-            const char* a0 = reinterpret_cast<const char*>(((unsigned long long)id.y << 32) | id.x);
-            float4 t0, t1, t2, t3;
-            if (LR_ES == 4 || id.w == 0) {
-                a0 += 16 * cl;
-                const char* a1 = a0 + id.z;
-                t0 = ld4(reinterpret_cast<const float*>(a0)); t1 = ld4(reinterpret_cast<const float*>(a0 + (size_t)C * 4));
-                t2 = ld4(reinterpret_cast<const float*>(a1)); t3 = ld4(reinterpret_cast<const float*>(a1 + (size_t)C * 4));
-            } else {
-                a0 += LR_ES * 4 * cl;
-                const char* a1 = a0 + id.z;
-                t0 = ld4(reinterpret_cast<const TLR*>(a0)); t1 = ld4(reinterpret_cast<const TLR*>(a0 + (size_t)C * LR_ES));
-                t2 = ld4(reinterpret_cast<const TLR*>(a1)); t3 = ld4(reinterpret_cast<const TLR*>(a1 + (size_t)C * LR_ES));
+        constexpr int NHW = WP_THREADS / 16;
+        for (int i0 = hw; i0 < 2 * WP_NP; i0 += NHW * WP_GJ) {
+            float4 tp[WP_GJ][4];
+#pragma unroll
+            for (int u = 0; u < WP_GJ; ++u) {
+                const int i = i0 + u * NHW;
+                if (i < 2 * WP_NP) {
+                    const uint4 id = s_a[i];
+                    const char* a0 = reinterpret_cast<const char*>(((unsigned long long)id.y << 32) | id.x);
+                    if (LR_ES == 4 || id.w == 0) {
+                        a0 += 16 * cl;
+                        const char* a1 = a0 + id.z;
+                        tp[u][0] = ld4(reinterpret_cast<const float*>(a0)); tp[u][1] = ld4(reinterpret_cast<const float*>(a0 + (size_t)C * 4));
+                        tp[u][2] = ld4(reinterpret_cast<const float*>(a1)); tp[u][3] = ld4(reinterpret_cast<const float*>(a1 + (size_t)C * 4));
+                    } else {
+                        a0 += LR_ES * 4 * cl;
+                        const char* a1 = a0 + id.z;
+                        tp[u][0] = ld4(reinterpret_cast<const TLR*>(a0)); tp[u][1] = ld4(reinterpret_cast<const TLR*>(a0 + (size_t)C * LR_ES));
+                        tp[u][2] = ld4(reinterpret_cast<const TLR*>(a1)); tp[u][3] = ld4(reinterpret_cast<const TLR*>(a1 + (size_t)C * LR_ES));
+                    }
+                }
             }
-            float4 v;
-            v.x = t0.x * w.x + t1.x * w.y + t2.x * w.z + t3.x * w.w;
-            v.y = t0.y * w.x + t1.y * w.y + t2.y * w.z + t3.y * w.w;
-            v.z = t0.z * w.x + t1.z * w.y + t2.z * w.z + t3.z * w.w;
-            v.w = t0.w * w.x + t1.w * w.y + t2.w * w.z + t3.w * w.w;
-            float* dst = (i < WP_NP ? s_hr + i * 64 : s_lr + (i - WP_NP) * 64) + 4 * cl;
-            *reinterpret_cast<float4*>(dst) = v;
+#pragma unroll
+            for (int u = 0; u < WP_GJ; ++u) {
+                const int i = i0 + u * NHW;
+                if (i < 2 * WP_NP) {
+                    const float4 w = s_w[i];
+                    float4 v;
+                    v.x = tp[u][0].x * w.x + tp[u][1].x * w.y + tp[u][2].x * w.z + tp[u][3].x * w.w;
+                    v.y = tp[u][0].y * w.x + tp[u][1].y * w.y + tp[u][2].y * w.z + tp[u][3].y * w.w;
+                    v.z = tp[u][0].z * w.x + tp[u][1].z * w.y + tp[u][2].z * w.z + tp[u][3].z * w.w;
+                    v.w = tp[u][0].w * w.x + tp[u][1].w * w.y + tp[u][2].w * w.z + tp[u][3].w * w.w;
+                    float* dst = (i < WP_NP ? s_hr + i * 64 : s_lr + (i - WP_NP) * 64) + 4 * cl;
+                    *reinterpret_cast<float4*>(dst) = v;
+                }
+            }
         }
     }
     __syncthreads();
-    // depthwise 3x3 convolutions (model/attention.py:194-197): work item = (pixel, 4 channels)
-    for (int it = tid; it < WP_TH * WP_TW * 16; it += WP_THREADS) {
-        const int px = it >> 4, cq = (it & 15) * 4, py = px / WP_TW, pxx = px - py * WP_TW;
-        const int y = y0 + py, x = x0 + pxx;
-        if (y >= p.H || x >= p.W) continue;
-        float4 ak = *reinterpret_cast<const float4*>(s_dw + 9 * 64 + cq), av = *reinterpret_cast<const float4*>(s_dw + (10 + 9) * 64 + cq),
-               aq = *reinterpret_cast<const float4*>(s_dw + (20 + 9) * 64 + cq);
+    // depthwise 3x3 convolutions (model/attention.py:194-197): warp = one output row of the tile, lane = channel pair,
+    // marching along x with a 3-column register window per source (3 new LDS.64 per source and column); weights in registers
+    {
+        const int lane = tid & 31, py = tid >> 5, y = y0 + py;
+        if (y < p.H) {
+            float2 wk[10], wv[10], wq[10];
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {
-                const int pz = (py + dy) * WP_HW + pxx + dx, tp = dy * 3 + dx;
-                const float4 h = *reinterpret_cast<const float4*>(s_hr + pz * 64 + cq), l = *reinterpret_cast<const float4*>(s_lr + pz * 64 + cq);
-                const float4 wk = *reinterpret_cast<const float4*>(s_dw + tp * 64 + cq), wv = *reinterpret_cast<const float4*>(s_dw + (10 + tp) * 64 + cq),
-                             wq = *reinterpret_cast<const float4*>(s_dw + (20 + tp) * 64 + cq);
-                ak.x = fmaf(wk.x, h.x, ak.x); ak.y = fmaf(wk.y, h.y, ak.y); ak.z = fmaf(wk.z, h.z, ak.z); ak.w = fmaf(wk.w, h.w, ak.w);
-                av.x = fmaf(wv.x, h.x, av.x); av.y = fmaf(wv.y, h.y, av.y); av.z = fmaf(wv.z, h.z, av.z); av.w = fmaf(wv.w, h.w, av.w);
-                aq.x = fmaf(wq.x, l.x, aq.x); aq.y = fmaf(wq.y, l.y, aq.y); aq.z = fmaf(wq.z, l.z, aq.z); aq.w = fmaf(wq.w, l.w, aq.w);
+            for (int i = 0; i < 10; ++i) {
+                wk[i] = *reinterpret_cast<const float2*>(s_dw + i * 64 + 2 * lane);
+                wv[i] = *reinterpret_cast<const float2*>(s_dw + (10 + i) * 64 + 2 * lane);
+                wq[i] = *reinterpret_cast<const float2*>(s_dw + (20 + i) * 64 + 2 * lane);
             }
-        const size_t o = (((size_t)n * p.H + y) * p.W + x) * C + c0 + cq;
-        *reinterpret_cast<uint2*>(q.K + o) = make_uint2(pack_h2_sat(ak.x, ak.y), pack_h2_sat(ak.z, ak.w));
-        *reinterpret_cast<uint2*>(q.V + o) = make_uint2(pack_h2_sat(av.x, av.y), pack_h2_sat(av.z, av.w));
-        *reinterpret_cast<uint2*>(q.Q + o) = make_uint2(pack_h2_sat(aq.x, aq.y), pack_h2_sat(aq.z, aq.w));
-        *reinterpret_cast<float4*>(q.R + o) = *reinterpret_cast<const float4*>(s_lr + ((py + 1) * WP_HW + pxx + 1) * 64 + cq);
+            const float* hrow = s_hr + (py * WP_HW) * 64 + 2 * lane;       // halo rows py .. py+2, column 0
+            const float* lrow = s_lr + (py * WP_HW) * 64 + 2 * lane;
+            float2 hwin[3][3], lwin[3][3];                                   // [row][slot], slot (x + d) % 3 holds column x + d
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    hwin[r][cc] = *reinterpret_cast<const float2*>(hrow + (r * WP_HW + cc) * 64);
+                    lwin[r][cc] = *reinterpret_cast<const float2*>(lrow + (r * WP_HW + cc) * 64);
+                }
+            auto dw9 = [](const float2 (&w)[10], const float2 (&win)[3][3], int sa, int sb, int sc) {
+                float2 a0 = __ffma2_rn(w[0], win[0][sa], w[9]), a1 = __fmul2_rn(w[3], win[1][sa]), a2 = __fmul2_rn(w[6], win[2][sa]);
+                a0 = __ffma2_rn(w[1], win[0][sb], a0); a1 = __ffma2_rn(w[4], win[1][sb], a1); a2 = __ffma2_rn(w[7], win[2][sb], a2);
+                a0 = __ffma2_rn(w[2], win[0][sc], a0); a1 = __ffma2_rn(w[5], win[1][sc], a1); a2 = __ffma2_rn(w[8], win[2][sc], a2);
+                return __fadd2_rn(__fadd2_rn(a0, a1), a2);
+            };
+            const size_t orow = (((size_t)n * p.H + y) * p.W + x0) * C + c0 + 2 * lane;
+#pragma unroll
+            for (int x = 0; x < WP_TW; ++x) {
+                const int sa = x % 3, sb = (x + 1) % 3, sc = (x + 2) % 3;
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    hwin[r][sc] = *reinterpret_cast<const float2*>(hrow + (r * WP_HW + x + 2) * 64);
+                    lwin[r][sc] = *reinterpret_cast<const float2*>(lrow + (r * WP_HW + x + 2) * 64);
+                }
+                if (x0 + x < p.W) {
+                    const float2 kk = dw9(wk, hwin, sa, sb, sc), vv = dw9(wv, hwin, sa, sb, sc), qq = dw9(wq, lwin, sa, sb, sc);
+                    const size_t o = orow + (size_t)x * C;
+                    *reinterpret_cast<uint32_t*>(q.K + o) = pack_h2_sat(kk.x, kk.y);
+                    *reinterpret_cast<uint32_t*>(q.V + o) = pack_h2_sat(vv.x, vv.y);
+                    *reinterpret_cast<uint32_t*>(q.Q + o) = pack_h2_sat(qq.x, qq.y);
+                    *reinterpret_cast<float2*>(q.R + o) = lwin[1][sb];
+                }
+            }
+        }
     }
 }
 

@@ -26,6 +26,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--precision", default="f16")
+    ap.add_argument("--only", default="", help="substring of the config name / architecture to run alone")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "configs.md"))
     a = ap.parse_args()
     torch.set_grad_enabled(False)
@@ -33,6 +34,8 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     lines = ["| config | architecture | frame | precision | launches/step | ms/step (11 frames) | frames/s | top kernels |", "|---|---|---|---|---|---|---|---|"]
     for name, arch, H, W in CONFIGS:
+        if a.only and a.only not in name and a.only not in arch:
+            continue
         C_, stride, ncls = ev.ARCH_INFO[arch]
         sd = synth.synth_state_dict(models.models_fuse[arch]().state_dict(), 4)
         N = 11
