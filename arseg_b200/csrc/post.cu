@@ -26,12 +26,75 @@ __global__ void resize_argmax_kernel(const float* __restrict__ logits, float* __
         const float* s = logits + ((size_t)n * ncls + c) * Hi * Wi;
         float v;
         if (mode == ARSEG_RESIZE_NEAREST) v = s[(size_t)y0 * Wi + x0];
-        else v = ly0 * (lx0 * s[(size_t)y0 * Wi + x0] + lx1 * s[(size_t)y0 * Wi + x1]) +
-                 ly1 * (lx0 * s[(size_t)y1 * Wi + x0] + lx1 * s[(size_t)y1 * Wi + x1]);
+        else v = __fmaf_rn(ly1, __fmaf_rn(lx1, s[(size_t)y1 * Wi + x1], __fmul_rn(lx0, s[(size_t)y1 * Wi + x0])),
+                           __fmul_rn(ly0, __fmaf_rn(lx1, s[(size_t)y0 * Wi + x1], __fmul_rn(lx0, s[(size_t)y0 * Wi + x0]))));
         if (out_logits) out_logits[(((size_t)n * ncls + c) * Ho + y) * Wo + x] = v;
         if (v > best) { best = v; arg = c; }
     }
     if (out_argmax) out_argmax[((size_t)n * Ho + y) * Wo + x] = (uint8_t)arg;
+}
+
+// Class maps only (evaluation.py:201-204, what the evaluation loop consumes): one thread per output column walks RSEG
+// output rows.  ATen's bilinear formula is horizontal-first -- h0 * (w0 p00 + w1 p01) + h1 * (w0 p10 + w1 p11) -- so the
+// two horizontally interpolated source rows of all classes stay in registers and are re-loaded only when the output row
+// crosses into the next source row (every ~Ho/Hi rows): ~4 loads per class per source-row change instead of 4 per class
+// per pixel.  Same expression tree as resize_argmax_kernel, spelled with explicit roundings in both.
+constexpr int RA_RSEG = 32;
+template <int NCMAX>
+__global__ void __launch_bounds__(128) resize_argmax_rows_kernel(const float* __restrict__ logits, uint8_t* __restrict__ out_argmax, int ncls,
+                                                                 int Hi, int Wi, int Ho, int Wo, int mode, float sh, float sw) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ya = blockIdx.y * RA_RSEG, n = blockIdx.z;
+    if (x >= Wo) return;
+    int x0, x1;
+    float lx0, lx1;
+    bilinear_src(sw, x, Wi, mode, x0, x1, lx0, lx1);
+    const float* src = logits + (size_t)n * ncls * Hi * Wi;
+    float h0[NCMAX], h1[NCMAX];
+    int cy0 = -1, cy1 = -1;
+    const int yb = min(ya + RA_RSEG, Ho);
+    for (int y = ya; y < yb; ++y) {
+        int y0, y1;
+        float ly0, ly1;
+        bilinear_src(sh, y, Hi, mode, y0, y1, ly0, ly1);
+        if (y0 != cy0) {
+            if (y0 == cy1) {
+#pragma unroll
+                for (int c = 0; c < NCMAX; ++c) h0[c] = h1[c];
+            } else {
+#pragma unroll
+                for (int c = 0; c < NCMAX; ++c)
+                    if (c < ncls) {
+                        const float* s = src + ((size_t)c * Hi + y0) * Wi;
+                        h0[c] = __fmaf_rn(lx1, __ldg(s + x1), __fmul_rn(lx0, __ldg(s + x0)));
+                    }
+            }
+            cy0 = y0;
+        }
+        if (y1 != cy1) {
+            if (y1 == y0) {
+#pragma unroll
+                for (int c = 0; c < NCMAX; ++c) h1[c] = h0[c];
+            } else {
+#pragma unroll
+                for (int c = 0; c < NCMAX; ++c)
+                    if (c < ncls) {
+                        const float* s = src + ((size_t)c * Hi + y1) * Wi;
+                        h1[c] = __fmaf_rn(lx1, __ldg(s + x1), __fmul_rn(lx0, __ldg(s + x0)));
+                    }
+            }
+            cy1 = y1;
+        }
+        float best = -INFINITY;
+        int arg = 0;
+#pragma unroll
+        for (int c = 0; c < NCMAX; ++c)
+            if (c < ncls) {
+                const float v = __fmaf_rn(ly1, h1[c], __fmul_rn(ly0, h0[c]));
+                if (v > best) { best = v; arg = c; }
+            }
+        out_argmax[((size_t)n * Ho + y) * Wo + x] = (uint8_t)arg;
+    }
 }
 
 // nn.LogSoftmax over dim 1 of an NCHW tensor (model/pspnet.py:122,229), in place allowed
@@ -77,6 +140,13 @@ int arseg_resize_argmax_nchw(const float* logits, float* out_logits, uint8_t* ou
                   "resize_argmax: bad shape");
     ARSEG_REQUIRE(mode >= 0 && mode <= 2, "resize_argmax: bad mode");
     const float sh = resize_scale(Hi, Ho, mode), sw = resize_scale(Wi, Wo, mode);
+    if (!out_logits && mode != ARSEG_RESIZE_NEAREST && ncls <= 32 && ceil_div(Ho, RA_RSEG) <= 65535) {
+        dim3 grid(ceil_div(Wo, 128), ceil_div(Ho, RA_RSEG), N);
+        if (ncls <= 20) resize_argmax_rows_kernel<20><<<grid, 128, 0, as_stream(stream)>>>(logits, out_argmax, ncls, Hi, Wi, Ho, Wo, mode, sh, sw);
+        else resize_argmax_rows_kernel<32><<<grid, 128, 0, as_stream(stream)>>>(logits, out_argmax, ncls, Hi, Wi, Ho, Wo, mode, sh, sw);
+        ARSEG_CHECK_LAUNCH("resize_argmax_rows");
+        return ARSEG_OK;
+    }
     dim3 grid(ceil_div(Wo, 128), Ho, N);
     resize_argmax_kernel<<<grid, 128, 0, as_stream(stream)>>>(logits, out_logits, out_argmax, ncls, Hi, Wi, Ho, Wo, mode, sh, sw);
     ARSEG_CHECK_LAUNCH("resize_argmax");

@@ -337,6 +337,13 @@ def test_resize_argmax_and_hist():
     pred, up = ops.resize_argmax(logits.to(DEV), (80, 96), L.RESIZE_BILINEAR_AC, want_logits=True)
     assert rel_err(up, ref_l) < FP32_TOL
     assert (pred.cpu().long() != ref_l.argmax(1)).float().mean() < 1e-3
+    # class maps only: the row-walking kernel (interpolated source rows cached in registers) == the per-pixel kernel
+    for mode, ncls, hw, HW in ((L.RESIZE_BILINEAR_AC, 12, (10, 12), (80, 96)), (L.RESIZE_BILINEAR, 19, (9, 13), (72, 104)),
+                               (L.RESIZE_BILINEAR_AC, 27, (7, 5), (53, 41))):
+        lg = rnd(2, ncls, *hw, seed=72).to(DEV)
+        p_full, _ = ops.resize_argmax(lg, HW, mode, want_logits=True)
+        p_rows, _ = ops.resize_argmax(lg, HW, mode, want_logits=False)
+        assert torch.equal(p_full, p_rows)
     g = torch.Generator().manual_seed(71)
     label = torch.randint(0, 12, (2, 80, 96), generator=g)
     label[0, :5] = 255
