@@ -103,9 +103,13 @@ __device__ __forceinline__ void xbar_wait(uint64_t* bars, int step) {
     __trap();
 }
 
-// byte offset of 16-byte chunk `chunk` of K/V ring position (slot row, col): the swizzle key is the column only,
-// so a row's offset is a pure function of (slot, col) and ldmatrix over 8 consecutive columns is conflict free
-__device__ __forceinline__ uint32_t kv_off(int pos, int col, int chunk) { return (uint32_t)(pos * 128 + (((chunk ^ col) & 7) << 4)); }
+// byte offset of 16-byte chunk `chunk` of K/V ring position `pos` = slot * KVC + col.  Swizzle key = col + WN * kr, kr =
+// the K/V row index (image row - (ya - R)): an ldmatrix 8x8 reads 8 consecutive keys of a WN-wide key patch, i.e. the
+// tail of one patch row and the head of the next; with the row term the head continues the tail's residues mod 8, so
+// the 8 rows always land in 8 different 16-byte bank groups (with the column alone, columns 8, 9 aliased 0, 1: +45 %
+// wavefronts on every K / V fragment load).  WN = k + 3 is even, so the key is the same for rows 4 steps apart: per
+// lane it is constant over the march on both the writing (D) and the reading (C) side.
+__device__ __forceinline__ uint32_t kv_off(int pos, int key, int chunk) { return (uint32_t)(pos * 128 + (((chunk ^ key) & 7) << 4)); }
 // Q tile [row 0..3][col 0..15]: key = (col & 3) | (row & 1) << 2 -> the 8 rows of every ldmatrix 8x8 are distinct
 __device__ __forceinline__ uint32_t q_off(int row, int col, int chunk) {
     return (uint32_t)((row * XSW + col) * 128 + (((chunk ^ ((col & 3) | ((row & 1) << 2))) & 7) << 4));
@@ -376,10 +380,8 @@ __device__ __forceinline__ void x_d_role(const CreffMmaParams& p, const XSmem& s
     const uint32_t lring = s_u32(sm.rings) + (uint32_t)(Cf::HR_BYTES + q_lo * (MC * 4) + lane * 8);
     const uint32_t kbase = s_u32(sm.sK), qbase = s_u32(sm.sQ);
     const uint32_t resbase = s_u32(sm.sRes) + (uint32_t)(((rp * XSW + q_lo) * XRES_LD + 2 * lane) * 4);
-    // per-column store offsets inside a K/V ring row / the Q tile (the swizzle key depends on the column)
-    uint32_t kst[KV3], qst[Q3];
-#pragma unroll
-    for (int x = 0; x < KV3; ++x) kst[x] = kv_off(kv_lo + x, kv_lo + x, lane_chunk) + lane_off;
+    // per-column store offsets inside the Q tile (the swizzle key depends on the column)
+    uint32_t qst[Q3];
 #pragma unroll
     for (int x = 0; x < Q3; ++x) qst[x] = q_off(rp, q_lo + x, lane_chunk) + lane_off;      // row rp + 2: + 2 * XSW * 128 (same key)
     // columns of this third inside the image (constant over the march)
@@ -413,13 +415,15 @@ __device__ __forceinline__ void x_d_role(const CreffMmaParams& p, const XSmem& s
             }
             int ksB = ks + 2;
             ksB = ksB >= Cf::KVR ? ksB - Cf::KVR : ksB;
-            const uint32_t kA = kbase + (uint32_t)(ks * (Cf::KVC * 128)), kB = kbase + (uint32_t)(ksB * (Cf::KVC * 128));
+            const uint32_t kA = kbase + (uint32_t)(ks * (Cf::KVC * 128)) + lane_off, kB = kbase + (uint32_t)(ksB * (Cf::KVC * 128)) + lane_off;
+            const int keyA = kv_lo + Cf::WN * krA, keyB = keyA + 2 * Cf::WN;            // swizzle keys of column kv_lo in rows A / B
             x_dw_rows5<2, KV3, KVL>(ra, full, wk, wv, [&](int x, float2 a1, float2 a2, float2 b1, float2 b2, float2, float2) {
-                sts_u32(kA + kst[x], pack_h2_sat(a1.x, a1.y));
-                sts_u32(kA + kst[x] + (uint32_t)Cf::KV_BYTES, pack_h2_sat(a2.x, a2.y));
+                const uint32_t oA = kA + kv_off(kv_lo + x, keyA + x, lane_chunk), oB = kB + kv_off(kv_lo + x, keyB + x, lane_chunk);
+                sts_u32(oA, pack_h2_sat(a1.x, a1.y));
+                sts_u32(oA + (uint32_t)Cf::KV_BYTES, pack_h2_sat(a2.x, a2.y));
                 if (haveB) {
-                    sts_u32(kB + kst[x], pack_h2_sat(b1.x, b1.y));
-                    sts_u32(kB + kst[x] + (uint32_t)Cf::KV_BYTES, pack_h2_sat(b2.x, b2.y));
+                    sts_u32(oB, pack_h2_sat(b1.x, b1.y));
+                    sts_u32(oB + (uint32_t)Cf::KV_BYTES, pack_h2_sat(b2.x, b2.y));
                 }
             });
             // K / V are exactly 0 outside the image (attention zero padding, model/attention.py:199,207): border strips and
@@ -430,9 +434,9 @@ __device__ __forceinline__ void x_d_role(const CreffMmaParams& p, const XSmem& s
 #pragma unroll 1
                 for (int x = 0; x < kv_n; ++x) {
                     const bool okx = fx_lo + x >= 0 && fx_lo + x < p.W;
-                    const uint32_t o = kv_off(kv_lo + x, kv_lo + x, lane_chunk) + lane_off;
-                    if (!(okA && okx)) { sts_u32(kA + o, 0u); sts_u32(kA + o + (uint32_t)Cf::KV_BYTES, 0u); }
-                    if (haveB && !(okB && okx)) { sts_u32(kB + o, 0u); sts_u32(kB + o + (uint32_t)Cf::KV_BYTES, 0u); }
+                    const uint32_t oA = kA + kv_off(kv_lo + x, keyA + x, lane_chunk), oB = kB + kv_off(kv_lo + x, keyB + x, lane_chunk);
+                    if (!(okA && okx)) { sts_u32(oA, 0u); sts_u32(oA + (uint32_t)Cf::KV_BYTES, 0u); }
+                    if (haveB && !(okB && okx)) { sts_u32(oB, 0u); sts_u32(oB + (uint32_t)Cf::KV_BYTES, 0u); }
                 }
             }
         }
@@ -521,14 +525,14 @@ __device__ __forceinline__ void x_c_role(const CreffMmaParams& p, const XSmem& s
         int nk = 8 * j + (lane & 7);
         nk = nk < Cf::NK ? nk : Cf::NK - 1;
         const int ky = nk / Cf::WN, kx = nk - ky * Cf::WN, col = 4 * cw + kx;
-        aq[j] = (uint32_t)ky * ROWB + (uint32_t)(col * 128 + (((mi ^ col) & 7) << 4));             // chunk mi; chunk 4+mi = ^ 64
+        aq[j] = (uint32_t)ky * ROWB + kv_off(col, col + Cf::WN * ky, mi);                            // chunk mi; chunk 4+mi = ^ 64
     }
 #pragma unroll
     for (int i = 0; i < Cf::NT16; ++i) {
         int nk = 16 * i + ((mi & 1) << 3) + (lane & 7);
         nk = nk < Cf::NK ? nk : Cf::NK - 1;
         const int ky = nk / Cf::WN, kx = nk - ky * Cf::WN, col = 4 * cw + kx;
-        av[i] = (uint32_t)ky * ROWB + (uint32_t)(col * 128 + ((((mi >> 1) ^ col) & 7) << 4));        // chunk (mi>>1) + 2cp = ^ (cp << 5)
+        av[i] = (uint32_t)ky * ROWB + kv_off(col, col + Cf::WN * ky, mi >> 1);                       // chunk (mi>>1) + 2cp = ^ (cp << 5)
     }
     static_assert(Cf::WN <= Cf::KVR, "a key patch fits the ring");
     // classifier B fragments (final_conv weights, f16) and biases stay in registers for the whole march
