@@ -18,7 +18,7 @@ tail -2 gpurun_out/launches.csv
 echo "=== ncu full creff (f16 plan, from bench.py)"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:creff_march -c 1 -f -o gpurun_out/creff_march_f16 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --alt-precision none 2>&1 | tail -2
 echo "=== ncu full conv up_1 (f16 plan, from bench.py)"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_tc_halo_kernel -s 20 -c 1 -f -o gpurun_out/conv_halo_f16 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --alt-precision none 2>&1 | tail -2
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"conv_tc_halo_kernel.*256" -s 14 -c 1 -f -o gpurun_out/conv_halo_f16 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --alt-precision none 2>&1 | tail -2
 echo "=== sweep"
 timeout 600 python tools/sweep_creff.py --iters 3 2>&1 | tail -32
 echo "=== configs"
