@@ -453,6 +453,23 @@ def test_creff_wide_with_mv_warp_and_classifier(flow_kind, C, ncls, lr_dtype):
             assert torch.equal(out_a[i:i + 1].cpu().long(), out_l[i:i + 1].cpu().argmax(1))
 
 
+@pytest.mark.parametrize("C", [64, 128])
+def test_creff_mma_per_frame_keyframe_features(C):
+    """hr_shared = 0: every frame has its own (already warped) keyframe feature, batch 3, ragged sizes -- both tensor-core
+    engines (C = 64 march, C = 128 wide) against the oracle frame by frame; frames must not leak into each other."""
+    k, H, W, h, w, N = 5, 19, 37, 10, 19, 3
+    sd = creff_sd(C)
+    hr, lr = rnd(N, C, H, W, seed=61) * 0.6, rnd(N, C, h, w, seed=62) * 0.4
+    out_p, _, _ = ops.creff_fused(ops.nchw_to_nhwc(hr.to(DEV)), ops.nchw_to_nhwc(lr.to(DEV)), *creff_args(sd), k,
+                                  want_logits=False, lr_layout=L.NHWC, hr_layout=L.NHWC, engine=L.CREFF_MMA_F16, hr_shared=False)
+    for i in range(N):
+        ref = O.creff(sd, "fuse_attention.", hr[i:i + 1], lr[i:i + 1], k)
+        assert rel_err(out_p[i:i + 1], ref) < MMA_TOL, (i, rel_err(out_p[i:i + 1], ref))
+    one, _, _ = ops.creff_fused(ops.nchw_to_nhwc(hr[1:2].to(DEV)), ops.nchw_to_nhwc(lr[1:2].to(DEV)), *creff_args(sd), k,
+                                want_logits=False, lr_layout=L.NHWC, hr_layout=L.NHWC, engine=L.CREFF_MMA_F16)
+    assert torch.equal(one, out_p[1:2])
+
+
 @pytest.mark.parametrize("k", [3, 7, 9])
 @pytest.mark.parametrize("seg_rows", [8, 12])
 def test_creff_march_row_segments_are_seamless(k, seg_rows, monkeypatch):
