@@ -61,6 +61,8 @@ class Plan:
         self.names: List[str] = []
         self.keep: List[object] = []       # keeps device tensors / ctypes structs alive
         self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.parts: Optional[List[torch.cuda.CUDAGraph]] = None    # split capture: [phase 1, CReFF + post]
+        self.split_at: Optional[int] = None
         self.conv_flops = 0                # 2*MACs of conv/linear layers as executed
         self.n_launches = 0
 
@@ -314,8 +316,34 @@ class Plan:
                 if rc != L.OK:
                     L.check(rc, name)
 
-    def capture(self) -> None:
-        """Capture the launch sequence into a CUDA graph (replayed by run())."""
+    def launch_range(self, lo: int, hi: int) -> None:
+        with torch.cuda.device(self.device):
+            s = torch.cuda.current_stream().cuda_stream
+            for name, fn in zip(self.names[lo:hi], self.steps[lo:hi]):
+                rc = fn(s)
+                if rc != L.OK:
+                    L.check(rc, name)
+
+    def capture(self, split_at: Optional[int] = None) -> None:
+        """Capture the launch sequence into a CUDA graph (replayed by run()).  split_at = i: two graphs, launches [0, i) and
+        [i, n) -- run_part(0) / run_part(1) replay them separately (the caller may put a stream dependency, e.g. the NCCL
+        broadcast of the keyframe feature, between phase 1 and the CReFF launches)."""
+        if split_at is not None and 0 < split_at < len(self.steps):
+            with torch.cuda.device(self.device):
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    self.launch()
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                parts = []
+                for lo, hi in ((0, split_at), (split_at, len(self.steps))):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self.launch_range(lo, hi)
+                    parts.append(g)
+                self.parts, self.split_at = parts, split_at
+            return
         with torch.cuda.device(self.device):
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -329,10 +357,19 @@ class Plan:
             self.graph = g
 
     def run(self) -> None:
-        if self.graph is not None:
+        if self.parts is not None:
+            self.parts[0].replay()
+            self.parts[1].replay()
+        elif self.graph is not None:
             self.graph.replay()
         else:
             self.launch()
+
+    def run_part(self, i: int) -> None:
+        """Replay one half of a split capture (0: up to the split, 1: from the split on)."""
+        if self.parts is None:
+            raise RuntimeError("plan was not captured with split_at")
+        self.parts[i].replay()
 
     def profile(self, iters: int = 5, warmup: int = 2) -> List[Tuple[str, float]]:
         """Per-kernel device time (ms, mean over `iters`) with CUDA events on the launching stream."""

@@ -71,7 +71,7 @@ class NonKeyEngine:
 
     def __init__(self, arch: str, sd: Dict[str, torch.Tensor], n_frames: int, H: int, W: int, scale: float = 0.5,
                  precision: str = "tf32", k: int = 7, device="cuda:0", want_logits: bool = False, want_p: bool = False,
-                 graph: bool = True):
+                 graph: bool = True, split_keyframe: bool = False):
         if arch not in ARCH_INFO:
             raise KeyError(arch)
         self.arch, self.N, self.H, self.W, self.scale, self.k = arch, n_frames, H, W, scale, k
@@ -117,7 +117,10 @@ class NonKeyEngine:
             else:
                 self.preds, _ = pl.resize_argmax(out_l, H, W, L.RESIZE_BILINEAR_AC)          # evaluation.py:201-204
             if graph:
-                pl.capture()
+                # split_keyframe: phase 1 (needs only the frames) and the launches that read the keyframe feature are two
+                # graphs, so a broadcast of the feature (frame-level sharding) can overlap phase 1: step_phase1() / step_phase2()
+                first_ref = next(i for i, nm in enumerate(pl.names) if nm.startswith("hr_nchw_to_nhwc") or nm.startswith("creff"))
+                pl.capture(split_at=first_ref if split_keyframe else None)
         self.conv_flops_per_frame = pl.conv_flops / n_frames
         self.launches_per_step = pl.n_launches
 
@@ -129,6 +132,15 @@ class NonKeyEngine:
     def step(self) -> torch.Tensor:
         """One pass over the N non-keyframes with inputs already resident in HBM."""
         self.plan.run()
+        return self.preds
+
+    def step_phase1(self) -> None:
+        """Everything that does not read the keyframe feature (frame down-scale + LR-branch network); split_keyframe engines."""
+        self.plan.run_part(0)
+
+    def step_phase2(self) -> torch.Tensor:
+        """Keyframe-feature transpose, MV warp + CReFF + classifier (+ post-processing); split_keyframe engines."""
+        self.plan.run_part(1)
         return self.preds
 
     def step_host(self, imgs_pinned: torch.Tensor, mv_pinned: torch.Tensor, preds_pinned: torch.Tensor) -> torch.Tensor:

@@ -225,16 +225,28 @@ def main():
 
     def measure(precision):
         """Device-resident throughput, end-to-end throughput (pipelined and serial) and the per-kernel table."""
-        eng = ev.NonKeyEngine(ARCH, sd, n_local, H, W, SCALE, precision, K_WIN, device=dev, want_logits=True)
+        frame_mode = args.shard == "frame" and world > 1
+        eng = ev.NonKeyEngine(ARCH, sd, n_local, H, W, SCALE, precision, K_WIN, device=dev, want_logits=True, split_keyframe=frame_mode)
         eng.set_inputs(frames.to(dev), mvs.to(dev), ref_p.to(dev))
+        bc_stream = torch.cuda.Stream(dev) if frame_mode else None
 
         def bcast_ref():
-            if args.shard == "frame" and world > 1:
+            if frame_mode:
                 dist.broadcast(eng.ref_p, src=0)     # keyframe feature, once per GOP (ncclBroadcast over NVLink)
 
         def dev_step():
-            bcast_ref()
-            eng.step()
+            if not frame_mode:
+                eng.step()
+                return
+            # frame-level sharding: the broadcast of the keyframe feature (177 MB, once per GOP) runs on a side stream and
+            # overlaps phase 1, which needs only the frames; the CReFF launches wait for it
+            main = torch.cuda.current_stream()
+            bc_stream.wait_stream(main)              # the previous GOP's CReFF has finished reading the feature
+            with torch.cuda.stream(bc_stream):
+                dist.broadcast(eng.ref_p, src=0)
+            eng.step_phase1()
+            main.wait_stream(bc_stream)
+            eng.step_phase2()
 
         def timed_steps(fn, steps):
             """K steps, L2 flushed between them (outside the per-step event brackets); sum of step times, max over ranks."""

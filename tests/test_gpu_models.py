@@ -174,3 +174,23 @@ def test_host_pipeline_matches_resident_steps():
     for s in range(STEPS):
         assert torch.equal(batches[s][2], want[s]), s
     assert not torch.equal(want[0], want[1])
+
+
+def test_split_keyframe_engine_matches_single_graph():
+    """split_keyframe=True (two graphs: phase 1 | keyframe-feature consumers, so a broadcast of the feature can overlap
+    phase 1) gives exactly the class maps of the single-graph engine, also when the feature arrives between the halves."""
+    g = load_golden("camvid_psp18_s05")
+    arch, _, sd, imgs, ref_p, mv, flow, scale = case_setup(g)
+    H, W = imgs.shape[-2:]
+    one = ev.NonKeyEngine(arch, sd, 1, H, W, scale, "f16", device=DEV)
+    two = ev.NonKeyEngine(arch, sd, 1, H, W, scale, "f16", device=DEV, split_keyframe=True)
+    mvd = torch.from_numpy(mv).unsqueeze(0).to(DEV)
+    one.set_inputs(imgs.to(DEV), mvd, ref_p.to(DEV))
+    want = one.step().clone()
+    two.set_inputs(imgs.to(DEV), mvd, torch.zeros_like(ref_p).to(DEV))
+    two.step_phase1()
+    two.ref_p.copy_(ref_p.to(DEV))          # the keyframe feature lands after phase 1 was enqueued
+    got = two.step_phase2()
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+    assert torch.equal(two.step(), want)
