@@ -7,7 +7,8 @@
 //
 // The softmax couples all channels of a pixel (S = sum over channels), so the one-pass column march of the C = 64 engine
 // would need m times its shared memory.  These maps are small (a few MB per operand), so the work is split in two
-// launches with Q, K, V in fp16 and the residual in fp32 going through HBM / L2 once:
+// launches (plus a tiny one that computes the per-pixel gather records once) with Q, K, V in fp16 and the residual in
+// fp32 going through HBM / L2 once:
 //   1. creff_wide_prep_kernel: CTA = 8x16 pixels x 64 channels.  Per position of the 10x18 halo tile one thread does the
 //      f64 MV arithmetic and leaves a gather record (the same 2x2-block records as the march engine); half-warps gather
 //      the MV-warped hr tile and the lr_up tile into shared memory (fp32); the three depthwise 3x3 convolutions run from
@@ -26,6 +27,8 @@ struct WideParams {
     CreffMmaParams b;
     __half *Q, *K, *V;        // [N,H,W,C] fp16
     float* R;                 // [N,H,W,C] fp32 residual (lr_up)
+    float4* rec_w;            // [N,H,W][2: hr, lr] block weights of the gather records
+    uint4* rec_a;             // [N,H,W][2] {block byte offset lo, hi (channel 0 of the block's top-left pixel), row stride, valid}
     int lr_dtype;
 };
 
@@ -49,6 +52,34 @@ __device__ __forceinline__ void w_block_of(const PosRec& r, int Wimg, int Himg, 
         if (by > 0 && by == Himg - 1) { by -= 1; w.x = 0.f; w.y = 0.f; w.z = ww; w.w = ee; }
         else { w.x = ww; w.y = ee; w.z = 0.f; w.w = 0.f; }
     }
+}
+
+// launch 0: the gather records, once per pixel (the prep CTAs of all C/64 channel groups and of neighbouring tiles share
+// them; the hr record carries the f64 MV arithmetic of evaluation.py:177-183, incl. the bilinear resize of the MV field)
+template <typename TLR>
+__global__ void __launch_bounds__(256) creff_wide_rec_kernel(WideParams q) {
+    const CreffMmaParams& p = q.b;
+    constexpr int LR_ES = (int)sizeof(TLR);
+    const long long total = (long long)p.N * p.H * p.W * 2;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int src = (int)(i & 1);
+    long long r = i >> 1;
+    const int fx = (int)(r % p.W); r /= p.W;
+    const int fy = (int)(r % p.H);
+    const int n = (int)(r / p.H);
+    const float lsh = resize_scale(p.h, p.H, ARSEG_RESIZE_BILINEAR_AC), lsw = resize_scale(p.w, p.W, ARSEG_RESIZE_BILINEAR_AC);
+    const PosRec rec = src == 0 ? pos_hr(p, n, fy, fx) : pos_lr(p, lsh, lsw, fy, fx);
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    unsigned long long off = 0;
+    uint32_t rs = src == 0 ? (uint32_t)p.W * p.C * 4 : (uint32_t)p.w * p.C * LR_ES;
+    if (rec.info >= 0) {
+        int bx, by;
+        if (src == 0) { w_block_of(rec, p.W, p.H, w, bx, by); off = ((unsigned long long)by * p.W + bx) * p.C * 4; }
+        else { w_block_of(rec, p.w, p.h, w, bx, by); off = ((unsigned long long)by * p.w + bx) * p.C * LR_ES; }
+    }
+    q.rec_w[i] = w;
+    q.rec_a[i] = make_uint4((uint32_t)off, (uint32_t)(off >> 32), rs, (uint32_t)src);
 }
 
 template <typename TLR>
@@ -75,23 +106,21 @@ __global__ void __launch_bounds__(WP_THREADS) creff_wide_prep_kernel(WideParams 
         const float* b = cv == 0 ? p.bk : (cv == 1 ? p.bv : p.bq);
         s_dw[i] = tp < 9 ? __ldg(w + (size_t)(c0 + ch) * 9 + tp) : __ldg(b + c0 + ch);
     }
-    // gather records: one thread per halo position and source (hr: MV-warped sample, evaluation.py:61-87; lr: lr_up sample,
-    // model/attention.py:191); positions outside the image are zero-weight records (depthwise zero padding)
+    // gather records of the halo tile (computed once per pixel by creff_wide_rec_kernel); positions outside the image are
+    // zero-weight records (depthwise zero padding); the block offset becomes an address of this frame / channel group
     for (int i = tid; i < 2 * WP_NP; i += WP_THREADS) {
         const int src = i / WP_NP, pz = i - src * WP_NP;
         const int fy = y0 - 1 + pz / WP_HW, fx = x0 - 1 + pz % WP_HW;
-        const PosRec r = src == 0 ? pos_hr(p, n, fy, fx) : pos_lr(p, lsh, lsw, fy, fx);
         float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-        const char* a = src == 0 ? hrb : lrb;
-        uint32_t rs = src == 0 ? (uint32_t)p.W * C * 4 : (uint32_t)p.w * C * LR_ES;
-        if (r.info >= 0) {
-            int bx, by;
-            if (src == 0) { w_block_of(r, p.W, p.H, w, bx, by); a = hrb + ((size_t)by * p.W + bx) * C * 4; }
-            else { w_block_of(r, p.w, p.h, w, bx, by); a = lrb + ((size_t)by * p.w + bx) * C * LR_ES; }
+        uint4 a = make_uint4(0u, 0u, src == 0 ? (uint32_t)p.W * C * 4 : (uint32_t)p.w * C * LR_ES, (uint32_t)src);
+        if (fy >= 0 && fy < p.H && fx >= 0 && fx < p.W) {
+            const size_t ri = ((((size_t)n * p.H + fy) * p.W + fx) << 1) + src;
+            w = __ldg(q.rec_w + ri);
+            a = __ldg(q.rec_a + ri);
         }
-        const unsigned long long au = reinterpret_cast<unsigned long long>(a);
+        const unsigned long long au = reinterpret_cast<unsigned long long>(src == 0 ? hrb : lrb) + (((unsigned long long)a.y << 32) | a.x);
         s_w[i] = w;
-        s_a[i] = make_uint4((uint32_t)au, (uint32_t)(au >> 32), rs, (uint32_t)src);
+        s_a[i] = make_uint4((uint32_t)au, (uint32_t)(au >> 32), a.z, (uint32_t)src);
     }
     __syncthreads();
     // gather: half-warp per position, 4 channels per lane, WP_GJ positions' loads in flight per half-warp
@@ -511,8 +540,8 @@ __global__ void __launch_bounds__(WA_THREADS, 2) creff_wide_attn_kernel(WidePara
 // host side
 // ---------------------------------------------------------------------------------------------
 size_t creff_wide_workspace_bytes(int N, int C, int H, int W) {
-    const size_t e = (size_t)N * H * W * C;
-    return e * (3 * sizeof(__half) + sizeof(float)) + 1024;
+    const size_t e = (size_t)N * H * W * C, px = (size_t)N * H * W;
+    return e * (3 * sizeof(__half) + sizeof(float)) + px * 2 * (sizeof(float4) + sizeof(uint4)) + 1024;
 }
 
 bool creff_wide_supported(const arseg_creff_args* a) {
@@ -558,9 +587,18 @@ int creff_wide_launch(const arseg_creff_args* a, void* ws, size_t ws_bytes, cuda
     q.Q = reinterpret_cast<__half*>(w8 + e * 4);
     q.K = q.Q + e;
     q.V = q.K + e;
+    q.rec_w = reinterpret_cast<float4*>(q.V + e);                 // e * 10 bytes so far: 16-byte aligned (e is a multiple of 64)
+    q.rec_a = reinterpret_cast<uint4*>(q.rec_w + (size_t)a->N * a->H * a->W * 2);
     q.lr_dtype = a->lr_dtype;
     ARSEG_REQUIRE(a->N <= 65535 && a->C / 64 <= 65535, "creff_wide: N / C too large");
     const dim3 grid((unsigned)(ceil_div(a->W, WP_TW) * ceil_div(a->H, WP_TH)), (unsigned)(a->C / 64), (unsigned)a->N);
+    {
+        const long long nrec = (long long)a->N * a->H * a->W * 2;
+        const unsigned rb = (unsigned)((nrec + 255) / 256);
+        if (a->lr_dtype == ARSEG_F32) creff_wide_rec_kernel<float><<<rb, 256, 0, st>>>(q);
+        else creff_wide_rec_kernel<__half><<<rb, 256, 0, st>>>(q);        // fp16 and bf16 LR features: same element size
+        ARSEG_CHECK_LAUNCH("creff_wide_rec");
+    }
     if (a->lr_dtype == ARSEG_F32) {
         ARSEG_CUDA(cudaFuncSetAttribute(creff_wide_prep_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WP_SMEM));
         creff_wide_prep_kernel<float><<<grid, WP_THREADS, WP_SMEM, st>>>(q);
