@@ -532,6 +532,16 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv_tc_halo_kernel(const __gr
 #pragma unroll 1
             for (int ci = 0; ci < CPW; ++ci) {
                 const int cb = (chalf * CPW + ci) * 32;
+                const int co0 = n0 + cb;
+                // residual of this chunk: 16-byte loads issued BEFORE the accumulator is read back, so their latency hides
+                // behind the TMEM load (32 scalar 2-byte loads after it cost BasicBlock.conv2 layers ~30 % of their time)
+                constexpr int RV = 16 / (int)sizeof(T), RN = 32 / RV;
+                uint4 rr[RN];
+                const bool rvec = res != nullptr && valid && co0 + 32 <= p.Cout && p.Cout % RV == 0;
+                if (rvec) {
+#pragma unroll
+                    for (int q = 0; q < RN; ++q) rr[q] = __ldg(reinterpret_cast<const uint4*>(res + co0) + q);
+                }
                 uint32_t r[32];
                 tmem_ld32(tmem_d + (uint32_t)cb, r);
                 tmem_ld_wait();
@@ -539,7 +549,6 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv_tc_halo_kernel(const __gr
                     tc_fence_before();
                     mbar_arrive(&tempty_bar[acc]);
                 }
-                const int co0 = n0 + cb;
                 if (!valid || co0 >= p.Cout) continue;
                 float v[32];
 #pragma unroll
@@ -550,7 +559,11 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv_tc_halo_kernel(const __gr
                     v[j + 2] = fmaf(__uint_as_float(r[j + 2]), sc.z, sh.z); v[j + 3] = fmaf(__uint_as_float(r[j + 3]), sc.w, sh.w);
                 }
                 const bool vec = co0 + 32 <= p.Cout && ((p.ocs | p.oco) % (16 / (int)sizeof(T)) == 0);
-                if (res) {
+                if (rvec) {
+                    const T* rt = reinterpret_cast<const T*>(rr);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] += to_f32(rt[j]);
+                } else if (res) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         if (co0 + j < p.Cout) v[j] += to_f32(res[co0 + j]);
