@@ -298,6 +298,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const uint32_t tmem_d = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS);
 #pragma unroll 1
             for (int cb = 0; cb < BLOCK_N; cb += 32) {
+                const int co0 = n0 + cb;
+                // residual as 16-byte loads issued before the accumulator read-back (see conv_tc_halo_kernel)
+                constexpr int RV = 16 / (int)sizeof(T), RN = 32 / RV;
+                uint4 rr[RN];
+                const bool rvec = res != nullptr && valid && co0 + 32 <= p.Cout && p.Cout % RV == 0;
+                if (rvec) {
+#pragma unroll
+                    for (int q = 0; q < RN; ++q) rr[q] = __ldg(reinterpret_cast<const uint4*>(res + co0) + q);
+                }
                 uint32_t r[32];
                 tmem_ld32(tmem_d + (uint32_t)cb, r);
                 tmem_ld_wait();
@@ -305,16 +314,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     tc_fence_before();
                     mbar_arrive(&tempty_bar[acc]);
                 }
-                const int co0 = n0 + cb;
                 if (!valid || co0 >= p.Cout) continue;
                 float v[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float a = fmaf(__uint_as_float(r[j]), s_scale[co0 + j], s_shift[co0 + j]);
-                    if (res && co0 + j < p.Cout) a += to_f32(res[co0 + j]);
-                    if (p.act == ARSEG_ACT_RELU) a = fmaxf(a, 0.f);
-                    else if (p.act == ARSEG_ACT_PRELU) a = a > 0.f ? a : a * p.slope;
-                    v[j] = a;
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 sc = *reinterpret_cast<const float4*>(s_scale + co0 + j);
+                    const float4 sh = *reinterpret_cast<const float4*>(s_shift + co0 + j);
+                    v[j] = fmaf(__uint_as_float(r[j]), sc.x, sh.x); v[j + 1] = fmaf(__uint_as_float(r[j + 1]), sc.y, sh.y);
+                    v[j + 2] = fmaf(__uint_as_float(r[j + 2]), sc.z, sh.z); v[j + 3] = fmaf(__uint_as_float(r[j + 3]), sc.w, sh.w);
+                }
+                if (rvec) {
+                    const T* rt = reinterpret_cast<const T*>(rr);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] += to_f32(rt[j]);
+                } else if (res) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (co0 + j < p.Cout) v[j] += to_f32(res[co0 + j]);
+                }
+                if (p.act == ARSEG_ACT_RELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                } else if (p.act == ARSEG_ACT_PRELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
                 }
                 if (!TF32 && p.out_f32) {
                     if (co0 + 32 <= p.Cout && ((p.ocs | p.oco) % 4 == 0)) {
