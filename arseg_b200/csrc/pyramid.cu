@@ -119,30 +119,47 @@ __global__ void __launch_bounds__(256) pyramid_upcat_kernel(const float* __restr
                                                             PyrLevels lv) {
     constexpr int VEC = 16 / (int)sizeof(T);               // channels per 16-byte store
     const int Ct = lv.nlev * Cout + Cf, total = lv.off[lv.nlev];
-    const int sv = lv.nlev * Cout / VEC, fv = Cf / VEC, row_elems = W * (sv + fv);
+    const int sv = lv.nlev * Cout / VEC, fv = Cf / VEC;
+    // horizontal taps / weights per (level, x): computed once per CTA instead of once per 16-byte store
+    extern __shared__ __align__(16) float4 s_xt[];          // [nlev][W] {x0, x1 (as int bits), lx0, lx1}
+    for (int i = threadIdx.x; i < lv.nlev * W; i += blockDim.x) {
+        const int l = i / W, x = i - l * W, s = lv.bins[l];
+        int x0, x1;
+        float lx0, lx1;
+        bilinear_src(resize_scale(s, W, mode), x, s, mode, x0, x1, lx0, lx1);
+        s_xt[i] = make_float4(__int_as_float(x0), __int_as_float(x1), lx0, lx1);
+    }
+    __syncthreads();
     for (int row = blockIdx.x; row < N * H; row += gridDim.x) {
         const int n = row / H, y = row - n * H;
         T* orow = out + (size_t)row * W * Ct;
         const T* frow = feats + (size_t)row * W * Cf;
-        for (int i = threadIdx.x; i < row_elems; i += blockDim.x) {
-            const int x = i / (sv + fv), e = i - x * (sv + fv);
-            PVec<T, VEC> o;
-            int dst_c;
+        // a thread owns one 16-byte channel pack and walks the row: level, channel and the vertical taps are loop invariant
+        for (int e = threadIdx.x; e < sv + fv; e += blockDim.x) {
             if (e >= sv) {
                 const int c = (e - sv) * VEC;
-                o = *reinterpret_cast<const PVec<T, VEC>*>(frow + (size_t)x * Cf + c);
-                dst_c = feats_coff + c;
-            } else {
-                const int ch = e * VEC, l = ch / Cout, c = ch - l * Cout, s = lv.bins[l];
-                int y0, y1, x0, x1;
-                float ly0, ly1, lx0, lx1;
-                bilinear_src(resize_scale(s, H, mode), y, s, mode, y0, y1, ly0, ly1);
-                bilinear_src(resize_scale(s, W, mode), x, s, mode, x0, x1, lx0, lx1);
-                const float* sb = stage + ((size_t)n * total + lv.off[l]) * Cout + c;
-                const float4* a = reinterpret_cast<const float4*>(sb + (size_t)(y0 * s + x0) * Cout);
-                const float4* b = reinterpret_cast<const float4*>(sb + (size_t)(y0 * s + x1) * Cout);
-                const float4* cc = reinterpret_cast<const float4*>(sb + (size_t)(y1 * s + x0) * Cout);
-                const float4* d = reinterpret_cast<const float4*>(sb + (size_t)(y1 * s + x1) * Cout);
+                for (int x = 0; x < W; ++x)
+                    *reinterpret_cast<PVec<T, VEC>*>(orow + (size_t)x * Ct + feats_coff + c) =
+                        *reinterpret_cast<const PVec<T, VEC>*>(frow + (size_t)x * Cf + c);
+                continue;
+            }
+            const int ch = e * VEC, l = ch / Cout, c = ch - l * Cout, s = lv.bins[l];
+            int y0, y1;
+            float ly0, ly1;
+            bilinear_src(resize_scale(s, H, mode), y, s, mode, y0, y1, ly0, ly1);
+            const float* sb = stage + ((size_t)n * total + lv.off[l]) * Cout + c;
+            const float* r0 = sb + (size_t)(y0 * s) * Cout;
+            const float* r1 = sb + (size_t)(y1 * s) * Cout;
+            const float4* xt = s_xt + l * W;
+            for (int x = 0; x < W; ++x) {
+                const float4 t = xt[x];
+                const int x0 = __float_as_int(t.x), x1 = __float_as_int(t.y);
+                const float lx0 = t.z, lx1 = t.w;
+                const float4* a = reinterpret_cast<const float4*>(r0 + (size_t)x0 * Cout);
+                const float4* b = reinterpret_cast<const float4*>(r0 + (size_t)x1 * Cout);
+                const float4* cc = reinterpret_cast<const float4*>(r1 + (size_t)x0 * Cout);
+                const float4* d = reinterpret_cast<const float4*>(r1 + (size_t)x1 * Cout);
+                PVec<T, VEC> o;
 #pragma unroll
                 for (int q = 0; q < VEC / 4; ++q) {
                     const float4 va = __ldg(a + q), vb = __ldg(b + q), vc = __ldg(cc + q), vd = __ldg(d + q);
@@ -152,9 +169,8 @@ __global__ void __launch_bounds__(256) pyramid_upcat_kernel(const float* __restr
                     o.v[4 * q + 2] = from_f32<T>(ly0 * (lx0 * va.z + lx1 * vb.z) + ly1 * (lx0 * vc.z + lx1 * vd.z));
                     o.v[4 * q + 3] = from_f32<T>(ly0 * (lx0 * va.w + lx1 * vb.w) + ly1 * (lx0 * vc.w + lx1 * vd.w));
                 }
-                dst_c = stage_coff + ch;
+                *reinterpret_cast<PVec<T, VEC>*>(orow + (size_t)x * Ct + stage_coff + ch) = o;
             }
-            *reinterpret_cast<PVec<T, VEC>*>(orow + (size_t)x * Ct + dst_c) = o;
         }
     }
 }
@@ -237,12 +253,14 @@ int arseg_pyramid_upsample_concat(const float* stage, const void* feats, void* o
     const long long rows = (long long)N * H, cap = (long long)sm_count() * 16;
     const int grid = (int)(rows < cap ? rows : cap);
     cudaStream_t st = as_stream(stream);
+    const size_t xt_bytes = (size_t)lv.nlev * W * sizeof(float4);
+    ARSEG_REQUIRE(xt_bytes <= 48 * 1024, "pyramid_upcat: W too large");
     if (dtype == ARSEG_F32)
-        pyramid_upcat_kernel<float><<<grid, 256, 0, st>>>(stage, (const float*)feats, (float*)out, N, H, W, Cout, Cf, stage_coff, feats_coff, mode, lv);
+        pyramid_upcat_kernel<float><<<grid, 256, xt_bytes, st>>>(stage, (const float*)feats, (float*)out, N, H, W, Cout, Cf, stage_coff, feats_coff, mode, lv);
     else if (dtype == ARSEG_F16)
-        pyramid_upcat_kernel<__half><<<grid, 256, 0, st>>>(stage, (const __half*)feats, (__half*)out, N, H, W, Cout, Cf, stage_coff, feats_coff, mode, lv);
+        pyramid_upcat_kernel<__half><<<grid, 256, xt_bytes, st>>>(stage, (const __half*)feats, (__half*)out, N, H, W, Cout, Cf, stage_coff, feats_coff, mode, lv);
     else if (dtype == ARSEG_BF16)
-        pyramid_upcat_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(stage, (const __nv_bfloat16*)feats, (__nv_bfloat16*)out, N, H, W, Cout, Cf, stage_coff, feats_coff, mode, lv);
+        pyramid_upcat_kernel<__nv_bfloat16><<<grid, 256, xt_bytes, st>>>(stage, (const __nv_bfloat16*)feats, (__nv_bfloat16*)out, N, H, W, Cout, Cf, stage_coff, feats_coff, mode, lv);
     else ARSEG_UNSUPPORTED("pyramid_upcat: dtype %d", dtype);
     ARSEG_CHECK_LAUNCH("pyramid_upcat");
     return ARSEG_OK;
