@@ -18,7 +18,7 @@ RESIZE_BILINEAR, RESIZE_BILINEAR_AC, RESIZE_NEAREST = 0, 1, 2
 NCHW, NHWC = 0, 1
 CONV_SIMT_F32, CONV_TC_TF32, CONV_TC_BF16, CONV_TC_F16 = 1, 2, 3, 4
 CREFF_EXACT_F32, CREFF_MMA_F16 = 0, 1
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 vp, ci, cf = C.c_void_p, C.c_int, C.c_float
 
@@ -35,7 +35,7 @@ class CreffArgs(C.Structure):
                 ("lr", vp), ("lr_layout", ci), ("lr_dtype", ci), ("h", ci), ("w", ci),
                 ("wq", vp), ("bq", vp), ("wk", vp), ("bk", vp), ("wv", vp), ("bv", vp), ("wcls", vp), ("bcls", vp),
                 ("ncls", ci), ("log_softmax", ci), ("out_p", vp), ("out_logits", vp), ("out_argmax", vp),
-                ("N", ci), ("C", ci), ("H", ci), ("W", ci), ("k", ci), ("workspace", vp), ("workspace_bytes", C.c_size_t)]
+                ("N", ci), ("C", ci), ("H", ci), ("W", ci), ("k", ci), ("workspace", vp), ("workspace_bytes", C.c_size_t), ("hr_dtype", ci)]
 
 
 _PROTOS = {

@@ -343,6 +343,10 @@ extern "C" int arseg_creff_fused_fwd(const arseg_creff_args* a, arseg_stream_t s
     ARSEG_REQUIRE(a->lr_layout == ARSEG_NCHW || a->lr_layout == ARSEG_NHWC, "creff: lr layout %d", a->lr_layout);
     if (a->lr_layout == ARSEG_NCHW) ARSEG_REQUIRE(a->lr_dtype == ARSEG_F32, "creff: NCHW lr must be fp32");
     else ARSEG_REQUIRE(a->lr_dtype == ARSEG_F32 || a->lr_dtype == ARSEG_BF16 || a->lr_dtype == ARSEG_F16, "creff: lr dtype %d", a->lr_dtype);
+    ARSEG_REQUIRE(a->hr_dtype == ARSEG_F32 || a->hr_dtype == ARSEG_F16, "creff: hr dtype %d", a->hr_dtype);
+    if (a->hr_dtype == ARSEG_F16)
+        ARSEG_REQUIRE(a->engine == ARSEG_CREFF_MMA_F16 && a->hr_layout == ARSEG_NHWC && a->C == 64,
+                      "creff: an f16 keyframe feature needs the tensor-core engine, NHWC and C = 64");
     cudaStream_t st = as_stream(stream);
     if (a->engine == ARSEG_CREFF_MMA_F16) {
         if (creff_wide_supported(a)) return creff_wide_launch(a, a->workspace, a->workspace_bytes, st);
@@ -353,7 +357,7 @@ extern "C" int arseg_creff_fused_fwd(const arseg_creff_args* a, arseg_stream_t s
     ARSEG_REQUIRE(a->engine == ARSEG_CREFF_EXACT_F32, "creff: unknown engine %d", a->engine);
     if (a->hr_layout != ARSEG_NCHW) ARSEG_UNSUPPORTED("creff: the exact fp32 engine takes hr in NCHW");
     CreffParams p;
-    p.hr = a->hr; p.hr_shared = a->hr_shared; p.flow = a->flow; p.flow_dtype = a->flow_dtype; p.Hm = a->Hm; p.Wm = a->Wm;
+    p.hr = reinterpret_cast<const float*>(a->hr); p.hr_shared = a->hr_shared; p.flow = a->flow; p.flow_dtype = a->flow_dtype; p.Hm = a->Hm; p.Wm = a->Wm;
     p.lr = a->lr; p.h = a->h; p.w = a->w;
     p.wq = a->wq; p.bq = a->bq; p.wk = a->wk; p.bk = a->bk; p.wv = a->wv; p.bv = a->bv; p.wcls = a->wcls; p.bcls = a->bcls;
     p.ncls = a->ncls; p.log_softmax = a->log_softmax; p.out_p = a->out_p; p.out_logits = a->out_logits;

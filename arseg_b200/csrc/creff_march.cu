@@ -1,6 +1,6 @@
 // creff_march.cu -- fused MV-warp + CReFF + classifier, column-marching tensor-core engine (sm_100a).
 //
-// Same contract and arithmetic as creff_mma.cu (reference: evaluation.py:177-183 MV rescale + warpFeature,
+// Contract and arithmetic (reference: evaluation.py:177-183 MV rescale + warpFeature,
 // model/attention.py:184-213 MyAttention.forward, model/pspnet.py:226-229 final_conv + LogSoftmax,
 // evaluation.py:204 argmax), C = 64, NHWC operands.  What changes is the decomposition:
 //
@@ -900,6 +900,30 @@ int creff_march_launch(CreffMmaParams& p, int k, int lr_dtype, cudaStream_t st) 
         case 9: return creff_march_launch_k<9>(p, lr_dtype, st);
         default: ARSEG_UNSUPPORTED("creff_march: window k=%d", k);
     }
+}
+
+bool creff_mma_supported(const arseg_creff_args* a) {
+    return a->C == MC && a->hr_layout == ARSEG_NHWC && a->lr_layout == ARSEG_NHWC && (a->k == 3 || a->k == 5 || a->k == 7 || a->k == 9) &&
+           (!a->wcls || a->ncls <= 32) && ((size_t)a->H * a->W < (1u << 29)) && ((size_t)a->h * a->w < (1u << 29));
+}
+
+int creff_tc_launch(CreffMmaParams& p, int k, cudaStream_t st);   // creff_tc.cu
+
+// ARSEG_CREFF_MMA_F16 at C = 64: f16 keyframe feature + f16 LR feature -> the tcgen05 engine (creff_tc.cu, k <= 7);
+// fp32 keyframe feature -> the column-marching mma.sync engine of this file (any LR dtype, k <= 9).
+int creff_mma_launch(const arseg_creff_args* a, cudaStream_t st) {
+    CreffMmaParams p;
+    p.hr = reinterpret_cast<const float*>(a->hr); p.hr_shared = a->hr_shared; p.flow = a->flow; p.flow_dtype = a->flow_dtype; p.Hm = a->Hm; p.Wm = a->Wm;
+    p.lr = a->lr; p.h = a->h; p.w = a->w;
+    p.wq = a->wq; p.bq = a->bq; p.wk = a->wk; p.bk = a->bk; p.wv = a->wv; p.bv = a->bv; p.wcls = a->wcls; p.bcls = a->bcls;
+    p.ncls = a->ncls; p.log_softmax = a->log_softmax; p.out_p = a->out_p; p.out_logits = a->out_logits;
+    p.out_argmax = a->out_argmax; p.N = a->N; p.C = a->C; p.H = a->H; p.W = a->W;
+    if (a->hr_dtype == ARSEG_F16) {
+        if (a->lr_dtype != ARSEG_F16 || a->k > 7)
+            ARSEG_UNSUPPORTED("creff: an f16 keyframe feature selects the tcgen05 engine, which needs an f16 LR feature and k <= 7 (lr dtype %d, k = %d)", a->lr_dtype, a->k);
+        return creff_tc_launch(p, a->k, st);
+    }
+    return creff_march_launch(p, a->k, a->lr_dtype, st);
 }
 
 }  // namespace arseg

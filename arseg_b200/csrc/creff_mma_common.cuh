@@ -140,6 +140,24 @@ __device__ __forceinline__ PosRec pos_lr(const CreffMmaParams& p, float lsh, flo
     return r;
 }
 
+// A gather record names a 2x2 source block that lies INSIDE the image (top-left pixel clamped to [0, W-2] x [0, H-2]) plus
+// the four weights of its pixels, so the taps are base, base + one pixel, base + one row, base + one row + one pixel.
+// PosRec names the taps by a clamped NW tap and dx / dy flags instead; where a flag is 0 both taps of that direction read
+// the same pixel (image border), and their weights are merged onto whichever block column / row holds it.
+__device__ __forceinline__ void rec_block_of(const PosRec& r, int Wimg, int Himg, float4& w, int& bx, int& by) {
+    w = r.w; bx = r.cx; by = r.cy;
+    if (!((r.info >> 1) & 1)) {
+        const float nn = w.x + w.y, ss = w.z + w.w;
+        if (bx > 0 && bx == Wimg - 1) { bx -= 1; w.x = 0.f; w.y = nn; w.z = 0.f; w.w = ss; }
+        else { w.x = nn; w.y = 0.f; w.z = ss; w.w = 0.f; }
+    }
+    if (!(r.info & 1)) {
+        const float ww = w.x + w.z, ee = w.y + w.w;
+        if (by > 0 && by == Himg - 1) { by -= 1; w.x = 0.f; w.y = 0.f; w.z = ww; w.w = ee; }
+        else { w.x = ww; w.y = ee; w.z = 0.f; w.w = 0.f; }
+    }
+}
+
 // two consecutive channels of a source pixel as float2
 __device__ __forceinline__ float2 ld2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
 __device__ __forceinline__ float2 ld2(const __nv_bfloat16* p) {

@@ -1,0 +1,833 @@
+// creff_tc.cu -- fused MV-warp + CReFF + classifier on the 5th-gen tensor cores (tcgen05 + TMEM), sm_100a, C = 64.
+//
+// Same contract and arithmetic as creff_march.cu (reference: evaluation.py:177-183 MV rescale + warpFeature,
+// model/attention.py:184-213 MyAttention.forward, model/pspnet.py:226-229 final_conv + LogSoftmax, evaluation.py:204
+// argmax).  The window contractions S = Q K^T and O = P V and the classifier run as tcgen05.mma with the accumulators,
+// P and the classifier input in tensor memory; nothing of the attention goes through ldmatrix / mma.sync any more.
+//
+//   * A CTA owns a 16-pixel-wide column strip of one frame and marches down it one TILE = 8 rows x 16 pixels = 128
+//     queries at a time: query (qy, qx) is row qy*16+qx of the M = 128 UMMA tile, i.e. TMEM lane qy*16+qx.
+//   * K and V live in shared-memory rings of image rows, every key one 128-byte row (64 x f16) in the canonical
+//     SWIZZLE_128B layout, TKP = 24 keys per ring row (16 + k - 1 used), so consecutive ring rows are contiguous
+//     8-key groups (SBO = 1024): ONE K-major B descriptor spans up to 8 key rows (N = 24 * rows), and the same bytes
+//     read as an MN-major B operand are V[key][channel] for O = P V.  Layouts verified by tools/umma_probe.cu.
+//   * S (128 lanes x NK fp32 columns, NK = 24 * (8 + k - 1)) is read back by four softmax warps (TMEM lane quarter =
+//     warp index): every lane owns one query, masks the columns outside its own k x k window, and writes the
+//     un-normalised P as packed f16 pairs over the S columns it has consumed; P is then the TMEM A operand of P V.
+//     The row sums come from one more MMA against a ones tile, the residual lr_up + O / sum is formed in registers,
+//     goes back to TMEM as f16 and is the A operand of the classifier MMA.
+//   * Producer roles as in the march engine, handing rows over through mbarriers:
+//       G (6 warps): bilinear gather of the MV-warped keyframe rows and the lr_up rows (quarter-warp per position,
+//                    8 channels = 16 bytes per lane, f16 sources) into f16 row rings;
+//       D (5 warps): depthwise 3x3 convolutions (FFMA2): two K warps, two V warps (4 rows x half the columns each),
+//                    one Q warp; K, V -> rings, Q -> the A tile;
+//       M (1 warp):  the single MMA-issuing thread;
+//       C (4 warps): softmax, residual, log-softmax / argmax, stores.
+#include "creff_mma_common.cuh"
+#include <cstdlib>
+
+namespace arseg {
+
+constexpr int TSW = 16;                    // strip width (pixels)
+constexpr int TTHREADS = 512;
+constexpr int TC_WARPS = 4;                // warps 0..3: TMEM lane quarter = warp
+constexpr int TM_WARP = 4;                 // MMA issuer (and TMEM allocator)
+constexpr int TG_W0 = 5, TG_WARPS = 6;     // gather warps 5..10
+constexpr int TD_W0 = 11, TD_WARPS = 5;    // depthwise warps 11..15: K K V V Q
+constexpr int TG_THREADS = 32 * TG_WARPS;
+constexpr int TNQW = 4 * TG_WARPS;         // gather quarter-warps: one position each per slot
+constexpr int TJA = 4;                     // gather positions in flight per quarter-warp
+constexpr int TKP = 24;                    // keys per K/V ring row
+constexpr int TROWB = TKP * 128;           // bytes per K/V ring row
+constexpr int THRR = 10, TLRR = 18;        // warped-hr / lr_up ring rows
+constexpr int TLC = TSW + 2;               // lr_up ring columns
+constexpr int TNB = 4;                     // mbarriers per hand-off (indexed by step & 3)
+constexpr int TBAR_G = 1;                  // named barrier of the G group
+constexpr int TNCLS = 32;                  // classifier rows staged (>= ncls)
+
+template <int K> struct TCfg {
+    static constexpr int R = K / 2;
+    static constexpr int NKR = 8 + 2 * R;                          // key rows of a tile
+    static constexpr int PADR = (4 - (2 * R) % 4) % 4;             // rows produced before the first key row (4-row half-steps)
+    static constexpr int HP = (2 * R + PADR) / 4;                  // half-steps before the first query row
+    static constexpr int KVC = TSW + 2 * R;                        // K/V ring columns in use (<= TKP)
+    static constexpr int HC = KVC + 2;                             // warped-hr ring columns
+    static constexpr int KVR = NKR + 4;                            // K/V ring rows
+    static constexpr int NK = NKR * TKP;                           // S columns
+    static constexpr int NITEM = 4 * HC + 4 * TLC;                 // gather positions of a step
+    static constexpr int NJ = (NITEM + TNQW - 1) / TNQW;
+    static constexpr int PMAX = NJ * TNQW;                         // padded with no-op records
+    static constexpr int KVC1 = (KVC + 1) / 2;                     // columns of the first K / V warp
+    static constexpr uint32_t COL_O = NK, COL_SUM = NK + 64, COL_A = NK + 80, COL_L = NK + 112;
+    static constexpr size_t KV_BYTES = (size_t)KVR * TROWB;
+    static constexpr size_t Q_BYTES = 128 * 128;
+    static constexpr size_t W_BYTES = TNCLS * 128;
+    static constexpr size_t ONES_BYTES = 2048;
+    static constexpr size_t HR_BYTES = (size_t)THRR * HC * 128;
+    static constexpr size_t LR_BYTES = (size_t)TLRR * TLC * 128;
+    static constexpr size_t SCRATCH_BYTES = 128;
+    static constexpr size_t REC_BYTES = (size_t)2 * PMAX * 32;     // double-buffered {float4 weights, uint4 address}
+    static constexpr size_t SMEM = 1024 + 2 * KV_BYTES + Q_BYTES + W_BYTES + ONES_BYTES + HR_BYTES + LR_BYTES + SCRATCH_BYTES + REC_BYTES +
+                                   TNCLS * 4 + 9 * TNB * 8 + 16;
+    static_assert(KVC <= TKP, "window too wide for the key pitch");
+    static_assert(NKR % 2 == 0 && KVR % 2 == 0 && PADR % 2 == 0, "even row counts: a 16-key MMA step never straddles the ring end");
+    static_assert(COL_L + TNCLS <= 512, "tensor memory columns");
+    static_assert(PMAX <= TG_THREADS, "one gather record per G thread");
+    static_assert(SMEM <= 232448, "shared memory budget");
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count));
+}
+// hand-off barriers are indexed by a step counter >= 0: slot idx & 3, phase parity (idx / 4) & 1
+__device__ __forceinline__ void tbar_arrive(uint64_t* bars, int idx) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0)
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(bars + (idx & (TNB - 1)))) : "memory");
+}
+__device__ __forceinline__ bool tbar_test(uint64_t* bars, int idx) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(s_u32(bars + (idx & (TNB - 1)))), "r"((uint32_t)((idx / TNB) & 1)) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void tbar_wait(uint64_t* bars, int idx, int tag = 0) {
+    const uint32_t addr = s_u32(bars + (idx & (TNB - 1)));
+    const uint32_t parity = (uint32_t)((idx / TNB) & 1);
+    uint32_t ok;
+    // bounded: a protocol bug must trap, not hang the GPU box
+#pragma unroll 1
+    for (int spin = 0; spin < (1 << 20); ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(addr), "r"(parity), "r"(100000u) : "memory");
+        if (ok) return;
+    }
+    if ((threadIdx.x & 31) == 0)
+        printf("arseg creff_tc: mbarrier wait timed out (block %d warp %d barrier %d index %d)\n", (int)blockIdx.x, (int)(threadIdx.x >> 5), tag, idx);
+    __trap();
+}
+__device__ __forceinline__ void t_commit(uint64_t* bars, int idx) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bars + (idx & (TNB - 1)))) : "memory");
+}
+__device__ __forceinline__ void t_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void t_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void t_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// SWIZZLE_128B shared-memory matrix descriptor, SBO = 1024 (8 rows of 128 bytes), version 1 (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t t_desc(uint32_t addr) {
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A / B f16, b_major @16 (1 = MN-major), N >> 3 @17, M >> 4 @24
+__host__ __device__ constexpr uint32_t t_idesc(int N, int b_mn) {
+    return (1u << 4) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void t_mma_ss(uint64_t da, uint64_t db, uint32_t td, uint32_t acc, uint32_t idesc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(td), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void t_mma_ts(uint32_t ta, uint64_t db, uint32_t td, uint32_t acc, uint32_t idesc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(td), "r"(ta), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void t_ld32(uint32_t ta, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(ta));
+}
+__device__ __forceinline__ void t_ld16(uint32_t ta, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(ta));
+}
+__device__ __forceinline__ void t_ld8(uint32_t ta, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(ta));
+}
+__device__ __forceinline__ void t_ld1(uint32_t ta, uint32_t& r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(ta));
+}
+__device__ __forceinline__ void t_st16(uint32_t ta, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(ta), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void t_st8(uint32_t ta, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(ta), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void t_st4(uint32_t ta, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ta), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void t_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void t_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float t_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float t_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ uint32_t t_lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint4 t_lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void t_sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void t_sts128(uint32_t a, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ float2 t_h2f(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
+__device__ __forceinline__ uint4 t_ldg128(const char* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+struct TSmem {
+    uint32_t sK, sV, sQ, sW, sOnes, rings;       // shared-window addresses; rings = hr ring, lr ring, scratch
+    float4* posw;                                // [2][PMAX]
+    uint4* posa;                                 // [2][PMAX]
+    float* s_bc;                                 // [TNCLS]
+    uint64_t *gfull /* index g + 1 */, *ddone, *lrfree, *sfull, *pfull, *ofull, *afull, *lfull;
+};
+
+// ---------------------------------------------------------------------------------------------
+// G role: gather.  Step g (g = -1 .. NH-1) fills warped-hr ring rows [h0, h0+nh) and lr_up ring rows [l0, l0+nl).
+// hr row r <-> image row ya - R - PADR - 1 + r (column c <-> x0 - R - 1 + c); lr row r <-> image row ya - 1 + r
+// (column c <-> x0 - 1 + c).
+// ---------------------------------------------------------------------------------------------
+template <int K>
+__device__ __forceinline__ void t_step_geom(int g, int& h0, int& nh, int& l0, int& nl) {
+    using Cf = TCfg<K>;
+    if (g < 0) { h0 = 0; nh = 2; l0 = 0; nl = 0; return; }
+    h0 = 4 * g + 2; nh = 4;
+    if (g >= Cf::HP) { l0 = 4 * (g - Cf::HP) + 2; nl = 4; }
+    else if (g == Cf::HP - 1) { l0 = 0; nl = 2; }
+    else { l0 = 0; nl = 0; }
+}
+
+template <int K, bool MVF>
+__device__ __forceinline__ void t_g_role(const CreffMmaParams& p, const TSmem& sm, int n, int x0, int ya, int NH, int S) {
+    using Cf = TCfg<K>;
+    const int gt = threadIdx.x - 32 * TG_W0, lane = gt & 31, qw = gt >> 3, l8 = lane & 7;
+    const float lsh = resize_scale(p.h, p.H, ARSEG_RESIZE_BILINEAR_AC), lsw = resize_scale(p.w, p.W, ARSEG_RESIZE_BILINEAR_AC);
+    const char* const hrb = reinterpret_cast<const char*>(p.hr) + (p.hr_shared ? (size_t)0 : (size_t)n * p.H * p.W * 128);
+    const char* const lrb = reinterpret_cast<const char*>(p.lr) + (size_t)n * p.h * p.w * 128;
+    const double rcp_w = 2.0 / (double)max(p.W - 1, 1), rcp_h = 2.0 / (double)max(p.H - 1, 1);
+    const uint32_t hr_rs = (uint32_t)p.W * 128, lr_rs = (uint32_t)p.w * 128;
+    constexpr uint32_t SCRATCH_OFF = (uint32_t)(Cf::HR_BYTES + Cf::LR_BYTES);
+    const int* const mvp = reinterpret_cast<const int*>(p.flow) + (size_t)n * p.H * p.W;
+
+    // the int16 MV pair of this thread's hr position of step g (loaded one step ahead of its record)
+    auto mv_of = [&](int g) -> int {
+        int h0, nh, l0, nl;
+        t_step_geom<K>(g, h0, nh, l0, nl);
+        if (!MVF || gt >= nh * Cf::HC) return 0;
+        const int rr = gt / Cf::HC, cc = gt - rr * Cf::HC;
+        const int fy = ya - Cf::R - Cf::PADR - 1 + h0 + rr, fx = x0 - Cf::R - 1 + cc;
+        return (fy >= 0 && fy < p.H && fx >= 0 && fx < p.W) ? __ldg(mvp + (size_t)fy * p.W + fx) : 0;
+    };
+    // gather record q of step g (one per G thread): posw = the 2x2 block's weights; posa = {block address (64 bit), row
+    // stride, ring byte offset of the destination position | (column & 7) << 28 for the lr ring's chunk swizzle}.
+    // Padded with no-op records (zero weights, scratch destination) to NJ positions per quarter-warp.
+    auto compute_pos = [&](int g, int mv) {
+        int h0, nh, l0, nl;
+        t_step_geom<K>(g, h0, nh, l0, nl);
+        const int nhp = nh * Cf::HC, npos = nhp + nl * TLC;
+        const int q = gt;
+        if (q >= Cf::PMAX) return;
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+        const char* src = hrb;
+        uint32_t rs = hr_rs, dst = SCRATCH_OFF;
+        if (q < nhp) {
+            const int rr = q / Cf::HC, cc = q - rr * Cf::HC, row = h0 + rr;
+            const int fy = ya - Cf::R - Cf::PADR - 1 + row, fx = x0 - Cf::R - 1 + cc;
+            const PosRec r = pos_hr(p, n, fy, fx, rcp_w, rcp_h, MVF ? &mv : nullptr);
+            dst = (uint32_t)(((row % THRR) * Cf::HC + cc) * 128);
+            if (r.info >= 0) {
+                int bx, by;
+                rec_block_of(r, p.W, p.H, w, bx, by);
+                src = hrb + ((size_t)by * p.W + bx) * 128;
+            }
+        } else if (q < npos) {
+            const int q2 = q - nhp, rr = q2 / TLC, cc = q2 - rr * TLC, row = l0 + rr;
+            const PosRec r = pos_lr(p, lsh, lsw, ya - 1 + row, x0 - 1 + cc);
+            dst = (uint32_t)(Cf::HR_BYTES + ((row % TLRR) * TLC + cc) * 128) | ((uint32_t)(cc & 7) << 28);
+            if (r.info >= 0) {
+                int bx, by;
+                rec_block_of(r, p.w, p.h, w, bx, by);
+                src = lrb + ((size_t)by * p.w + bx) * 128;
+                rs = lr_rs;
+            }
+        }
+        const int buf = (g + 1) & 1;
+        sm.posw[buf * Cf::PMAX + q] = w;
+        const unsigned long long a = reinterpret_cast<unsigned long long>(src);
+        sm.posa[buf * Cf::PMAX + q] = make_uint4((uint32_t)a, (uint32_t)(a >> 32), rs, dst);
+    };
+    uint4 tap[TJA][4];
+    auto issue = [&](uint4 (&tp)[4], int buf, int j) {
+        const uint4 id = sm.posa[buf * Cf::PMAX + qw + TNQW * j];
+        const char* a0 = reinterpret_cast<const char*>(((unsigned long long)id.y << 32) | id.x) + 16 * l8;
+        const char* a1 = a0 + id.z;
+        tp[0] = t_ldg128(a0);
+        tp[1] = t_ldg128(a0 + 128);
+        tp[2] = t_ldg128(a1);
+        tp[3] = t_ldg128(a1 + 128);
+    };
+    auto commit = [&](const uint4 (&tp)[4], int buf, int j) {
+        const int i = buf * Cf::PMAX + qw + TNQW * j;
+        const float4 w = sm.posw[i];
+        const uint32_t d = sm.posa[i].w;
+        const uint32_t* t0 = reinterpret_cast<const uint32_t*>(&tp[0]);
+        const uint32_t* t1 = reinterpret_cast<const uint32_t*>(&tp[1]);
+        const uint32_t* t2 = reinterpret_cast<const uint32_t*>(&tp[2]);
+        const uint32_t* t3 = reinterpret_cast<const uint32_t*>(&tp[3]);
+        uint32_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 a = t_h2f(t0[e]), b = t_h2f(t1[e]), c = t_h2f(t2[e]), dd = t_h2f(t3[e]);
+            const float vx = a.x * w.x + b.x * w.y + c.x * w.z + dd.x * w.w;
+            const float vy = a.y * w.x + b.y * w.y + c.y * w.z + dd.y * w.w;
+            o[e] = pack_h2_sat(vx, vy);
+        }
+        t_sts128(sm.rings + (d & 0x0fffffffu) + (((uint32_t)l8 ^ (d >> 28)) << 4), make_uint4(o[0], o[1], o[2], o[3]));
+    };
+
+    compute_pos(-1, mv_of(-1));
+    nbar_sync(TBAR_G, TG_THREADS);
+#pragma unroll 1
+    for (int g = -1; g < NH; ++g) {
+        const int buf = (g + 1) & 1;
+        // rolling pipeline: TJA positions' loads are always in flight while the oldest one is combined and stored
+#pragma unroll
+        for (int j = 0; j < TJA; ++j) issue(tap[j], buf, j);
+        const int mv_next = g + 1 < NH ? mv_of(g + 1) : 0;          // in flight during the gather loop
+        if (g >= 2) tbar_wait(sm.ddone, g - 2, 2);                     // D half-step g-2 done: the hr / lr rows this step overwrites are read
+        {
+            // lr_up rows double as the residual: C takes the rows of tile i at the start of its step
+            const int num = 4 * (g - Cf::HP) + 5 - TLRR - 1;        // last overwritten lr row - 1
+            if (num >= 0) { const int im = num >> 3; tbar_wait(sm.lrfree, im < S - 1 ? im : S - 1, 3); }
+        }
+#pragma unroll 1
+        for (int j0 = 0; j0 < Cf::NJ; j0 += TJA) {
+#pragma unroll
+            for (int j = 0; j < TJA; ++j) {
+                if (j0 + j < Cf::NJ) {
+                    commit(tap[j], buf, j0 + j);
+                    if (j0 + j + TJA < Cf::NJ) issue(tap[j], buf, j0 + j + TJA);
+                }
+            }
+        }
+        tbar_arrive(sm.gfull, g + 1);
+        if (g + 1 < NH) compute_pos(g + 1, mv_next);
+        nbar_sync(TBAR_G, TG_THREADS);                              // records of step g+1 visible; everyone is done with those of step g-1
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// D role: depthwise 3x3 convolutions, four output rows per pass with an x-marching 6-row x 3-column register window.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 t_dw9(const float2 (&w)[10], const float2 (&r0)[3], const float2 (&r1)[3], const float2 (&r2)[3], int sa, int sb, int sc) {
+    float2 a0 = __ffma2_rn(w[0], r0[sa], w[9]), a1 = __fmul2_rn(w[3], r1[sa]), a2 = __fmul2_rn(w[6], r2[sa]);
+    a0 = __ffma2_rn(w[1], r0[sb], a0); a1 = __ffma2_rn(w[4], r1[sb], a1); a2 = __ffma2_rn(w[7], r2[sb], a2);
+    a0 = __ffma2_rn(w[2], r0[sc], a0); a1 = __ffma2_rn(w[5], r1[sc], a1); a2 = __ffma2_rn(w[8], r2[sc], a2);
+    return __fadd2_rn(__fadd2_rn(a0, a1), a2);
+}
+
+// jmax: the last tile whose K/V rows are overwritten by half-step h (K/V row kr lives in ring slot kr % KVR)
+template <int K>
+__device__ __forceinline__ int t_kv_last_reader(int h) {
+    using Cf = TCfg<K>;
+    const int num = 4 * h + 3 - Cf::KVR - Cf::PADR;
+    return num >= 0 ? (num >> 3) : -1;
+}
+
+template <int K>
+__device__ __forceinline__ void t_d_role(const CreffMmaParams& p, const TSmem& sm, int x0, int ya, int NH, int S) {
+    using Cf = TCfg<K>;
+    const int lane = threadIdx.x & 31, d = (threadIdx.x >> 5) - TD_W0;
+    const uint32_t lane_sub = (uint32_t)((lane & 3) * 4), lane_chunk = (uint32_t)(lane >> 2);
+    if (d < 4) {
+        // ---------------- K (d = 0, 1) or V (d = 2, 3): columns [c_lo, c_lo + ncol) of four K/V rows per half-step ----------------
+        const int isv = d >> 1, half = d & 1;
+        const int c_lo = half ? Cf::KVC1 : 0, ncol = half ? Cf::KVC - Cf::KVC1 : Cf::KVC1;
+        float2 w[10];
+        {
+            const float* wp = isv ? p.wv : p.wk;
+            const float* bp = isv ? p.bv : p.bk;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) w[i] = make_float2(__ldg(wp + (2 * lane) * 9 + i), __ldg(wp + (2 * lane + 1) * 9 + i));
+            w[9] = make_float2(__ldg(bp + 2 * lane), __ldg(bp + 2 * lane + 1));
+        }
+        const uint32_t ring = isv ? sm.sV : sm.sK;
+        const uint32_t hbase = sm.rings + (uint32_t)(c_lo * 128 + lane * 4);
+#pragma unroll 1
+        for (int h = 0; h < NH; ++h) {
+            tbar_wait(sm.gfull, h + 1, 1);
+            {
+                const int jm = t_kv_last_reader<K>(h);
+                if (jm >= 0) tbar_wait(sm.ofull, jm < S - 1 ? jm : S - 1, 4);     // P V of the last tile that read these ring slots has retired
+            }
+            uint32_t ra[6], ko[4];
+            bool rok[4];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) ra[i] = hbase + (uint32_t)(((4 * h + i) % THRR) * (Cf::HC * 128));
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int kr = 4 * h + r, fy = ya - Cf::R - Cf::PADR + kr;
+                ko[r] = ring + (uint32_t)((kr % Cf::KVR) * TROWB) + lane_sub;
+                rok[r] = fy >= 0 && fy < p.H;                                  // K / V are exactly 0 outside the image (attention zero padding)
+            }
+            float2 win[6][3];
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int i = 0; i < 6; ++i) win[i][c] = t_h2f(t_lds32(ra[i] + c * 128));
+#pragma unroll
+            for (int x = 0; x < Cf::KVC1; ++x) {
+                if (x < ncol) {
+                    const int sa = x % 3, sb = (x + 1) % 3, sc = (x + 2) % 3;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) win[i][sc] = t_h2f(t_lds32(ra[i] + (x + 2) * 128));
+                    const int col = c_lo + x, fx = x0 - Cf::R + col;
+                    const bool okx = fx >= 0 && fx < p.W;
+                    const uint32_t co = (uint32_t)(col * 128) + ((lane_chunk ^ (uint32_t)(col & 7)) << 4);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const float2 v = t_dw9(w, win[r], win[r + 1], win[r + 2], sa, sb, sc);
+                        t_sts32(ko[r] + co, (okx && rok[r]) ? pack_h2_sat(v.x, v.y) : 0u);
+                    }
+                }
+            }
+            t_fence_async_smem();                                              // generic-proxy writes -> visible to the UMMA reads
+            tbar_arrive(sm.ddone, h);
+        }
+    } else {
+        // ---------------- Q: four query rows per half-step (h >= HP) into the A tile ----------------
+        float2 w[10];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) w[i] = make_float2(__ldg(p.wq + (2 * lane) * 9 + i), __ldg(p.wq + (2 * lane + 1) * 9 + i));
+        w[9] = make_float2(__ldg(p.bq + 2 * lane), __ldg(p.bq + 2 * lane + 1));
+        uint32_t lx[8];     // byte offset of this lane's channel pair inside a 128-byte position whose column & 7 = c (chunk swizzle)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) lx[c] = ((lane_chunk ^ (uint32_t)c) << 4) + lane_sub;
+        const uint32_t lbase = sm.rings + (uint32_t)Cf::HR_BYTES;
+#pragma unroll 1
+        for (int h = 0; h < NH; ++h) {
+            tbar_wait(sm.gfull, h + 1, 1);
+            if (h >= Cf::HP) {
+                const int q0 = 4 * (h - Cf::HP), ti = q0 >> 3, qy0 = q0 & 7;
+                if (ti >= 1) tbar_wait(sm.sfull, ti - 1, 5);                      // S = Q K^T of the previous tile has retired: the A tile is free
+                uint32_t ra[6];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) ra[i] = lbase + (uint32_t)(((q0 + i) % TLRR) * (TLC * 128));
+                const uint32_t qo = sm.sQ + (uint32_t)(qy0 * TSW * 128);
+                float2 win[6][3];
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) win[i][c] = t_h2f(t_lds32(ra[i] + c * 128 + lx[c & 7]));
+#pragma unroll
+                for (int x = 0; x < TSW; ++x) {
+                    const int sa = x % 3, sb = (x + 1) % 3, sc = (x + 2) % 3;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) win[i][sc] = t_h2f(t_lds32(ra[i] + (x + 2) * 128 + lx[(x + 2) & 7]));
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const float2 v = t_dw9(w, win[r], win[r + 1], win[r + 2], sa, sb, sc);
+                        t_sts32(qo + (uint32_t)((r * TSW + x) * 128) + lx[x & 7], pack_h2_sat(v.x, v.y));
+                    }
+                }
+            }
+            t_fence_async_smem();
+            tbar_arrive(sm.ddone, h);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// M role: the MMA-issuing thread.
+// ---------------------------------------------------------------------------------------------
+template <int K>
+__device__ __forceinline__ void t_issue_qk(const TSmem& sm, uint32_t tmem, int i) {
+    using Cf = TCfg<K>;
+    // key rows [8i + PADR, + NKR) of the ring in chunks of <= 8 rows that do not cross the ring end (N = 24 * rows <= 192)
+    const int b0 = (8 * i + Cf::PADR) % Cf::KVR;
+    int done = 0;
+#pragma unroll 1
+    while (done < Cf::NKR) {
+        const int rs = (b0 + done) % Cf::KVR;
+        int nr = Cf::NKR - done;
+        if (nr > 8) nr = 8;
+        if (rs + nr > Cf::KVR) nr = Cf::KVR - rs;
+        const uint32_t id = t_idesc(nr * TKP, 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            t_mma_ss(t_desc(sm.sQ + k * 32), t_desc(sm.sK + rs * TROWB + k * 32), tmem + (uint32_t)(done * TKP), k != 0, id);
+        done += nr;
+    }
+}
+template <int K>
+__device__ __forceinline__ void t_issue_pv(const TSmem& sm, uint32_t tmem, int i) {
+    using Cf = TCfg<K>;
+    const int b0 = (8 * i + Cf::PADR) % Cf::KVR;
+    constexpr uint32_t IDV = t_idesc(64, 1), IDS = t_idesc(16, 0);
+    const uint64_t ones = t_desc(sm.sOnes);
+    // 16 keys (2 KB of ring) per MMA: P columns [8 ks, 8 ks + 8) x V rows; the row sums come from the same A against ones
+#pragma unroll 1
+    for (int ks = 0; ks < Cf::NK / 16; ++ks) {
+        const int kk = ks * 16, row = kk / TKP;
+        const uint32_t addr = sm.sV + (uint32_t)(((b0 + row) % Cf::KVR) * TROWB + (kk - row * TKP) * 128);
+        t_mma_ts(tmem + (uint32_t)(ks * 8), t_desc(addr), tmem + Cf::COL_O, ks != 0, IDV);
+        t_mma_ts(tmem + (uint32_t)(ks * 8), ones, tmem + Cf::COL_SUM, ks != 0, IDS);
+    }
+}
+template <int K, int NCP>
+__device__ __forceinline__ void t_issue_cls(const TSmem& sm, uint32_t tmem) {
+    using Cf = TCfg<K>;
+    constexpr uint32_t ID = t_idesc(NCP, 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) t_mma_ts(tmem + Cf::COL_A + (uint32_t)(k * 8), t_desc(sm.sW + k * 32), tmem + Cf::COL_L, k != 0, ID);
+}
+
+template <int K, int NCP>
+__device__ __forceinline__ void t_m_role(const TSmem& sm, uint32_t tmem, int S) {
+    using Cf = TCfg<K>;
+    if ((threadIdx.x & 31) != 0) return;
+    bool qk_ahead = false;          // S of the next tile already issued
+#pragma unroll 1
+    for (int i = 0; i < S; ++i) {
+        if (!qk_ahead) {
+            tbar_wait(sm.ddone, 2 * i + Cf::HP + 1, 6);           // K/V rows and Q of tile i are in shared memory
+            t_fence_after();
+            t_issue_qk<K>(sm, tmem, i);
+            t_commit(sm.sfull, i);
+        }
+        qk_ahead = false;
+        tbar_wait(sm.pfull, i, 7);                                   // P is in tensor memory
+        t_fence_after();
+        t_issue_pv<K>(sm, tmem, i);
+        t_commit(sm.ofull, i);
+        if (NCP > 0) {
+            tbar_wait(sm.afull, i, 8);                               // residual + O / sum is back in tensor memory (f16)
+            t_fence_after();
+            t_issue_cls<K, NCP>(sm, tmem);
+            t_commit(sm.lfull, i);
+        }
+        // the S columns are free once P V has been issued (the tensor pipe runs in order): start the next tile's S early
+        if (i + 1 < S && tbar_test(sm.ddone, 2 * (i + 1) + Cf::HP + 1)) {
+            t_fence_after();
+            t_issue_qk<K>(sm, tmem, i + 1);
+            t_commit(sm.sfull, i + 1);
+            qk_ahead = true;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// C role: softmax, residual, classifier epilogue.  Warp w owns TMEM lanes 32w .. 32w+31 = query rows 2w, 2w+1.
+// ---------------------------------------------------------------------------------------------
+template <int K, int NCP>
+__device__ __forceinline__ void t_c_role(const CreffMmaParams& p, const TSmem& sm, uint32_t tmem, int n, int x0, int ya, int yb, int S) {
+    using Cf = TCfg<K>;
+    constexpr float LOG2E = 1.4426950408889634f;
+    const int lane = threadIdx.x & 31, cw = threadIdx.x >> 5;
+    const int b = lane >> 4, qx = lane & 15, qy = 2 * cw + b;
+    const uint32_t tq = tmem + ((uint32_t)(32 * cw) << 16);
+    const int W = p.W;
+    const size_t plane = (size_t)p.H * W;
+    const int px = x0 + qx;
+    float* const ol = p.out_logits ? p.out_logits + (size_t)n * p.ncls * plane : nullptr;
+    float* const op = p.out_p ? p.out_p + (size_t)n * MC * plane : nullptr;
+    uint8_t* const oa = p.out_argmax ? p.out_argmax + (size_t)n * plane : nullptr;
+    // column mask of this lane's window: key column c is inside iff qx <= c < qx + K
+    float cb[Cf::KVC];
+#pragma unroll
+    for (int c = 0; c < Cf::KVC; ++c) cb[c] = ((unsigned)(c - qx) < (unsigned)K) ? 0.f : -INFINITY;
+    // the warp reads key rows 2cw .. 2cw + K of the tile; the first is outside the window of its odd query row, the last outside that of the even one
+    const float rb_first = b ? -INFINITY : 0.f, rb_last = b ? 0.f : -INFINITY;
+    const uint32_t res_col = (uint32_t)((1 + qx) * 128), res_sw = (uint32_t)((1 + qx) & 7);
+    const uint32_t lbase = sm.rings + (uint32_t)Cf::HR_BYTES;
+
+#pragma unroll 1
+    for (int i = 0; i < S; ++i) {
+        // ---------------- residual lr_up (model/attention.py:191,210): lr ring row 8i + 1 + qy, column 1 + qx ----------------
+        // (a parity wait may only name a phase the barrier has already entered: every role's FIRST wait on a hand-off uses an
+        // index < TNB and later ones advance by < TNB, so "tile ready" = ddone(2i + HP + 1) is used here, not gfull(2i + HP + 2))
+        tbar_wait(sm.ddone, 2 * i + Cf::HP + 1, 1);
+        uint4 res[8];
+        {
+            const uint32_t ra = lbase + (uint32_t)(((8 * i + 1 + qy) % TLRR) * (TLC * 128)) + res_col;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) res[c] = t_lds128(ra + (((uint32_t)c ^ res_sw) << 4));
+        }
+        tbar_arrive(sm.lrfree, i);
+        // ---------------- softmax over the k x k window (model/attention.py:203) ----------------
+        tbar_wait(sm.sfull, i, 9);
+        t_fence_after();
+        const uint32_t srow = tq + (uint32_t)(2 * cw * TKP);        // S columns of the warp's first key row
+        float m = -INFINITY;
+#pragma unroll
+        for (int j = 0; j <= K; ++j) {
+            uint32_t s[24];
+            t_ld16(srow + j * TKP, s);
+            t_ld8(srow + j * TKP + 16, s + 16);
+            t_ld_wait();
+            const float rb = j == 0 ? rb_first : (j == K ? rb_last : 0.f);
+#pragma unroll
+            for (int c = 0; c < Cf::KVC; ++c) {
+                float v = __uint_as_float(s[c]) + cb[c];
+                if (j == 0 || j == K) v += rb;
+                m = fmaxf(m, v);
+            }
+        }
+        const float ml = m * LOG2E;
+        const uint32_t prow = tq + (uint32_t)(2 * cw * (TKP / 2));  // P columns of the warp's first key row
+#pragma unroll
+        for (int j = 0; j <= K; ++j) {
+            uint32_t s[24];
+            t_ld16(srow + j * TKP, s);
+            t_ld8(srow + j * TKP + 16, s + 16);
+            t_ld_wait();
+            const float rb = (j == 0 ? rb_first : (j == K ? rb_last : 0.f)) - ml;
+            uint32_t pk[12];
+#pragma unroll
+            for (int c = 0; c < 24; c += 2) {
+                if (c < Cf::KVC) {
+                    const float e0 = t_ex2(fmaf(__uint_as_float(s[c]), LOG2E, cb[c] + rb));
+                    const float e1 = c + 1 < Cf::KVC ? t_ex2(fmaf(__uint_as_float(s[c + 1]), LOG2E, cb[c + 1] + rb)) : 0.f;
+                    pk[c >> 1] = pack_h2(e0, e1);
+                } else {
+                    pk[c >> 1] = 0u;
+                }
+            }
+            t_st8(prow + j * (TKP / 2), pk);
+            t_st4(prow + j * (TKP / 2) + 8, pk[8], pk[9], pk[10], pk[11]);
+        }
+        // P of the key rows outside the warp's range is zero (written after the S reads: the P columns alias S)
+#pragma unroll 1
+        for (int r = 0; r < Cf::NKR; ++r) {
+            if (r < 2 * cw || r > 2 * cw + K) {
+                const uint32_t a = tq + (uint32_t)(r * (TKP / 2));
+                t_st4(a, 0u, 0u, 0u, 0u); t_st4(a + 4, 0u, 0u, 0u, 0u); t_st4(a + 8, 0u, 0u, 0u, 0u);
+            }
+        }
+        t_st_wait();
+        t_fence_before();
+        tbar_arrive(sm.pfull, i);
+        // ---------------- fused = lr_up + O / sum (model/attention.py:207,210) ----------------
+        tbar_wait(sm.ofull, i, 10);
+        t_fence_after();
+        const int py = ya + 8 * i + qy;
+        const bool ok = py < yb && px < W;
+        const size_t off = (size_t)py * W + px;
+        uint32_t su;
+        t_ld1(tq + Cf::COL_SUM, su);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            uint32_t o[32];
+            t_ld32(tq + Cf::COL_O + 32 * hf, o);
+            t_ld_wait();
+            const float inv = t_rcp(__uint_as_float(su));
+            uint32_t pk[16];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint32_t* rr = reinterpret_cast<const uint32_t*>(&res[4 * hf + c]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 r2 = t_h2f(rr[e]);
+                    const int ch = 8 * c + 2 * e;                              // channel 32 hf + ch
+                    const float f0 = fmaf(__uint_as_float(o[ch]), inv, r2.x), f1 = fmaf(__uint_as_float(o[ch + 1]), inv, r2.y);
+                    if (op && ok) {
+                        op[(size_t)(32 * hf + ch) * plane + off] = f0;
+                        op[(size_t)(32 * hf + ch + 1) * plane + off] = f1;
+                    }
+                    pk[4 * c + e] = pack_h2_sat(f0, f1);
+                }
+            }
+            if (NCP > 0) t_st16(tq + Cf::COL_A + 16 * hf, pk);
+        }
+        if (NCP == 0) continue;
+        t_st_wait();
+        t_fence_before();
+        tbar_arrive(sm.afull, i);
+        // ---------------- classifier (model/pspnet.py:226), log-softmax (:229), argmax (evaluation.py:204) ----------------
+        tbar_wait(sm.lfull, i, 11);
+        t_fence_after();
+        constexpr int NCPA = NCP > 0 ? NCP : 16;
+        uint32_t lg[NCPA];
+        t_ld16(tq + Cf::COL_L, lg);
+        if (NCPA > 16) t_ld16(tq + Cf::COL_L + 16, lg + (NCPA > 16 ? 16 : 0));
+        t_ld_wait();
+        float lmax = -INFINITY;
+        int am = 0;
+#pragma unroll
+        for (int j = 0; j < NCPA; ++j) {
+            float v = __uint_as_float(lg[j]) + sm.s_bc[j];
+            v = j < p.ncls ? v : -INFINITY;                                    // padding classes
+            lg[j] = __float_as_uint(v);
+            if (v > lmax) { lmax = v; am = j; }                                // first maximum, like torch.argmax
+        }
+        float lse = 0.f;
+        if (p.log_softmax) {
+            const float q0 = lmax * LOG2E;
+#pragma unroll
+            for (int j = 0; j < NCPA; ++j) lse += t_ex2(fmaf(__uint_as_float(lg[j]), LOG2E, -q0));
+            lse = __logf(lse) + lmax;
+        }
+        if (ok) {
+            if (ol) {
+#pragma unroll
+                for (int j = 0; j < NCPA; ++j)
+                    if (j < p.ncls) ol[(size_t)j * plane + off] = __uint_as_float(lg[j]) - lse;
+            }
+            if (oa) oa[off] = (uint8_t)am;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------
+template <int K, int NCP, bool MVF>
+__global__ void __launch_bounds__(TTHREADS, 1) creff_tc_kernel(CreffMmaParams p) {
+    using Cf = TCfg<K>;
+    extern __shared__ __align__(1024) uint8_t tsm_raw[];
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tsm_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* pK = base;
+    uint8_t* pV = pK + Cf::KV_BYTES;
+    uint8_t* pQ = pV + Cf::KV_BYTES;
+    uint8_t* pW = pQ + Cf::Q_BYTES;
+    uint8_t* pOnes = pW + Cf::W_BYTES;
+    uint8_t* pRings = pOnes + Cf::ONES_BYTES;
+    uint8_t* pRec = pRings + Cf::HR_BYTES + Cf::LR_BYTES + Cf::SCRATCH_BYTES;
+    TSmem sm;
+    sm.sK = s_u32(pK); sm.sV = s_u32(pV); sm.sQ = s_u32(pQ); sm.sW = s_u32(pW); sm.sOnes = s_u32(pOnes); sm.rings = s_u32(pRings);
+    sm.posw = reinterpret_cast<float4*>(pRec);
+    sm.posa = reinterpret_cast<uint4*>(pRec + (size_t)2 * Cf::PMAX * 16);
+    sm.s_bc = reinterpret_cast<float*>(pRec + Cf::REC_BYTES);
+    sm.gfull = reinterpret_cast<uint64_t*>(sm.s_bc + TNCLS);
+    sm.ddone = sm.gfull + TNB; sm.lrfree = sm.ddone + TNB; sm.sfull = sm.lrfree + TNB; sm.pfull = sm.sfull + TNB;
+    sm.ofull = sm.pfull + TNB; sm.afull = sm.ofull + TNB; sm.lfull = sm.afull + TNB;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm.lfull + TNB);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    // frame index fastest: the N frames of a GOP visit the same keyframe rows back to back (L2 reuse)
+    int bi = blockIdx.x;
+    const int n = bi % p.N; bi /= p.N;
+    const int x0 = (bi % p.ncols) * TSW;
+    const int ya = (bi / p.ncols) * p.seg_rows;
+    const int yb = min(ya + p.seg_rows, p.H);
+    const int S = (yb - ya + 7) >> 3;             // tiles
+    const int NH = 2 * S + Cf::HP;                // D half-steps (G steps -1 .. NH-1)
+
+    if (tid == 0) {
+        for (int i = 0; i < TNB; ++i) {
+            tbar_init(sm.gfull + i, TG_WARPS); tbar_init(sm.ddone + i, TD_WARPS); tbar_init(sm.lrfree + i, TC_WARPS);
+            tbar_init(sm.sfull + i, 1); tbar_init(sm.pfull + i, TC_WARPS); tbar_init(sm.ofull + i, 1);
+            tbar_init(sm.afull + i, TC_WARPS); tbar_init(sm.lfull + i, 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == TM_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // K / V rings start as zeros: the pad columns (KVC .. TKP-1) are never written and must stay finite (P = 0 there)
+    for (int i = tid; i < (int)(2 * Cf::KV_BYTES / 16); i += TTHREADS) reinterpret_cast<uint4*>(pK)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < (int)(Cf::ONES_BYTES / 4); i += TTHREADS) reinterpret_cast<uint32_t*>(pOnes)[i] = 0x3C003C00u;   // f16 ones
+    // classifier weights [TNCLS][64] f16, K-major SWIZZLE_128B rows (16-byte chunk c of row j at (c ^ (j & 7)) << 4)
+    for (int i = tid; i < TNCLS * MC; i += TTHREADS) {
+        const int j = i / MC, c = i % MC;
+        const float v = (p.wcls && j < p.ncls) ? clamp_h(__ldg(p.wcls + (size_t)j * MC + c)) : 0.f;
+        *reinterpret_cast<__half*>(pW + j * 128 + ((((c >> 3) ^ j) & 7) << 4) + (c & 7) * 2) = __float2half_rn(v);
+    }
+    if (tid < TNCLS) sm.s_bc[tid] = (p.wcls && p.bcls && tid < p.ncls) ? __ldg(p.bcls + tid) : 0.f;
+    t_fence_async_smem();
+    t_fence_before();
+    __syncthreads();
+    t_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    // register file re-balance (warpgroup-aligned): the softmax / epilogue warps take what the producers do not need
+    if (warp < TC_WARPS) asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
+    if (warp < TC_WARPS) t_c_role<K, NCP>(p, sm, tmem, n, x0, ya, yb, S);
+    else if (warp == TM_WARP) t_m_role<K, NCP>(sm, tmem, S);
+    else if (warp < TD_W0) t_g_role<K, MVF>(p, sm, n, x0, ya, NH, S);
+    else t_d_role<K>(p, sm, x0, ya, NH, S);
+
+    t_fence_before();
+    __syncthreads();
+    if (warp == TM_WARP) {
+        t_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+    }
+}
+
+template <int K, int NCP, bool MVF>
+static int creff_tc_launch_n(CreffMmaParams& p, cudaStream_t st) {
+    using Cf = TCfg<K>;
+    auto kern = creff_tc_kernel<K, NCP, MVF>;
+    // per device, written once per process: an idempotent attribute, so the unsynchronised flag is a benign race between
+    // nn.DataParallel worker threads
+    static bool configured[64] = {false};
+    int dev = 0;
+    ARSEG_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        ARSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cf::SMEM));
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    p.ncols = ceil_div(p.W, TSW);
+    // row segments: enough CTAs for >= ~6 waves of one CTA per SM, but segments of >= 48 rows (each segment pays
+    // ~K+5 redundant halo rows and the pipeline fill)
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    int nseg = 1;
+    const char* e = getenv("ARSEG_CREFF_SEG_ROWS");
+    if (e && atoi(e) >= 8) nseg = ceil_div(p.H, (atoi(e) + 7) / 8 * 8);
+    else while ((long long)p.N * p.ncols * nseg < 6LL * sms && ceil_div(p.H, nseg + 1) >= 48) ++nseg;
+    p.seg_rows = (ceil_div(p.H, nseg) + 7) / 8 * 8;
+    p.nseg = ceil_div(p.H, p.seg_rows);
+    const long long blocks = (long long)p.N * p.ncols * p.nseg;
+    ARSEG_REQUIRE(blocks > 0 && blocks < 2147483647LL, "creff_tc: grid too large");
+    kern<<<(unsigned)blocks, TTHREADS, Cf::SMEM, st>>>(p);
+    ARSEG_CHECK_LAUNCH("creff_tc");
+    return ARSEG_OK;
+}
+
+template <int K>
+static int creff_tc_launch_k(CreffMmaParams& p, cudaStream_t st) {
+    const bool mvf = p.flow && p.flow_dtype == ARSEG_I16 && p.Hm == p.H && p.Wm == p.W;
+    if (mvf) {
+        if (!p.wcls) return creff_tc_launch_n<K, 0, true>(p, st);
+        if (p.ncls <= 16) return creff_tc_launch_n<K, 16, true>(p, st);
+        return creff_tc_launch_n<K, 32, true>(p, st);
+    }
+    if (!p.wcls) return creff_tc_launch_n<K, 0, false>(p, st);
+    if (p.ncls <= 16) return creff_tc_launch_n<K, 16, false>(p, st);
+    return creff_tc_launch_n<K, 32, false>(p, st);
+}
+
+// hr and lr are f16 NHWC ([.,H,W,64] / [N,h,w,64]); k in {3, 5, 7}
+int creff_tc_launch(CreffMmaParams& p, int k, cudaStream_t st) {
+    if (p.H < 2 || p.W < 2 || p.h < 2 || p.w < 2) ARSEG_UNSUPPORTED("creff_tc: maps must be at least 2x2 (hr %dx%d, lr %dx%d)", p.H, p.W, p.h, p.w);
+    switch (k) {
+        case 3: return creff_tc_launch_k<3>(p, st);
+        case 5: return creff_tc_launch_k<5>(p, st);
+        case 7: return creff_tc_launch_k<7>(p, st);
+        default: ARSEG_UNSUPPORTED("creff_tc: window k=%d (3, 5, 7)", k);
+    }
+}
+
+}  // namespace arseg

@@ -575,7 +575,7 @@ int creff_wide_launch(const arseg_creff_args* a, void* ws, size_t ws_bytes, cuda
                   "creff_wide: workspace of %zu bytes needed (arseg_creff_workspace_bytes)", creff_wide_workspace_bytes(a->N, a->C, a->H, a->W));
     WideParams q;
     CreffMmaParams& p = q.b;
-    p.hr = a->hr; p.hr_shared = a->hr_shared; p.flow = a->flow; p.flow_dtype = a->flow_dtype; p.Hm = a->Hm; p.Wm = a->Wm;
+    p.hr = reinterpret_cast<const float*>(a->hr); p.hr_shared = a->hr_shared; p.flow = a->flow; p.flow_dtype = a->flow_dtype; p.Hm = a->Hm; p.Wm = a->Wm;
     p.lr = a->lr; p.h = a->h; p.w = a->w;
     p.wq = a->wq; p.bq = a->bq; p.wk = a->wk; p.bk = a->bk; p.wv = a->wv; p.bv = a->bv; p.wcls = a->wcls; p.bcls = a->bcls;
     p.ncls = a->ncls; p.log_softmax = a->log_softmax; p.out_p = a->out_p; p.out_logits = a->out_logits;

@@ -21,6 +21,7 @@ model/pspnet.py:14-46,103-131,198-231; model/bisenet.py:25-113,162-180,207-223,2
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -248,13 +249,17 @@ class Plan:
                       and (wcls is None or wcls.shape[0] <= 32) and min(H, W) >= 2)
             engine = L.CREFF_MMA_F16 if mma_ok else L.CREFF_EXACT_F32
         hr_layout = L.NCHW
+        # C = 64 with an f16 LR feature (the 'f16' plan): the keyframe feature is converted to f16 NHWC as well and the
+        # tcgen05 / TMEM engine runs (csrc/creff_tc.cu, k <= 7); ARSEG_CREFF_TC=0 keeps the mma.sync march engine (A/B runs)
+        tc = (engine == L.CREFF_MMA_F16 and Cc == 64 and k <= 7 and lr_layout == L.NHWC and lr.dtype == torch.float16
+              and os.environ.get("ARSEG_CREFF_TC", "1") != "0")
         if engine == L.CREFF_MMA_F16:
-            hr_nhwc = self.empty((hr.shape[0], H, W, Cc), torch.float32)
+            hr_nhwc = self.empty((hr.shape[0], H, W, Cc), torch.float16 if tc else torch.float32)
             fn_t = self.lib.arseg_nchw_to_nhwc
-            targs = (hr.data_ptr(), hr_nhwc.data_ptr(), L.F32, hr.shape[0], Cc, H, W)
+            targs = (hr.data_ptr(), hr_nhwc.data_ptr(), L.F16 if tc else L.F32, hr.shape[0], Cc, H, W)
             self._add("hr_nchw_to_nhwc", lambda s: fn_t(*targs, s))
             hr, hr_layout = hr_nhwc, L.NHWC
-            name = name + "_mma"
+            name = name + ("_tc" if tc else "_mma")
         if lr_layout == L.NHWC:
             N, h, w, _ = lr.shape
         else:
@@ -279,7 +284,7 @@ class Plan:
                         wc.data_ptr() if wc is not None else None, bc.data_ptr() if bc is not None else None, ncls,
                         int(log_softmax), out_p.data_ptr() if out_p is not None else None,
                         out_l.data_ptr() if out_l is not None else None, out_a.data_ptr() if out_a is not None else None,
-                        N, Cc, H, W, k, None, 0)
+                        N, Cc, H, W, k, None, 0, L.F16 if tc else L.F32)
         need = int(self.lib.arseg_creff_workspace_bytes(C.byref(a)))
         if need:
             wsb = self.empty((need,), torch.uint8)
@@ -448,9 +453,11 @@ def build_psp_phase1(pl: Plan, sd: SD, x_nchw: torch.Tensor, p: str = "", sizes=
         Nn, hh, ww, _ = t.shape
         t = pl.resize(t, 2 * hh, 2 * ww, L.RESIZE_BILINEAR, name=u + "upsample")
         sc, sh = fold_bn(sd, p + u + "conv.1.", sd[p + u + "conv.0.bias"])
-        # up_3 produces the LR feature p: kept fp32 in 16-bit plans (it is the residual of the CReFF kernel)
+        # up_3 produces the LR feature p (the residual of the CReFF kernel): f16 in the 'f16' plan (11-bit significand, the
+        # tcgen05 CReFF engine's operand type), fp32 in the 'bf16' plan
         t = pl.conv(t, sd[p + u + "conv.0.weight"], sc, sh, pad=1, act=L.ACT_PRELU,
-                    slope=float(sd[p + u + "conv.2.weight"].reshape(-1)[0]), name=u + "conv", out_f32=(u == "up_3."))
+                    slope=float(sd[p + u + "conv.2.weight"].reshape(-1)[0]), name=u + "conv",
+                    out_f32=(u == "up_3." and pl.precision != "f16"))
     cls = None
     if aux:                                                         # model/pspnet.py:215-217
         a = pl.gmaxpool(x3)

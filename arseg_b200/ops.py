@@ -219,7 +219,8 @@ def creff_fused(hr, lr, wq, bq, wk, bk, wv, bv, k, flow=None, flow_hw=None, wcls
                 engine=L.CREFF_EXACT_F32, hr_layout=L.NCHW):
     """Fused (MV warp +) CReFF (+ classifier).  hr fp32 NCHW [1|N,C,H,W] (or NHWC [1|N,H,W,C] with hr_layout=NHWC);
     lr NCHW fp32 [N,C,h,w] or NHWC [N,h,w,C].  engine: L.CREFF_EXACT_F32 (fp32 SIMT, NCHW hr) or L.CREFF_MMA_F16
-    (tensor-core window attention, TF32-class error, C = 64 m, NHWC hr and lr)."""
+    (tensor-core window attention, TF32-class error, C = 64 m, NHWC hr and lr; C = 64 with fp16 hr AND fp16 lr runs the
+    tcgen05 / TMEM engine, k <= 7)."""
     _chk_cuda("creff_fused", hr, lr, wq, bq, wk, bk, wv, bv, flow, wcls, bcls)
     if hr_layout == L.NHWC:
         Nh, H, W, Cc = hr.shape
@@ -240,7 +241,8 @@ def creff_fused(hr, lr, wq, bq, wk, bk, wv, bv, k, flow=None, flow_hw=None, wcls
     Hm, Wm = (flow.shape[1], flow.shape[2]) if flow is not None else (0, 0)
     a = L.CreffArgs(_p(hr), int(hr_shared), hr_layout, engine, _p(flow), dtype_code(flow.dtype) if flow is not None else 0, Hm, Wm,
                     _p(lr), lr_layout, dtype_code(lr.dtype), h, w, _p(wq), _p(bq), _p(wk), _p(bk), _p(wv), _p(bv),
-                    _p(wcls), _p(bcls), ncls, int(log_softmax), _p(out_p), _p(out_l), _p(out_a), N, Cc, H, W, k, None, 0)
+                    _p(wcls), _p(bcls), ncls, int(log_softmax), _p(out_p), _p(out_l), _p(out_a), N, Cc, H, W, k, None, 0,
+                    dtype_code(hr.dtype))
     with torch.cuda.device(dev):
         lib = L.load()
         need = int(lib.arseg_creff_workspace_bytes(C.byref(a)))

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define ARSEG_ABI_VERSION 4
+#define ARSEG_ABI_VERSION 5
 
 enum { ARSEG_OK = 0, ARSEG_E_BADARG = -1, ARSEG_E_UNSUPPORTED = -2, ARSEG_E_CUDA = -3 };
 enum { ARSEG_F32 = 0, ARSEG_BF16 = 1, ARSEG_F64 = 2, ARSEG_I16 = 3, ARSEG_F16 = 4 };
@@ -34,8 +34,8 @@ enum { ARSEG_RESIZE_BILINEAR = 0, ARSEG_RESIZE_BILINEAR_AC = 1, ARSEG_RESIZE_NEA
 enum { ARSEG_NCHW = 0, ARSEG_NHWC = 1 };
 /* convolution engines: SIMT fp32 (exact-order fp32 FMA), tcgen05 kind::tf32, tcgen05 kind::f16 (bf16) */
 enum { ARSEG_CONV_SIMT_F32 = 1, ARSEG_CONV_TC_TF32 = 2, ARSEG_CONV_TC_BF16 = 3, ARSEG_CONV_TC_F16 = 4 };
-/* CReFF engines: exact fp32 SIMT (any C, NCHW hr), or tensor-core window attention (mma.sync f16 operands with
- * fp32 accumulate -- TF32-class error; C = 64, NHWC hr and lr) */
+/* CReFF engines: exact fp32 SIMT (any C, NCHW hr), or tensor-core window attention (f16 operands with fp32 accumulate
+ * -- TF32-class error; NHWC hr and lr; C = 64: tcgen05 / TMEM for fp16 hr + lr, mma.sync for fp32 hr; C = 128..1024: mma.sync) */
 enum { ARSEG_CREFF_EXACT_F32 = 0, ARSEG_CREFF_MMA_F16 = 1 };
 
 typedef void* arseg_stream_t;
@@ -162,8 +162,8 @@ int arseg_pyramid_upsample_concat(const float* stage, const void* feats, void* o
  *    final_conv/log-softmax of model/pspnet.py:226-229, + argmax of evaluation.py:204)
  * ---------------------------------------------------------------------------------------------- */
 typedef struct arseg_creff_args {
-    const float* hr;        /* keyframe feature p_HR fp32, NCHW [Nhr,C,H,W] or NHWC [Nhr,H,W,C] (hr_layout);
-                               Nhr = 1 (shared by all N frames) or N */
+    const void* hr;         /* keyframe feature p_HR, NCHW [Nhr,C,H,W] or NHWC [Nhr,H,W,C] (hr_layout), fp32 or (NHWC, C = 64,
+                               ARSEG_CREFF_MMA_F16 only) fp16 (hr_dtype); Nhr = 1 (shared by all N frames) or N */
     int hr_shared;          /* 1: hr has batch 1 and is broadcast over the N frames */
     int hr_layout;          /* ARSEG_NCHW (required by ARSEG_CREFF_EXACT_F32) | ARSEG_NHWC (required by ARSEG_CREFF_MMA_F16) */
     int engine;             /* ARSEG_CREFF_*; an engine that does not support the arguments returns ARSEG_E_UNSUPPORTED */
@@ -183,6 +183,7 @@ typedef struct arseg_creff_args {
     void* workspace;        /* device scratch of >= arseg_creff_workspace_bytes(a) bytes, owned by the caller; may be NULL
                                when that function returns 0 (C = 64 and the exact engine need none) */
     size_t workspace_bytes;
+    int hr_dtype;           /* ARSEG_F32 (0) | ARSEG_F16.  With C = 64, fp16 hr + fp16 NHWC lr run the tcgen05 engine (k <= 7) */
 } arseg_creff_args;
 int arseg_creff_fused_fwd(const arseg_creff_args* a, arseg_stream_t stream);
 /* Scratch the call above needs for these arguments (ARSEG_CREFF_MMA_F16 with C = 128, 192, ... 1024: Q, K, V in fp16

@@ -498,16 +498,108 @@ def test_creff_march_row_segments_are_seamless(k, seg_rows, monkeypatch):
         assert rel_err(seg[0][i:i + 1], fused) < MMA_TOL
 
 
-def test_creff_tile_engine_still_matches(monkeypatch):
-    """ARSEG_CREFF_TILE=1 selects the square-tile engine (kept for A/B measurements)."""
-    monkeypatch.setenv("ARSEG_CREFF_TILE", "1")
-    C, H, W, h, w, k = 64, 32, 48, 16, 24, 7
+# ---------------------------------------------------------------- fused CReFF, tcgen05 / TMEM engine (csrc/creff_tc.cu)
+# f16 keyframe feature + f16 LR feature (what the 'f16' plan feeds it).  The oracle runs on the f16-rounded inputs in
+# fp32, so the tolerance covers the kernel's own roundings: warped-hr / lr_up rows, Q, K, V, P and the classifier input
+# are f16 (11-bit significand), every accumulation fp32 -> the MMA_TOL of the mma.sync engine (3e-3 of max magnitude).
+def _h(x):
+    return x.half().float()
+
+
+def _tc_run(hr, lr, sd, k, **kw):
+    return ops.creff_fused(ops.nchw_to_nhwc(hr.to(DEV), torch.float16), ops.nchw_to_nhwc(lr.to(DEV), torch.float16), *creff_args(sd), k,
+                           lr_layout=L.NHWC, hr_layout=L.NHWC, engine=L.CREFF_MMA_F16, **kw)
+
+
+@pytest.mark.parametrize("k", [3, 5, 7])
+@pytest.mark.parametrize("H,W,h,w", [(32, 48, 16, 24), (21, 37, 11, 19), (64, 16, 32, 8), (9, 70, 5, 33)])
+def test_creff_tc_prewarped(k, H, W, h, w):
+    """MyAttention.forward (model/attention.py:184-213) on tcgen05: ragged sizes exercise partial tiles, strips and segments."""
+    C = 64
     sd = creff_sd(C)
-    hr, lr = rnd(1, C, H, W, seed=51) * 0.6, rnd(1, C, h, w, seed=52) * 0.4
+    hr, lr = _h(rnd(1, C, H, W, seed=51) * 0.6), _h(rnd(1, C, h, w, seed=52) * 0.4)
     ref = O.creff(sd, "fuse_attention.", hr, lr, k)
-    out_p, _, _ = ops.creff_fused(ops.nchw_to_nhwc(hr.to(DEV)), ops.nchw_to_nhwc(lr.to(DEV)), *creff_args(sd), k,
-                                  want_logits=False, lr_layout=L.NHWC, hr_layout=L.NHWC, engine=L.CREFF_MMA_F16)
-    assert rel_err(out_p, ref) < MMA_TOL
+    out_p, _, _ = _tc_run(hr, lr, sd, k, want_logits=False)
+    assert out_p.shape == ref.shape
+    assert rel_err(out_p, ref) < MMA_TOL, rel_err(out_p, ref)
+    assert rms_err(out_p, ref) < MMA_TOL / 4
+
+
+@pytest.mark.parametrize("flow_kind", ["i16", "f64"])
+@pytest.mark.parametrize("stride", [1, 8])
+@pytest.mark.parametrize("ncls", [12, 19])
+def test_creff_tc_with_mv_warp_and_classifier(flow_kind, stride, ncls):
+    """evaluation.py:177-183 + MyAttention + final_conv + log-softmax + argmax in one tcgen05 launch."""
+    from arseg_b200 import synth
+    C, k = 64, 7
+    Hm, Wm = 48 * stride, 64 * stride
+    H, W, h, w = Hm // stride, Wm // stride, Hm // stride // 2, Wm // stride // 2
+    sd = creff_sd(C)
+    hr, lr = _h(rnd(1, C, H, W, seed=53) * 0.6), _h(rnd(2, C, h, w, seed=54) * 0.4)
+    wcls, bcls = rnd(ncls, C, seed=55) * 0.2, rnd(ncls, seed=56) * 0.1
+    mvs = np.stack([synth.synth_mv_int16(Hm, Wm, 60 + i, distance=5 + 3 * i) for i in range(2)])
+    flow64 = torch.from_numpy(mvs.astype(np.float64) / 4.0)
+    flow = {"i16": torch.from_numpy(mvs), "f64": flow64}[flow_kind].to(DEV)
+    out_p, out_l, out_a = _tc_run(hr, lr, sd, k, flow=flow, wcls=wcls.to(DEV), bcls=bcls.to(DEV), log_softmax=True, want_argmax=True,
+                                  hr_shared=True)
+    for i in range(2):
+        fl = O.resize_flow(flow64[i:i + 1], H, W)
+        warped = O.warp_feature(hr, fl)
+        fused = O.creff(sd, "fuse_attention.", warped, lr[i:i + 1], k)
+        logits = F.log_softmax(F.conv2d(fused, wcls.view(ncls, C, 1, 1), bcls), dim=1)
+        assert rel_err(out_p[i:i + 1], fused) < MMA_TOL, rel_err(out_p[i:i + 1], fused)
+        assert rel_err(out_l[i:i + 1], logits) < MMA_TOL, rel_err(out_l[i:i + 1], logits)
+        mism = (out_a[i:i + 1].cpu().long() != logits.argmax(1)).float().mean().item()
+        assert mism < 5e-3, mism
+        assert torch.equal(out_a[i:i + 1].cpu().long(), out_l[i:i + 1].cpu().argmax(1))
+
+
+def test_creff_tc_per_frame_keyframe_features():
+    """hr_shared = 0: every frame has its own (already warped) keyframe feature; frames must not leak into each other."""
+    C, k, H, W, h, w, N = 64, 5, 19, 37, 10, 19, 3
+    sd = creff_sd(C)
+    hr, lr = _h(rnd(N, C, H, W, seed=61) * 0.6), _h(rnd(N, C, h, w, seed=62) * 0.4)
+    out_p, _, _ = _tc_run(hr, lr, sd, k, want_logits=False, hr_shared=False)
+    for i in range(N):
+        ref = O.creff(sd, "fuse_attention.", hr[i:i + 1], lr[i:i + 1], k)
+        assert rel_err(out_p[i:i + 1], ref) < MMA_TOL, (i, rel_err(out_p[i:i + 1], ref))
+    one, _, _ = _tc_run(hr[1:2], lr[1:2], sd, k, want_logits=False)
+    assert torch.equal(one, out_p[1:2])
+
+
+@pytest.mark.parametrize("k", [3, 7])
+@pytest.mark.parametrize("seg_rows", [8, 24])
+def test_creff_tc_row_segments_are_seamless(k, seg_rows, monkeypatch):
+    """Row segments (one CTA each) must not change any pixel: segmented == single-segment bit for bit."""
+    from arseg_b200 import synth
+    C, ncls, H, W, h, w = 64, 12, 42, 52, 21, 26
+    sd = creff_sd(C)
+    hr, lr = _h(rnd(1, C, H, W, seed=153) * 0.6), _h(rnd(2, C, h, w, seed=154) * 0.4)
+    wcls, bcls = rnd(ncls, C, seed=155) * 0.2, rnd(ncls, seed=156) * 0.1
+    mvs = torch.from_numpy(np.stack([synth.synth_mv_int16(H, W, 160 + i, distance=4 + 5 * i) for i in range(2)])).to(DEV)
+
+    def run():
+        return _tc_run(hr, lr, sd, k, flow=mvs, wcls=wcls.to(DEV), bcls=bcls.to(DEV), log_softmax=True, want_argmax=True, hr_shared=True)
+    monkeypatch.setenv("ARSEG_CREFF_SEG_ROWS", "4096")
+    one = run()
+    monkeypatch.setenv("ARSEG_CREFF_SEG_ROWS", str(seg_rows))
+    seg = run()
+    for a, b in zip(one, seg):
+        assert torch.equal(a, b)
+    flow64 = mvs.cpu().double() / 4.0
+    for i in range(2):
+        fused = O.creff(sd, "fuse_attention.", O.warp_feature(hr, O.resize_flow(flow64[i:i + 1], H, W)), lr[i:i + 1], k)
+        assert rel_err(seg[0][i:i + 1], fused) < MMA_TOL
+
+
+def test_creff_tc_rejects_k9_and_mixed_dtypes():
+    sd = creff_sd(64)
+    hr, lr = rnd(1, 64, 16, 16, seed=1), rnd(1, 64, 8, 8, seed=2)
+    with pytest.raises(L.ArsegError):
+        _tc_run(hr, lr, sd, 9, want_logits=False)
+    with pytest.raises(L.ArsegError):      # f16 keyframe feature with an fp32 LR feature
+        ops.creff_fused(ops.nchw_to_nhwc(hr.to(DEV), torch.float16), ops.nchw_to_nhwc(lr.to(DEV)), *creff_args(sd), 7, want_logits=False,
+                        lr_layout=L.NHWC, hr_layout=L.NHWC, engine=L.CREFF_MMA_F16)
 
 
 def test_creff_mma_rejects_unsupported():
