@@ -91,6 +91,9 @@ struct PosRec { float4 w; int info; int cx, cy; };   // (cx, cy) = the clamped N
 // rcp_w / rcp_h > 0: 2/(W-1), 2/(H-1) in f64 -- the grid normalisation (evaluation.py:80-81) is then a multiply
 // instead of an f64 divide (differs from the divide by <= 1 ulp of f64 BEFORE the cast to fp32, evaluation.py:83)
 // mv_raw != nullptr: the position's MV was loaded by the caller (int16 quarter-pel pair at feature resolution).
+// RCP (compile time): rcp_w / rcp_h are known to be > 0 -- the exact-divide path (two f64 divisions, ~300 instructions) is
+// then not even instantiated (instruction-cache footprint of the warp-specialised engines).
+template <bool RCP = false>
 __device__ __forceinline__ PosRec pos_hr(const CreffMmaParams& p, int n, int fy, int fx, double rcp_w = 0.0, double rcp_h = 0.0,
                                          const int* mv_raw = nullptr) {
     PosRec r; r.w = make_float4(0.f, 0.f, 0.f, 0.f); r.info = -1; r.cx = r.cy = 0;
@@ -104,7 +107,7 @@ __device__ __forceinline__ PosRec pos_hr(const CreffMmaParams& p, int n, int fy,
         } else {
             mflow_at(p, n, fy, fx, u, v);
         }
-        if (rcp_w > 0.0) {
+        if (RCP || rcp_w > 0.0) {
             const float gx = (float)(((double)(float)fx + u) * rcp_w - 1.0), gy = (float)(((double)(float)fy + v) * rcp_h - 1.0);
             ix = ((gx + 1.f) * (float)p.W - 1.f) / 2.f;
             iy = ((gy + 1.f) * (float)p.H - 1.f) / 2.f;

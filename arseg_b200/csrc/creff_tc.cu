@@ -30,10 +30,13 @@ namespace arseg {
 
 constexpr int TSW = 16;                    // strip width (pixels)
 constexpr int TTHREADS = 512;
-constexpr int TC_WARPS = 4;                // warps 0..3: TMEM lane quarter = warp
-constexpr int TM_WARP = 4;                 // MMA issuer (and TMEM allocator)
-constexpr int TG_W0 = 5, TG_WARPS = 6;     // gather warps 5..10
-constexpr int TD_W0 = 11, TD_WARPS = 5;    // depthwise warps 11..15: K K V V Q
+// The hardware arbiter prefers the highest warp id of a scheduler: the latency-critical chain (M -> C -> M) gets the top ids.
+// FMA-pipe work per tile and warp: Q 80k lane-ops, K / V 60k each, G 15-30k, C 13k -- the two heaviest (a K warp and the Q
+// warp) must not share a scheduler (warp id % 4): D = warps 0..3 (K K V V) and 7 (Q), G = warps 4, 5, 6, 8, 9, 10.
+constexpr int TD_WARPS = 5, TQ_WARP = 7;
+constexpr int TG_WARPS = 6;
+constexpr int TM_WARP = 11;                // MMA issuer (and TMEM allocator)
+constexpr int TC_W0 = 12, TC_WARPS = 4;    // warps 12..15: TMEM lane quarter = warp % 4
 constexpr int TG_THREADS = 32 * TG_WARPS;
 constexpr int TNQW = 4 * TG_WARPS;         // gather quarter-warps: one position each per slot
 constexpr int TJA = 4;                     // gather positions in flight per quarter-warp
@@ -73,6 +76,7 @@ template <int K> struct TCfg {
     static_assert(NKR % 2 == 0 && KVR % 2 == 0 && PADR % 2 == 0, "even row counts: a 16-key MMA step never straddles the ring end");
     static_assert(COL_L + TNCLS <= 512, "tensor memory columns");
     static_assert(PMAX <= TG_THREADS, "one gather record per G thread");
+    static_assert(TC_W0 % 4 == 0 && TC_W0 + TC_WARPS == TTHREADS / 32, "C = the last warpgroup (setmaxnreg, TMEM lane quarters)");
     static_assert(SMEM <= 232448, "shared memory budget");
 };
 
@@ -97,7 +101,31 @@ __device__ __forceinline__ bool tbar_test(uint64_t* bars, int idx) {
         : "=r"(ok) : "r"(s_u32(bars + (idx & (TNB - 1)))), "r"((uint32_t)((idx / TNB) & 1)) : "memory");
     return ok != 0;
 }
+__device__ __noinline__ void tbar_timeout(int tag, int idx) {
+    if ((threadIdx.x & 31) == 0)
+        printf("arseg creff_tc: mbarrier wait timed out (block %d warp %d barrier %d index %d)\n", (int)blockIdx.x, (int)(threadIdx.x >> 5), tag, idx);
+    __trap();
+}
+// Optional wait-time trace (compile with -DARSEG_TTRACE): lane 0 of every warp of CTA TTRACE_CTA accumulates the cycles it
+// spends in tbar_wait per barrier tag, [15] = cycles of its whole role; read back with arseg_debug_creff_tc_trace().
+#ifdef ARSEG_TTRACE
+constexpr int TTRACE_CTA = 148 * 3 + 11;
+__device__ long long g_ttrace[16 * 16];
+__device__ long long g_tev[2 * 64 * 12];     // [M | C0][tile][event] clock64 stamps
+__device__ __forceinline__ void tev(int role, int tile, int ev) {
+    if (blockIdx.x == TTRACE_CTA && (threadIdx.x & 31) == 0 && tile < 64) g_tev[(role * 64 + tile) * 12 + ev] = clock64();
+}
+#define TEV(role, tile, ev) tev(role, tile, ev)
+#else
+#define TEV(role, tile, ev)
+#endif
+// SLEEP: producer roles (G, D) back off with nanosleep between polls -- a polling warp takes issue slots from the working
+// ones (35 % of all issued instructions before); the latency-critical roles (M, C) poll without sleeping.
+template <bool SLEEP = false>
 __device__ __forceinline__ void tbar_wait(uint64_t* bars, int idx, int tag = 0) {
+#ifdef ARSEG_TTRACE
+    const long long t_in = clock64();
+#endif
     const uint32_t addr = s_u32(bars + (idx & (TNB - 1)));
     const uint32_t parity = (uint32_t)((idx / TNB) & 1);
     uint32_t ok;
@@ -106,14 +134,18 @@ __device__ __forceinline__ void tbar_wait(uint64_t* bars, int idx, int tag = 0) 
     for (int spin = 0; spin < (1 << 20); ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok) : "r"(addr), "r"(parity), "r"(100000u) : "memory");
-        if (ok) return;
+            : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) {
+#ifdef ARSEG_TTRACE
+            if (blockIdx.x == TTRACE_CTA && (threadIdx.x & 31) == 0) g_ttrace[(threadIdx.x >> 5) * 16 + tag] += clock64() - t_in;
+#endif
+            return;
+        }
+        if (SLEEP) __nanosleep(spin < 4 ? 32 : 128);
     }
-    if ((threadIdx.x & 31) == 0)
-        printf("arseg creff_tc: mbarrier wait timed out (block %d warp %d barrier %d index %d)\n", (int)blockIdx.x, (int)(threadIdx.x >> 5), tag, idx);
-    __trap();
+    tbar_timeout(tag, idx);
 }
 __device__ __forceinline__ void t_commit(uint64_t* bars, int idx) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bars + (idx & (TNB - 1)))) : "memory");
@@ -190,6 +222,9 @@ __device__ __forceinline__ void t_sts32(uint32_t a, uint32_t v) { asm volatile("
 __device__ __forceinline__ void t_sts128(uint32_t a, uint4 v) {
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+__device__ __forceinline__ void t_fhfma(float& acc, uint16_t a, uint16_t b) {
+    asm("fma.rn.f32.f16 %0, %1, %2, %0;" : "+f"(acc) : "h"(a), "h"(b));
+}
 __device__ __forceinline__ float2 t_h2f(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
 __device__ __forceinline__ uint4 t_ldg128(const char* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
@@ -219,7 +254,8 @@ __device__ __forceinline__ void t_step_geom(int g, int& h0, int& nh, int& l0, in
 template <int K, bool MVF>
 __device__ __forceinline__ void t_g_role(const CreffMmaParams& p, const TSmem& sm, int n, int x0, int ya, int NH, int S) {
     using Cf = TCfg<K>;
-    const int gt = threadIdx.x - 32 * TG_W0, lane = gt & 31, qw = gt >> 3, l8 = lane & 7;
+    const int gw = (int)(threadIdx.x >> 5), gi = gw < TQ_WARP ? gw - 4 : gw - 5;     // gather warp index 0..5
+    const int gt = gi * 32 + (int)(threadIdx.x & 31), lane = gt & 31, qw = gt >> 3, l8 = lane & 7;
     const float lsh = resize_scale(p.h, p.H, ARSEG_RESIZE_BILINEAR_AC), lsw = resize_scale(p.w, p.W, ARSEG_RESIZE_BILINEAR_AC);
     const char* const hrb = reinterpret_cast<const char*>(p.hr) + (p.hr_shared ? (size_t)0 : (size_t)n * p.H * p.W * 128);
     const char* const lrb = reinterpret_cast<const char*>(p.lr) + (size_t)n * p.h * p.w * 128;
@@ -252,7 +288,7 @@ __device__ __forceinline__ void t_g_role(const CreffMmaParams& p, const TSmem& s
         if (q < nhp) {
             const int rr = q / Cf::HC, cc = q - rr * Cf::HC, row = h0 + rr;
             const int fy = ya - Cf::R - Cf::PADR - 1 + row, fx = x0 - Cf::R - 1 + cc;
-            const PosRec r = pos_hr(p, n, fy, fx, rcp_w, rcp_h, MVF ? &mv : nullptr);
+            const PosRec r = pos_hr<true>(p, n, fy, fx, rcp_w, rcp_h, MVF ? &mv : nullptr);
             dst = (uint32_t)(((row % THRR) * Cf::HC + cc) * 128);
             if (r.info >= 0) {
                 int bx, by;
@@ -293,44 +329,56 @@ __device__ __forceinline__ void t_g_role(const CreffMmaParams& p, const TSmem& s
         const uint32_t* t1 = reinterpret_cast<const uint32_t*>(&tp[1]);
         const uint32_t* t2 = reinterpret_cast<const uint32_t*>(&tp[2]);
         const uint32_t* t3 = reinterpret_cast<const uint32_t*>(&tp[3]);
+        // mixed-precision FMA (f16 x f16 + f32 -> f32, SASS FHFMA): the taps are consumed as they are, no f16 -> f32 conversions;
+        // the bilinear weights are rounded to f16 (<= 2^-12 relative, below the f16 rounding of the result itself)
+        const uint16_t w0 = __half_as_ushort(__float2half_rn(w.x)), w1 = __half_as_ushort(__float2half_rn(w.y));
+        const uint16_t w2 = __half_as_ushort(__float2half_rn(w.z)), w3 = __half_as_ushort(__float2half_rn(w.w));
         uint32_t o[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const float2 a = t_h2f(t0[e]), b = t_h2f(t1[e]), c = t_h2f(t2[e]), dd = t_h2f(t3[e]);
-            const float vx = a.x * w.x + b.x * w.y + c.x * w.z + dd.x * w.w;
-            const float vy = a.y * w.x + b.y * w.y + c.y * w.z + dd.y * w.w;
+            float vx = 0.f, vy = 0.f;
+            t_fhfma(vx, (uint16_t)(t0[e] & 0xffffu), w0); t_fhfma(vy, (uint16_t)(t0[e] >> 16), w0);
+            t_fhfma(vx, (uint16_t)(t1[e] & 0xffffu), w1); t_fhfma(vy, (uint16_t)(t1[e] >> 16), w1);
+            t_fhfma(vx, (uint16_t)(t2[e] & 0xffffu), w2); t_fhfma(vy, (uint16_t)(t2[e] >> 16), w2);
+            t_fhfma(vx, (uint16_t)(t3[e] & 0xffffu), w3); t_fhfma(vy, (uint16_t)(t3[e] >> 16), w3);
             o[e] = pack_h2_sat(vx, vy);
         }
         t_sts128(sm.rings + (d & 0x0fffffffu) + (((uint32_t)l8 ^ (d >> 28)) << 4), make_uint4(o[0], o[1], o[2], o[3]));
     };
 
-    compute_pos(-1, mv_of(-1));
-    nbar_sync(TBAR_G, TG_THREADS);
+    int mv_next = mv_of(-1);
+    // trip g = -2 only computes the records of step -1 (one instance of the record code: instruction-cache footprint)
 #pragma unroll 1
-    for (int g = -1; g < NH; ++g) {
+    for (int g = -2; g < NH; ++g) {
         const int buf = (g + 1) & 1;
-        // rolling pipeline: TJA positions' loads are always in flight while the oldest one is combined and stored
+        const int mv_cur = mv_next;
+        if (g >= -1) {
+            // rolling pipeline: TJA positions' loads are always in flight while the oldest one is combined and stored
 #pragma unroll
-        for (int j = 0; j < TJA; ++j) issue(tap[j], buf, j);
-        const int mv_next = g + 1 < NH ? mv_of(g + 1) : 0;          // in flight during the gather loop
-        if (g >= 2) tbar_wait(sm.ddone, g - 2, 2);                     // D half-step g-2 done: the hr / lr rows this step overwrites are read
-        {
-            // lr_up rows double as the residual: C takes the rows of tile i at the start of its step
-            const int num = 4 * (g - Cf::HP) + 5 - TLRR - 1;        // last overwritten lr row - 1
-            if (num >= 0) { const int im = num >> 3; tbar_wait(sm.lrfree, im < S - 1 ? im : S - 1, 3); }
-        }
+            for (int j = 0; j < TJA; ++j) issue(tap[j], buf, j);
+            mv_next = g + 1 < NH ? mv_of(g + 1) : 0;                    // in flight during the gather loop
+            if (g >= 2) tbar_wait<true>(sm.ddone, g - 2, 2);                  // D half-step g-2 done: the hr / lr rows this step overwrites are read
+            {
+                // lr_up rows double as the residual: C takes the rows of tile i at the start of its step
+                const int num = 4 * (g - Cf::HP) + 5 - TLRR - 1;        // last overwritten lr row - 1
+                if (num >= 0) { const int im = num >> 3; tbar_wait<true>(sm.lrfree, im < S - 1 ? im : S - 1, 3); }
+            }
+#ifdef ARSEG_TTRACE
+            if (!(p.dbg & 4))
+#endif
 #pragma unroll 1
-        for (int j0 = 0; j0 < Cf::NJ; j0 += TJA) {
+            for (int j0 = 0; j0 < Cf::NJ; j0 += TJA) {
 #pragma unroll
-            for (int j = 0; j < TJA; ++j) {
-                if (j0 + j < Cf::NJ) {
-                    commit(tap[j], buf, j0 + j);
-                    if (j0 + j + TJA < Cf::NJ) issue(tap[j], buf, j0 + j + TJA);
+                for (int j = 0; j < TJA; ++j) {
+                    if (j0 + j < Cf::NJ) {
+                        commit(tap[j], buf, j0 + j);
+                        if (j0 + j + TJA < Cf::NJ) issue(tap[j], buf, j0 + j + TJA);
+                    }
                 }
             }
+            tbar_arrive(sm.gfull, g + 1);
         }
-        tbar_arrive(sm.gfull, g + 1);
-        if (g + 1 < NH) compute_pos(g + 1, mv_next);
+        if (g + 1 < NH) compute_pos(g + 1, g >= -1 ? mv_next : mv_cur);
         nbar_sync(TBAR_G, TG_THREADS);                              // records of step g+1 visible; everyone is done with those of step g-1
     }
 }
@@ -356,7 +404,7 @@ __device__ __forceinline__ int t_kv_last_reader(int h) {
 template <int K>
 __device__ __forceinline__ void t_d_role(const CreffMmaParams& p, const TSmem& sm, int x0, int ya, int NH, int S) {
     using Cf = TCfg<K>;
-    const int lane = threadIdx.x & 31, d = (threadIdx.x >> 5) - TD_W0;
+    const int lane = threadIdx.x & 31, d = (threadIdx.x >> 5) == TQ_WARP ? 4 : (int)(threadIdx.x >> 5);
     const uint32_t lane_sub = (uint32_t)((lane & 3) * 4), lane_chunk = (uint32_t)(lane >> 2);
     if (d < 4) {
         // ---------------- K (d = 0, 1) or V (d = 2, 3): columns [c_lo, c_lo + ncol) of four K/V rows per half-step ----------------
@@ -374,39 +422,48 @@ __device__ __forceinline__ void t_d_role(const CreffMmaParams& p, const TSmem& s
         const uint32_t hbase = sm.rings + (uint32_t)(c_lo * 128 + lane * 4);
 #pragma unroll 1
         for (int h = 0; h < NH; ++h) {
-            tbar_wait(sm.gfull, h + 1, 1);
+            tbar_wait<true>(sm.gfull, h + 1, 1);
             {
                 const int jm = t_kv_last_reader<K>(h);
-                if (jm >= 0) tbar_wait(sm.ofull, jm < S - 1 ? jm : S - 1, 4);     // P V of the last tile that read these ring slots has retired
+                if (jm >= 0) tbar_wait<true>(sm.ofull, jm < S - 1 ? jm : S - 1, 4);     // P V of the last tile that read these ring slots has retired
             }
             uint32_t ra[6], ko[4];
-            bool rok[4];
+            uint32_t rok[4];                                                   // all-ones / zero masks: the select must stay branch-free
 #pragma unroll
             for (int i = 0; i < 6; ++i) ra[i] = hbase + (uint32_t)(((4 * h + i) % THRR) * (Cf::HC * 128));
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 const int kr = 4 * h + r, fy = ya - Cf::R - Cf::PADR + kr;
                 ko[r] = ring + (uint32_t)((kr % Cf::KVR) * TROWB) + lane_sub;
-                rok[r] = fy >= 0 && fy < p.H;                                  // K / V are exactly 0 outside the image (attention zero padding)
+                rok[r] = (fy >= 0 && fy < p.H) ? 0xffffffffu : 0u;             // K / V are exactly 0 outside the image (attention zero padding)
             }
+#ifdef ARSEG_TTRACE
+            if (p.dbg & 1) { t_fence_async_smem(); tbar_arrive(sm.ddone, h); continue; }
+#endif
             float2 win[6][3];
 #pragma unroll
             for (int c = 0; c < 2; ++c)
 #pragma unroll
                 for (int i = 0; i < 6; ++i) win[i][c] = t_h2f(t_lds32(ra[i] + c * 128));
+            // three columns per trip (the register window rotates by renaming inside a trip); the loop stays rolled: the five
+            // roles of the CTA share one instruction cache
+#pragma unroll 1
+            for (int x3 = 0; x3 < ncol; x3 += 3) {
 #pragma unroll
-            for (int x = 0; x < Cf::KVC1; ++x) {
-                if (x < ncol) {
-                    const int sa = x % 3, sb = (x + 1) % 3, sc = (x + 2) % 3;
+                for (int u = 0; u < 3; ++u) {
+                    const int x = x3 + u;
+                    if (x < ncol) {
+                        const int sa = u, sb = (u + 1) % 3, sc = (u + 2) % 3;
 #pragma unroll
-                    for (int i = 0; i < 6; ++i) win[i][sc] = t_h2f(t_lds32(ra[i] + (x + 2) * 128));
-                    const int col = c_lo + x, fx = x0 - Cf::R + col;
-                    const bool okx = fx >= 0 && fx < p.W;
-                    const uint32_t co = (uint32_t)(col * 128) + ((lane_chunk ^ (uint32_t)(col & 7)) << 4);
+                        for (int i = 0; i < 6; ++i) win[i][sc] = t_h2f(t_lds32(ra[i] + (x + 2) * 128));
+                        const int col = c_lo + x, fx = x0 - Cf::R + col;
+                        const uint32_t okx = (fx >= 0 && fx < p.W) ? 0xffffffffu : 0u;
+                        const uint32_t co = (uint32_t)(col * 128) + ((lane_chunk ^ (uint32_t)(col & 7)) << 4);
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const float2 v = t_dw9(w, win[r], win[r + 1], win[r + 2], sa, sb, sc);
-                        t_sts32(ko[r] + co, (okx && rok[r]) ? pack_h2_sat(v.x, v.y) : 0u);
+                        for (int r = 0; r < 4; ++r) {
+                            const float2 v = t_dw9(w, win[r], win[r + 1], win[r + 2], sa, sb, sc);
+                            t_sts32(ko[r] + co, pack_h2_sat(v.x, v.y) & okx & rok[r]);
+                        }
                     }
                 }
             }
@@ -419,16 +476,19 @@ __device__ __forceinline__ void t_d_role(const CreffMmaParams& p, const TSmem& s
 #pragma unroll
         for (int i = 0; i < 9; ++i) w[i] = make_float2(__ldg(p.wq + (2 * lane) * 9 + i), __ldg(p.wq + (2 * lane + 1) * 9 + i));
         w[9] = make_float2(__ldg(p.bq + 2 * lane), __ldg(p.bq + 2 * lane + 1));
-        uint32_t lx[8];     // byte offset of this lane's channel pair inside a 128-byte position whose column & 7 = c (chunk swizzle)
+        uint32_t lx[2];     // byte offset of this lane's channel pair inside a 128-byte position whose column & 7 = c (chunk swizzle)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) lx[c] = ((lane_chunk ^ (uint32_t)c) << 4) + lane_sub;
+        for (int c = 0; c < 2; ++c) lx[c] = ((lane_chunk ^ (uint32_t)c) << 4) + lane_sub;
         const uint32_t lbase = sm.rings + (uint32_t)Cf::HR_BYTES;
 #pragma unroll 1
         for (int h = 0; h < NH; ++h) {
-            tbar_wait(sm.gfull, h + 1, 1);
+            tbar_wait<true>(sm.gfull, h + 1, 1);
+#ifdef ARSEG_TTRACE
+            if (p.dbg & 1) { t_fence_async_smem(); tbar_arrive(sm.ddone, h); continue; }
+#endif
             if (h >= Cf::HP) {
                 const int q0 = 4 * (h - Cf::HP), ti = q0 >> 3, qy0 = q0 & 7;
-                if (ti >= 1) tbar_wait(sm.sfull, ti - 1, 5);                      // S = Q K^T of the previous tile has retired: the A tile is free
+                if (ti >= 1) tbar_wait<true>(sm.sfull, ti - 1, 5);                      // S = Q K^T of the previous tile has retired: the A tile is free
                 uint32_t ra[6];
 #pragma unroll
                 for (int i = 0; i < 6; ++i) ra[i] = lbase + (uint32_t)(((q0 + i) % TLRR) * (TLC * 128));
@@ -437,16 +497,24 @@ __device__ __forceinline__ void t_d_role(const CreffMmaParams& p, const TSmem& s
 #pragma unroll
                 for (int c = 0; c < 2; ++c)
 #pragma unroll
-                    for (int i = 0; i < 6; ++i) win[i][c] = t_h2f(t_lds32(ra[i] + c * 128 + lx[c & 7]));
+                    for (int i = 0; i < 6; ++i) win[i][c] = t_h2f(t_lds32(ra[i] + c * 128 + lx[c]));
+#pragma unroll 1
+                for (int x3 = 0; x3 < TSW; x3 += 3) {
 #pragma unroll
-                for (int x = 0; x < TSW; ++x) {
-                    const int sa = x % 3, sb = (x + 1) % 3, sc = (x + 2) % 3;
+                    for (int u = 0; u < 3; ++u) {
+                        const int x = x3 + u;
+                        if (x < TSW) {
+                            const int sa = u, sb = (u + 1) % 3, sc = (u + 2) % 3;
+                            const uint32_t lin = (uint32_t)((x + 2) * 128) + (((lane_chunk ^ (uint32_t)((x + 2) & 7)) << 4) + lane_sub);
 #pragma unroll
-                    for (int i = 0; i < 6; ++i) win[i][sc] = t_h2f(t_lds32(ra[i] + (x + 2) * 128 + lx[(x + 2) & 7]));
+                            for (int i = 0; i < 6; ++i) win[i][sc] = t_h2f(t_lds32(ra[i] + lin));
+                            const uint32_t qst = qo + (uint32_t)(x * 128) + (((lane_chunk ^ (uint32_t)(x & 7)) << 4) + lane_sub);
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const float2 v = t_dw9(w, win[r], win[r + 1], win[r + 2], sa, sb, sc);
-                        t_sts32(qo + (uint32_t)((r * TSW + x) * 128) + lx[x & 7], pack_h2_sat(v.x, v.y));
+                            for (int r = 0; r < 4; ++r) {
+                                const float2 v = t_dw9(w, win[r], win[r + 1], win[r + 2], sa, sb, sc);
+                                t_sts32(qst + (uint32_t)(r * TSW * 128), pack_h2_sat(v.x, v.y));
+                            }
+                        }
                     }
                 }
             }
@@ -459,22 +527,27 @@ __device__ __forceinline__ void t_d_role(const CreffMmaParams& p, const TSmem& s
 // ---------------------------------------------------------------------------------------------
 // M role: the MMA-issuing thread.
 // ---------------------------------------------------------------------------------------------
+// The issuing thread is ONE lane: every instruction it executes is a dependent scalar chain, so the descriptors are advanced
+// incrementally (one add per MMA) instead of being rebuilt from row / column arithmetic.
 template <int K>
 __device__ __forceinline__ void t_issue_qk(const TSmem& sm, uint32_t tmem, int i) {
     using Cf = TCfg<K>;
     // key rows [8i + PADR, + NKR) of the ring in chunks of <= 8 rows that do not cross the ring end (N = 24 * rows <= 192)
     const int b0 = (8 * i + Cf::PADR) % Cf::KVR;
+    const uint64_t dq = t_desc(sm.sQ), dk = t_desc(sm.sK);
     int done = 0;
 #pragma unroll 1
     while (done < Cf::NKR) {
-        const int rs = (b0 + done) % Cf::KVR;
+        int rs = b0 + done;
+        rs = rs >= Cf::KVR ? rs - Cf::KVR : rs;
         int nr = Cf::NKR - done;
-        if (nr > 8) nr = 8;
-        if (rs + nr > Cf::KVR) nr = Cf::KVR - rs;
+        nr = nr > 8 ? 8 : nr;
+        nr = rs + nr > Cf::KVR ? Cf::KVR - rs : nr;
         const uint32_t id = t_idesc(nr * TKP, 0);
+        const uint64_t dkr = dk + (uint64_t)(rs * (TROWB >> 4));
+        const uint32_t td = tmem + (uint32_t)(done * TKP);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-            t_mma_ss(t_desc(sm.sQ + k * 32), t_desc(sm.sK + rs * TROWB + k * 32), tmem + (uint32_t)(done * TKP), k != 0, id);
+        for (int k = 0; k < 4; ++k) t_mma_ss(dq + (uint64_t)(2 * k), dkr + (uint64_t)(2 * k), td, k != 0, id);
         done += nr;
     }
 }
@@ -483,14 +556,18 @@ __device__ __forceinline__ void t_issue_pv(const TSmem& sm, uint32_t tmem, int i
     using Cf = TCfg<K>;
     const int b0 = (8 * i + Cf::PADR) % Cf::KVR;
     constexpr uint32_t IDV = t_idesc(64, 1), IDS = t_idesc(16, 0);
-    const uint64_t ones = t_desc(sm.sOnes);
-    // 16 keys (2 KB of ring) per MMA: P columns [8 ks, 8 ks + 8) x V rows; the row sums come from the same A against ones
-#pragma unroll 1
+    constexpr uint32_t RING16 = (uint32_t)(Cf::KVR * TROWB) >> 4;      // ring size in descriptor units (16 bytes)
+    const uint64_t ones = t_desc(sm.sOnes), dv = t_desc(sm.sV);
+    // 16 keys (2 KB of ring) per MMA: P columns [8 ks, 8 ks + 8) x V rows; the row sums come from the same A against ones.
+    // An even number of rows precedes the ring end, so a 16-key step never straddles it: the offset just wraps.
+    uint32_t off = (uint32_t)(b0 * (TROWB >> 4)), ta = tmem;
+#pragma unroll
     for (int ks = 0; ks < Cf::NK / 16; ++ks) {
-        const int kk = ks * 16, row = kk / TKP;
-        const uint32_t addr = sm.sV + (uint32_t)(((b0 + row) % Cf::KVR) * TROWB + (kk - row * TKP) * 128);
-        t_mma_ts(tmem + (uint32_t)(ks * 8), t_desc(addr), tmem + Cf::COL_O, ks != 0, IDV);
-        t_mma_ts(tmem + (uint32_t)(ks * 8), ones, tmem + Cf::COL_SUM, ks != 0, IDS);
+        t_mma_ts(ta, dv + off, tmem + Cf::COL_O, ks != 0, IDV);
+        t_mma_ts(ta, ones, tmem + Cf::COL_SUM, ks != 0, IDS);
+        off += 2048 >> 4;
+        off = off >= RING16 ? off - RING16 : off;
+        ta += 8;
     }
 }
 template <int K, int NCP>
@@ -501,35 +578,48 @@ __device__ __forceinline__ void t_issue_cls(const TSmem& sm, uint32_t tmem) {
     for (int k = 0; k < 4; ++k) t_mma_ts(tmem + Cf::COL_A + (uint32_t)(k * 8), t_desc(sm.sW + k * 32), tmem + Cf::COL_L, k != 0, ID);
 }
 
+__device__ __forceinline__ bool t_elect() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+// The whole warp runs the control flow (warp-uniform operands live in uniform registers, which tcgen05.mma reads
+// directly); one elected lane issues.
 template <int K, int NCP>
 __device__ __forceinline__ void t_m_role(const TSmem& sm, uint32_t tmem, int S) {
     using Cf = TCfg<K>;
-    if ((threadIdx.x & 31) != 0) return;
     bool qk_ahead = false;          // S of the next tile already issued
 #pragma unroll 1
     for (int i = 0; i < S; ++i) {
         if (!qk_ahead) {
             tbar_wait(sm.ddone, 2 * i + Cf::HP + 1, 6);           // K/V rows and Q of tile i are in shared memory
+            TEV(0, i, 0);
             t_fence_after();
-            t_issue_qk<K>(sm, tmem, i);
-            t_commit(sm.sfull, i);
+            if (t_elect()) { t_issue_qk<K>(sm, tmem, i); t_commit(sm.sfull, i); }
+            __syncwarp();
+            TEV(0, i, 1);
         }
         qk_ahead = false;
         tbar_wait(sm.pfull, i, 7);                                   // P is in tensor memory
+        TEV(0, i, 2);
         t_fence_after();
-        t_issue_pv<K>(sm, tmem, i);
-        t_commit(sm.ofull, i);
+        if (t_elect()) { t_issue_pv<K>(sm, tmem, i); t_commit(sm.ofull, i); }
+        __syncwarp();
+        TEV(0, i, 3);
         if (NCP > 0) {
             tbar_wait(sm.afull, i, 8);                               // residual + O / sum is back in tensor memory (f16)
+            TEV(0, i, 4);
             t_fence_after();
-            t_issue_cls<K, NCP>(sm, tmem);
-            t_commit(sm.lfull, i);
+            if (t_elect()) { t_issue_cls<K, NCP>(sm, tmem); t_commit(sm.lfull, i); }
+            __syncwarp();
+            TEV(0, i, 5);
         }
         // the S columns are free once P V has been issued (the tensor pipe runs in order): start the next tile's S early
         if (i + 1 < S && tbar_test(sm.ddone, 2 * (i + 1) + Cf::HP + 1)) {
             t_fence_after();
-            t_issue_qk<K>(sm, tmem, i + 1);
-            t_commit(sm.sfull, i + 1);
+            if (t_elect()) { t_issue_qk<K>(sm, tmem, i + 1); t_commit(sm.sfull, i + 1); }
+            __syncwarp();
             qk_ahead = true;
         }
     }
@@ -542,7 +632,7 @@ template <int K, int NCP>
 __device__ __forceinline__ void t_c_role(const CreffMmaParams& p, const TSmem& sm, uint32_t tmem, int n, int x0, int ya, int yb, int S) {
     using Cf = TCfg<K>;
     constexpr float LOG2E = 1.4426950408889634f;
-    const int lane = threadIdx.x & 31, cw = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, cw = (threadIdx.x >> 5) - TC_W0;
     const int b = lane >> 4, qx = lane & 15, qy = 2 * cw + b;
     const uint32_t tq = tmem + ((uint32_t)(32 * cw) << 16);
     const int W = p.W;
@@ -566,6 +656,7 @@ __device__ __forceinline__ void t_c_role(const CreffMmaParams& p, const TSmem& s
         // (a parity wait may only name a phase the barrier has already entered: every role's FIRST wait on a hand-off uses an
         // index < TNB and later ones advance by < TNB, so "tile ready" = ddone(2i + HP + 1) is used here, not gfull(2i + HP + 2))
         tbar_wait(sm.ddone, 2 * i + Cf::HP + 1, 1);
+        if (cw == 0) TEV(1, i, 0);
         uint4 res[8];
         {
             const uint32_t ra = lbase + (uint32_t)(((8 * i + 1 + qy) % TLRR) * (TLC * 128)) + res_col;
@@ -575,39 +666,41 @@ __device__ __forceinline__ void t_c_role(const CreffMmaParams& p, const TSmem& s
         tbar_arrive(sm.lrfree, i);
         // ---------------- softmax over the k x k window (model/attention.py:203) ----------------
         tbar_wait(sm.sfull, i, 9);
+        if (cw == 0) TEV(1, i, 1);
         t_fence_after();
         const uint32_t srow = tq + (uint32_t)(2 * cw * TKP);        // S columns of the warp's first key row
         float m = -INFINITY;
-#pragma unroll
-        for (int j = 0; j <= K; ++j) {
+#pragma unroll 1
+        for (int j = 0; j <= K; ++j) {                              // rolled: see the D role
             uint32_t s[24];
             t_ld16(srow + j * TKP, s);
             t_ld8(srow + j * TKP + 16, s + 16);
             t_ld_wait();
-            const float rb = j == 0 ? rb_first : (j == K ? rb_last : 0.f);
+            float rm = -INFINITY;
 #pragma unroll
-            for (int c = 0; c < Cf::KVC; ++c) {
-                float v = __uint_as_float(s[c]) + cb[c];
-                if (j == 0 || j == K) v += rb;
-                m = fmaxf(m, v);
-            }
+            for (int c = 0; c < Cf::KVC; ++c) rm = fmaxf(rm, __uint_as_float(s[c]) + cb[c]);
+            m = fmaxf(m, rm + (j == 0 ? rb_first : (j == K ? rb_last : 0.f)));
         }
+        if (cw == 0) TEV(1, i, 2);
         const float ml = m * LOG2E;
-        const uint32_t prow = tq + (uint32_t)(2 * cw * (TKP / 2));  // P columns of the warp's first key row
+        float cbm[Cf::KVC];
 #pragma unroll
+        for (int c = 0; c < Cf::KVC; ++c) cbm[c] = cb[c] - ml;
+        const uint32_t prow = tq + (uint32_t)(2 * cw * (TKP / 2));  // P columns of the warp's first key row
+#pragma unroll 1
         for (int j = 0; j <= K; ++j) {
             uint32_t s[24];
             t_ld16(srow + j * TKP, s);
             t_ld8(srow + j * TKP + 16, s + 16);
             t_ld_wait();
-            const float rb = (j == 0 ? rb_first : (j == K ? rb_last : 0.f)) - ml;
+            const bool rowok = !((j == 0 && b) || (j == K && !b));
             uint32_t pk[12];
 #pragma unroll
             for (int c = 0; c < 24; c += 2) {
                 if (c < Cf::KVC) {
-                    const float e0 = t_ex2(fmaf(__uint_as_float(s[c]), LOG2E, cb[c] + rb));
-                    const float e1 = c + 1 < Cf::KVC ? t_ex2(fmaf(__uint_as_float(s[c + 1]), LOG2E, cb[c + 1] + rb)) : 0.f;
-                    pk[c >> 1] = pack_h2(e0, e1);
+                    const float e0 = t_ex2(fmaf(__uint_as_float(s[c]), LOG2E, cbm[c]));
+                    const float e1 = c + 1 < Cf::KVC ? t_ex2(fmaf(__uint_as_float(s[c + 1]), LOG2E, cbm[c + 1 < Cf::KVC ? c + 1 : c])) : 0.f;
+                    pk[c >> 1] = rowok ? pack_h2(e0, e1) : 0u;
                 } else {
                     pk[c >> 1] = 0u;
                 }
@@ -615,6 +708,7 @@ __device__ __forceinline__ void t_c_role(const CreffMmaParams& p, const TSmem& s
             t_st8(prow + j * (TKP / 2), pk);
             t_st4(prow + j * (TKP / 2) + 8, pk[8], pk[9], pk[10], pk[11]);
         }
+        if (cw == 0) TEV(1, i, 3);
         // P of the key rows outside the warp's range is zero (written after the S reads: the P columns alias S)
 #pragma unroll 1
         for (int r = 0; r < Cf::NKR; ++r) {
@@ -626,8 +720,10 @@ __device__ __forceinline__ void t_c_role(const CreffMmaParams& p, const TSmem& s
         t_st_wait();
         t_fence_before();
         tbar_arrive(sm.pfull, i);
+        if (cw == 0) TEV(1, i, 4);
         // ---------------- fused = lr_up + O / sum (model/attention.py:207,210) ----------------
         tbar_wait(sm.ofull, i, 10);
+        if (cw == 0) TEV(1, i, 5);
         t_fence_after();
         const int py = ya + 8 * i + qy;
         const bool ok = py < yb && px < W;
@@ -649,21 +745,47 @@ __device__ __forceinline__ void t_c_role(const CreffMmaParams& p, const TSmem& s
                     const float2 r2 = t_h2f(rr[e]);
                     const int ch = 8 * c + 2 * e;                              // channel 32 hf + ch
                     const float f0 = fmaf(__uint_as_float(o[ch]), inv, r2.x), f1 = fmaf(__uint_as_float(o[ch + 1]), inv, r2.y);
-                    if (op && ok) {
-                        op[(size_t)(32 * hf + ch) * plane + off] = f0;
-                        op[(size_t)(32 * hf + ch + 1) * plane + off] = f1;
-                    }
                     pk[4 * c + e] = pack_h2_sat(f0, f1);
                 }
             }
             if (NCP > 0) t_st16(tq + Cf::COL_A + 16 * hf, pk);
         }
+        if (op) {
+            // the fused feature itself (the second value of forward_phase2, discarded by evaluation.py:193): a cold, warp-uniform
+            // branch that re-reads O instead of predicating 64 stores into the hot path
+            float* o_ptr = op + off;
+            const float inv = t_rcp(__uint_as_float(su));
+#pragma unroll 1
+            for (int q8 = 0; q8 < 8; ++q8) {
+                uint32_t o[8];
+                t_ld8(tq + Cf::COL_O + 8 * q8, o);
+                t_ld_wait();
+                const uint32_t* rr = reinterpret_cast<const uint32_t*>(&res[0]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    // res[q8] holds channels 8 q8 .. 8 q8 + 7 as four f16 pairs (dynamic q8: select by a rolled copy below)
+                    const float2 r2 = t_h2f(rr[e]);
+                    if (ok) {
+                        o_ptr[(size_t)(2 * e) * plane] = fmaf(__uint_as_float(o[2 * e]), inv, r2.x);
+                        o_ptr[(size_t)(2 * e + 1) * plane] = fmaf(__uint_as_float(o[2 * e + 1]), inv, r2.y);
+                    }
+                }
+                o_ptr += 8 * plane;
+                // rotate the residual registers so that res[0] is the next 8-channel group
+                const uint4 t0 = res[0];
+#pragma unroll
+                for (int c = 0; c < 7; ++c) res[c] = res[c + 1];
+                res[7] = t0;
+            }
+        }
         if (NCP == 0) continue;
         t_st_wait();
         t_fence_before();
         tbar_arrive(sm.afull, i);
+        if (cw == 0) TEV(1, i, 6);
         // ---------------- classifier (model/pspnet.py:226), log-softmax (:229), argmax (evaluation.py:204) ----------------
         tbar_wait(sm.lfull, i, 11);
+        if (cw == 0) TEV(1, i, 7);
         t_fence_after();
         constexpr int NCPA = NCP > 0 ? NCP : 16;
         uint32_t lg[NCPA];
@@ -694,6 +816,7 @@ __device__ __forceinline__ void t_c_role(const CreffMmaParams& p, const TSmem& s
             }
             if (oa) oa[off] = (uint8_t)am;
         }
+        if (cw == 0) TEV(1, i, 8);
     }
 }
 
@@ -761,12 +884,18 @@ __global__ void __launch_bounds__(TTHREADS, 1) creff_tc_kernel(CreffMmaParams p)
     const uint32_t tmem = *tmem_slot;
 
     // register file re-balance (warpgroup-aligned): the softmax / epilogue warps take what the producers do not need
-    if (warp < TC_WARPS) asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+    if (warp >= TC_W0) asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
     else asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
-    if (warp < TC_WARPS) t_c_role<K, NCP>(p, sm, tmem, n, x0, ya, yb, S);
+#ifdef ARSEG_TTRACE
+    const long long t_role = clock64();
+#endif
+    if (warp >= TC_W0) t_c_role<K, NCP>(p, sm, tmem, n, x0, ya, yb, S);
     else if (warp == TM_WARP) t_m_role<K, NCP>(sm, tmem, S);
-    else if (warp < TD_W0) t_g_role<K, MVF>(p, sm, n, x0, ya, NH, S);
-    else t_d_role<K>(p, sm, x0, ya, NH, S);
+    else if (warp < 4 || warp == TQ_WARP) t_d_role<K>(p, sm, x0, ya, NH, S);
+    else t_g_role<K, MVF>(p, sm, n, x0, ya, NH, S);
+#ifdef ARSEG_TTRACE
+    if (blockIdx.x == TTRACE_CTA && (tid & 31) == 0) { g_ttrace[warp * 16 + 15] += clock64() - t_role; g_ttrace[warp * 16 + 14] += S; }
+#endif
 
     t_fence_before();
     __syncthreads();
@@ -790,6 +919,7 @@ static int creff_tc_launch_n(CreffMmaParams& p, cudaStream_t st) {
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     p.ncols = ceil_div(p.W, TSW);
+    { const char* d = getenv("ARSEG_CREFF_DBG"); p.dbg = d ? atoi(d) : 0; }      // -DARSEG_TTRACE builds only
     // row segments: enough CTAs for >= ~6 waves of one CTA per SM, but segments of >= 48 rows (each segment pays
     // ~K+5 redundant halo rows and the pipeline fill)
     const int sms = sm_count() > 0 ? sm_count() : 148;
@@ -831,3 +961,14 @@ int creff_tc_launch(CreffMmaParams& p, int k, cudaStream_t st) {
 }
 
 }  // namespace arseg
+#ifdef ARSEG_TTRACE
+extern "C" int arseg_debug_creff_tc_events(long long* host) {
+    cudaMemcpyFromSymbol(host, arseg::g_tev, sizeof(long long) * 2 * 64 * 12);
+    return 2 * 64 * 12;
+}
+extern "C" int arseg_debug_creff_tc_trace(long long* host, int reset) {
+    cudaMemcpyFromSymbol(host, arseg::g_ttrace, sizeof(long long) * 256);
+    if (reset) { long long z[256] = {0}; cudaMemcpyToSymbol(arseg::g_ttrace, z, sizeof(z)); }
+    return 256;
+}
+#endif

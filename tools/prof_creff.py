@@ -1,6 +1,6 @@
 """Runs the fused warp+CReFF kernel alone at the CamVid 720x960 shape (for ncu / quick timing).
 
-    python tools/prof_creff.py [--frames N] [--k 7] [--engine mma|exact] [--iters I] [--want-p]
+    python tools/prof_creff.py [--frames N] [--k 7] [--engine tc|mma|exact] [--iters I] [--want-p]
 """
 import argparse
 import os
@@ -39,8 +39,10 @@ def main():
     for _ in range(3):
         ws += [(torch.randn(C * 9, generator=g) * 0.3).to(dev), (torch.randn(C, generator=g) * 0.1).to(dev)]
     wcls, bcls = (torch.randn(ncls, C, generator=g) * 0.2).to(dev), (torch.randn(ncls, generator=g) * 0.1).to(dev)
-    lr_nhwc = ops.nchw_to_nhwc(lr)
-    if a.engine == "mma":
+    lr_nhwc = ops.nchw_to_nhwc(lr, torch.float16 if a.engine == "tc" else torch.float32)
+    if a.engine == "tc":      # tcgen05 engine: f16 keyframe feature + f16 LR feature
+        hr_in, kw = ops.nchw_to_nhwc(hr, torch.float16), dict(hr_layout=L.NHWC, engine=L.CREFF_MMA_F16)
+    elif a.engine == "mma":
         hr_in, kw = ops.nchw_to_nhwc(hr), dict(hr_layout=L.NHWC, engine=L.CREFF_MMA_F16)
     else:
         hr_in, kw = hr, dict(hr_layout=L.NCHW, engine=L.CREFF_EXACT_F32)

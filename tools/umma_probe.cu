@@ -276,6 +276,146 @@ __global__ void __launch_bounds__(160, 1) probe_kernel(Args a) {
     if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// timing kernel: issue / completion cost of the MMA shapes and TMEM read patterns the engine uses (one CTA, clock64)
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+}
+__global__ void __launch_bounds__(160, 1) time_kernel(long long* out, float* sink) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + 128 * 128;
+    uint8_t* sV = sK + RR * ROWB;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + RR * ROWB);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < (128 * 128 + 2 * RR * ROWB) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x2c002c00u;   // small f16 values
+    fence_async_smem();
+    if (tid == 0) {
+        for (int i = 0; i < 16; ++i) mbar_init(bars + i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    if (warp == 4) {
+        // whole warp runs the loops (warp-uniform operands -> uniform registers), one elected lane issues
+        const uint64_t dq = desc_sw128(s_u32(sQ), 1024, 0), dk = desc_sw128(s_u32(sK), 1024, 0), dv = desc_sw128(s_u32(sV), 1024, 0);
+        for (int test = 0; test < 6; ++test) {
+            const long long t0 = clock64();
+            if (elect_one()) {
+                if (test == 0) {            // S = Q K^T: N = 192 + 144, 4 k-steps each
+                    for (int k = 0; k < 4; ++k) umma_ss(dq + 2 * k, dk + 2 * k, tmem, k != 0, idesc_f16(128, 192, 0));
+                    for (int k = 0; k < 4; ++k) umma_ss(dq + 2 * k, dk + 8 * (ROWB >> 4) + 2 * k, tmem + 192, k != 0, idesc_f16(128, 144, 0));
+                } else if (test == 1) {     // O = P V: 21 x (N = 64, A from TMEM, B MN-major)
+                    for (int ks = 0; ks < 21; ++ks) umma_ts(tmem + 8 * ks, dv + ks * 128, tmem + 336, ks != 0, idesc_f16(128, 64, 1));
+                } else if (test == 2) {     // O = P V + row sums (N = 16 against a constant tile)
+                    for (int ks = 0; ks < 21; ++ks) {
+                        umma_ts(tmem + 8 * ks, dv + ks * 128, tmem + 336, ks != 0, idesc_f16(128, 64, 1));
+                        umma_ts(tmem + 8 * ks, dk, tmem + 400, ks != 0, idesc_f16(128, 16, 0));
+                    }
+                } else if (test == 3) {     // O = P V with N = 80: V extended by 16 channels would give the sums in the same MMA
+                    for (int ks = 0; ks < 21; ++ks) umma_ts(tmem + 8 * ks, dv + ks * 128, tmem + 336, ks != 0, idesc_f16(128, 64, 1));
+                    for (int ks = 0; ks < 21; ++ks) umma_ts(tmem + 8 * ks, dk, tmem + 400, ks != 0, idesc_f16(128, 16, 0));
+                } else if (test == 4) {     // P as an smem A operand (K-major), V MN-major
+                    for (int ks = 0; ks < 21; ++ks) umma_ss(dq + 2 * (ks & 3), dv + ks * 128, tmem + 336, ks != 0, idesc_f16(128, 64, 1));
+                } else {                    // classifier: 4 x (N = 16, A from TMEM)
+                    for (int k = 0; k < 4; ++k) umma_ts(tmem + 416 + 8 * k, dk + 2 * k, tmem + 448, k != 0, idesc_f16(128, 16, 0));
+                }
+                umma_commit(bars + test);
+            }
+            __syncwarp();
+            const long long t1 = clock64();
+            mbar_wait(bars + test, 0);
+            const long long t2 = clock64();
+            if (lane == 0) { out[2 * test] = t1 - t0; out[2 * test + 1] = t2 - t0; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp < 4) {
+        const uint32_t tq = tmem + ((uint32_t)(warp * 32) << 16);
+        float acc = 0.f;
+        // (a) row by row: ld16 + ld8, wait, consume -- 8 rows, as pass 1 of the softmax
+        long long t0 = clock64();
+        for (int j = 0; j < 8; ++j) {
+            uint32_t r[24];
+            tmem_ld16(tq + j * 24, reinterpret_cast<uint32_t(&)[16]>(r[0]));
+            tmem_ld8(tq + j * 24 + 16, r + 16);
+            tmem_ld_wait();
+            for (int c = 0; c < 22; ++c) acc = fmaxf(acc, __uint_as_float(r[c]));
+        }
+        long long t1 = clock64();
+        if (tid == 0) out[16] = t1 - t0;
+        // (b) the same with the next row's loads in flight while the current row is consumed
+        t0 = clock64();
+        {
+            uint32_t ra[24], rb[24];
+            tmem_ld16(tq, reinterpret_cast<uint32_t(&)[16]>(ra[0])); tmem_ld8(tq + 16, ra + 16);
+            for (int j = 0; j < 8; j += 2) {
+                tmem_ld_wait();
+                tmem_ld16(tq + (j + 1) * 24, reinterpret_cast<uint32_t(&)[16]>(rb[0])); tmem_ld8(tq + (j + 1) * 24 + 16, rb + 16);
+                for (int c = 0; c < 22; ++c) acc = fmaxf(acc, __uint_as_float(ra[c]));
+                tmem_ld_wait();
+                if (j + 2 < 8) { tmem_ld16(tq + (j + 2) * 24, reinterpret_cast<uint32_t(&)[16]>(ra[0])); tmem_ld8(tq + (j + 2) * 24 + 16, ra + 16); }
+                for (int c = 0; c < 22; ++c) acc = fmaxf(acc, __uint_as_float(rb[c]));
+            }
+        }
+        t1 = clock64();
+        if (tid == 0) out[17] = t1 - t0;
+        // (c) one 32-column load + wait, repeated: raw round trip
+        t0 = clock64();
+        for (int j = 0; j < 8; ++j) {
+            uint32_t r[32];
+            tmem_ld32(tq + j * 32, r);
+            tmem_ld_wait();
+            acc += __uint_as_float(r[j]);
+        }
+        t1 = clock64();
+        if (tid == 0) out[18] = t1 - t0;
+        // (d) 176 ex2 + 88 packs per lane (pass 2 arithmetic without TMEM traffic)
+        t0 = clock64();
+        float x = acc * 1e-30f;
+        uint32_t pk = 0;
+        for (int j = 0; j < 88; ++j) {
+            float e0, e1;
+            asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(x + (float)j));
+            asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(x - (float)j));
+            __half2 h = __floats2half2_rn(e0, e1);
+            pk ^= *reinterpret_cast<uint32_t*>(&h);
+        }
+        t1 = clock64();
+        if (tid == 0) out[19] = t1 - t0;
+        // (e) tcgen05.st of 12 columns x 8 rows + wait
+        t0 = clock64();
+        for (int j = 0; j < 8; ++j) {
+            uint32_t r[8] = {pk, pk, pk, pk, pk, pk, pk, pk};
+            tmem_st8(tq + j * 12, r);
+        }
+        tmem_st_wait();
+        t1 = clock64();
+        if (tid == 0) out[20] = t1 - t0;
+        if (acc == 123.f) sink[tid] = acc + (float)pk;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
 static float frand(uint32_t& s) { s = s * 1664525u + 1013904223u; return ((s >> 8) & 0xffff) / 65536.f - 0.5f; }
 
 int main() {
@@ -335,6 +475,22 @@ int main() {
         }
         printf("variant r0=%2d v_lbo=%4d p_swap=%d : max|err| S=%.3e  O=%.3e  L=%.3e   clocks: qk_issue=%lld s_readback=%lld pv_issue=%lld\n",
                v.r0, v.v_lbo, v.p_swap, es, eo, el, hc[0], hc[1], hc[2]);
+    }
+    {
+        long long* dt; float* sink;
+        CK(cudaMalloc(&dt, 64 * 8)); CK(cudaMalloc(&sink, 1024)); CK(cudaMemset(dt, 0, 64 * 8));
+        const size_t tsm = 1024 + 128 * 128 + 2 * RR * ROWB + 512;
+        CK(cudaFuncSetAttribute(time_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+        for (int rep = 0; rep < 2; ++rep) {
+            time_kernel<<<1, 160, tsm>>>(dt, sink);
+            CK(cudaDeviceSynchronize());
+        }
+        long long h[64];
+        CK(cudaMemcpy(h, dt, 64 * 8, cudaMemcpyDeviceToHost));
+        const char* names[6] = {"QK 8 MMAs (N=192,144)", "PV 21 x N=64 TS", "PV+SUM interleaved 42", "PV then SUM 42", "PV 21 x N=64 SS", "CLS 4 x N=16 TS"};
+        for (int i = 0; i < 6; ++i) printf("mma timing %-26s issue %5lld  complete %5lld cycles\n", names[i], h[2 * i], h[2 * i + 1]);
+        printf("tmem: 8 rows ld24+wait+max %lld | double-buffered %lld | 8 x (ld32+wait) %lld | 176 ex2 + 88 pack %lld | 8 x st8 + wait %lld cycles\n",
+               h[16], h[17], h[18], h[19], h[20]);
     }
     return 0;
 }
