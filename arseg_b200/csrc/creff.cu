@@ -322,6 +322,7 @@ int creff_mma_launch(const arseg_creff_args* a, cudaStream_t st);
 bool creff_wide_supported(const arseg_creff_args* a);                                   // creff_wide.cu
 int creff_wide_launch(const arseg_creff_args* a, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t creff_wide_workspace_bytes(int N, int C, int H, int W);
+size_t creff_tc_workspace_bytes(int N, int H, int W);                                   // creff_tc.cu
 
 }  // namespace arseg
 
@@ -372,6 +373,8 @@ extern "C" int arseg_creff_fused_fwd(const arseg_creff_args* a, arseg_stream_t s
 }
 
 extern "C" size_t arseg_creff_workspace_bytes(const arseg_creff_args* a) {
-    if (!a || a->engine != ARSEG_CREFF_MMA_F16 || !creff_wide_supported(a)) return 0;
+    if (!a || a->engine != ARSEG_CREFF_MMA_F16) return 0;
+    if (a->C == 64 && a->hr_dtype == ARSEG_F16) return creff_tc_workspace_bytes(a->N, a->H, a->W);   // per-pixel gather records
+    if (!creff_wide_supported(a)) return 0;
     return creff_wide_workspace_bytes(a->N, a->C, a->H, a->W);
 }

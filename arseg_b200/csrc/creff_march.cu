@@ -907,7 +907,7 @@ bool creff_mma_supported(const arseg_creff_args* a) {
            (!a->wcls || a->ncls <= 32) && ((size_t)a->H * a->W < (1u << 29)) && ((size_t)a->h * a->w < (1u << 29));
 }
 
-int creff_tc_launch(CreffMmaParams& p, int k, cudaStream_t st);   // creff_tc.cu
+int creff_tc_launch(CreffMmaParams& p, int k, void* ws, size_t ws_bytes, cudaStream_t st);   // creff_tc.cu
 
 // ARSEG_CREFF_MMA_F16 at C = 64: f16 keyframe feature + f16 LR feature -> the tcgen05 engine (creff_tc.cu, k <= 7);
 // fp32 keyframe feature -> the column-marching mma.sync engine of this file (any LR dtype, k <= 9).
@@ -921,7 +921,7 @@ int creff_mma_launch(const arseg_creff_args* a, cudaStream_t st) {
     if (a->hr_dtype == ARSEG_F16) {
         if (a->lr_dtype != ARSEG_F16 || a->k > 7)
             ARSEG_UNSUPPORTED("creff: an f16 keyframe feature selects the tcgen05 engine, which needs an f16 LR feature and k <= 7 (lr dtype %d, k = %d)", a->lr_dtype, a->k);
-        return creff_tc_launch(p, a->k, st);
+        return creff_tc_launch(p, a->k, a->workspace, a->workspace_bytes, st);
     }
     return creff_march_launch(p, a->k, a->lr_dtype, st);
 }

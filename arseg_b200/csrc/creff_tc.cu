@@ -18,25 +18,28 @@
 //     goes back to TMEM as f16 and is the A operand of the classifier MMA.
 //   * Producer roles as in the march engine, handing rows over through mbarriers:
 //       G (6 warps): bilinear gather of the MV-warped keyframe rows and the lr_up rows (quarter-warp per position,
-//                    8 channels = 16 bytes per lane, f16 sources) into f16 row rings;
-//       D (5 warps): depthwise 3x3 convolutions (FFMA2): two K warps, two V warps (4 rows x half the columns each),
-//                    one Q warp; K, V -> rings, Q -> the A tile;
-//       M (1 warp):  the single MMA-issuing thread;
-//       C (4 warps): softmax, residual, log-softmax / argmax, stores.
+//                    8 channels = 16 bytes per lane, f16 sources, mixed-precision FHFMA) into f16 row rings;
+//       D (6 warps): depthwise 3x3 convolutions (FFMA2): two K warps, two V warps (4 rows x half the columns each),
+//                    two Q warps; K, V -> rings, Q -> the A tile;
+//       M (1 warp):  MMA issue (one elected lane);
+//       S (4 warps): softmax: S -> P in tensor memory;
+//       E (4 warps): residual, classifier input, log-softmax / argmax, stores -- one tile behind S.
 #include "creff_mma_common.cuh"
 #include <cstdlib>
 
 namespace arseg {
 
 constexpr int TSW = 16;                    // strip width (pixels)
-constexpr int TTHREADS = 512;
-// The hardware arbiter prefers the highest warp id of a scheduler: the latency-critical chain (M -> C -> M) gets the top ids.
-// FMA-pipe work per tile and warp: Q 80k lane-ops, K / V 60k each, G 15-30k, C 13k -- the two heaviest (a K warp and the Q
-// warp) must not share a scheduler (warp id % 4): D = warps 0..3 (K K V V) and 7 (Q), G = warps 4, 5, 6, 8, 9, 10.
-constexpr int TD_WARPS = 5, TQ_WARP = 7;
-constexpr int TG_WARPS = 6;
+// 20 warps, no register re-balancing (640 threads x 96 registers).  Scheduler = warp id % 4 = TMEM lane quarter.  The roles are
+// spread so that the FMA-pipe work of a tile (K / V warp 60k lane-ops, Q half 40k, G 18k, S + E 13k) is even across the four
+// schedulers, and the latency-critical chain M -> S -> M -> E has the highest warp ids (the arbiter prefers them):
+//   0 K0  1 K1  2 V0  3 V1 | 4 G0  5 G1  6 Qa  7 Qb | 8 G2  9 G3  10 G4  11 M | 12..15 E | 16..19 S
+constexpr int TTHREADS = 640;
+constexpr int TD_WARPS = 6;                // K0 K1 V0 V1 Qa Qb
+constexpr int TQ_WARP0 = 6;                // warps 6, 7: the two column halves of Q
+constexpr int TG_WARPS = 5;                // warps 4, 5, 8, 9, 10
 constexpr int TM_WARP = 11;                // MMA issuer (and TMEM allocator)
-constexpr int TC_W0 = 12, TC_WARPS = 4;    // warps 12..15: TMEM lane quarter = warp % 4
+constexpr int TE_W0 = 12, TS_W0 = 16, TC_WARPS = 4;   // epilogue warps 12..15, softmax warps 16..19 (lane quarter = warp % 4)
 constexpr int TG_THREADS = 32 * TG_WARPS;
 constexpr int TNQW = 4 * TG_WARPS;         // gather quarter-warps: one position each per slot
 constexpr int TJA = 4;                     // gather positions in flight per quarter-warp
@@ -69,16 +72,17 @@ template <int K> struct TCfg {
     static constexpr size_t HR_BYTES = (size_t)THRR * HC * 128;
     static constexpr size_t LR_BYTES = (size_t)TLRR * TLC * 128;
     static constexpr size_t SCRATCH_BYTES = 128;
-    static constexpr size_t REC_BYTES = (size_t)2 * PMAX * 32;     // double-buffered {float4 weights, uint4 address}
+    static constexpr size_t REC_BYTES = (size_t)2 * PMAX * 16;     // double-buffered gather records (uint4)
     static constexpr size_t SMEM = 1024 + 2 * KV_BYTES + Q_BYTES + W_BYTES + ONES_BYTES + HR_BYTES + LR_BYTES + SCRATCH_BYTES + REC_BYTES +
-                                   TNCLS * 4 + 9 * TNB * 8 + 16;
+                                   TNCLS * 4 + 10 * TNB * 8 + 16;
     static_assert(KVC <= TKP, "window too wide for the key pitch");
     static_assert(NKR % 2 == 0 && KVR % 2 == 0 && PADR % 2 == 0, "even row counts: a 16-key MMA step never straddles the ring end");
     static_assert(COL_L + TNCLS <= 512, "tensor memory columns");
-    static_assert(PMAX <= TG_THREADS, "one gather record per G thread");
-    static_assert(TC_W0 % 4 == 0 && TC_W0 + TC_WARPS == TTHREADS / 32, "C = the last warpgroup (setmaxnreg, TMEM lane quarters)");
+    static_assert(PMAX <= 2 * TG_THREADS && 4 * HC <= TG_THREADS, "at most two gather records per G thread, the MV-dependent ones in the first pass");
     static_assert(SMEM <= 232448, "shared memory budget");
 };
+
+size_t creff_tc_workspace_bytes(int N, int H, int W) { return (size_t)(N + 1) * H * W * sizeof(uint4); }
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -110,8 +114,8 @@ __device__ __noinline__ void tbar_timeout(int tag, int idx) {
 // spends in tbar_wait per barrier tag, [15] = cycles of its whole role; read back with arseg_debug_creff_tc_trace().
 #ifdef ARSEG_TTRACE
 constexpr int TTRACE_CTA = 148 * 3 + 11;
-__device__ long long g_ttrace[16 * 16];
-__device__ long long g_tev[2 * 64 * 12];     // [M | C0][tile][event] clock64 stamps
+__device__ long long g_ttrace[32 * 16];
+__device__ long long g_tev[3 * 64 * 12];     // [M | S0 | E0][tile][event] clock64 stamps
 __device__ __forceinline__ void tev(int role, int tile, int ev) {
     if (blockIdx.x == TTRACE_CTA && (threadIdx.x & 31) == 0 && tile < 64) g_tev[(role * 64 + tile) * 12 + ev] = clock64();
 }
@@ -143,7 +147,10 @@ __device__ __forceinline__ void tbar_wait(uint64_t* bars, int idx, int tag = 0) 
 #endif
             return;
         }
+        // a polling warp takes issue slots from the working ones (S / E poll for most of a tile and have the highest
+        // scheduling priority): back off -- a few immediate polls for the short hand-offs, then sleep
         if (SLEEP) __nanosleep(spin < 4 ? 32 : 128);
+        else if (spin >= 8) __nanosleep(spin < 64 ? 40 : 100);
     }
     tbar_timeout(tag, idx);
 }
@@ -230,10 +237,9 @@ __device__ __forceinline__ uint4 t_ldg128(const char* p) { return __ldg(reinterp
 
 struct TSmem {
     uint32_t sK, sV, sQ, sW, sOnes, rings;       // shared-window addresses; rings = hr ring, lr ring, scratch
-    float4* posw;                                // [2][PMAX]
-    uint4* posa;                                 // [2][PMAX]
+    uint4* posa;                                 // [2][PMAX] gather records: {w0 | w1 << 16, w2 | w3 << 16 (f16), source pixel | lr << 31, ring offset | swizzle << 28}
     float* s_bc;                                 // [TNCLS]
-    uint64_t *gfull /* index g + 1 */, *ddone, *lrfree, *sfull, *pfull, *ofull, *afull, *lfull;
+    uint64_t *gfull /* index g + 1 */, *ddone, *lrfree, *sfull, *pfull, *ofull, *ofree, *afull, *lfull;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -251,88 +257,86 @@ __device__ __forceinline__ void t_step_geom(int g, int& h0, int& nh, int& l0, in
     else { l0 = 0; nl = 0; }
 }
 
-template <int K, bool MVF>
-__device__ __forceinline__ void t_g_role(const CreffMmaParams& p, const TSmem& sm, int n, int x0, int ya, int NH, int S) {
+// The per-position gather records (2x2 source block + four bilinear weights; for the keyframe feature this is the f64 MV
+// arithmetic of evaluation.py:177-183 + the grid_sample geometry of :61-87) are computed once per pixel by
+// creff_tc_rec_kernel into the caller's workspace; the G warps only copy the records of the next step into shared memory
+// (one 16-byte load per thread, in flight during the gather loop) and stream the taps.
+template <int K>
+__device__ __forceinline__ void t_g_role(const CreffMmaParams& p, const TSmem& sm, const uint4* __restrict__ rec, int n, int x0, int ya, int NH, int S) {
     using Cf = TCfg<K>;
-    const int gw = (int)(threadIdx.x >> 5), gi = gw < TQ_WARP ? gw - 4 : gw - 5;     // gather warp index 0..5
+    const int gw = (int)(threadIdx.x >> 5), gi = gw < TQ_WARP0 ? gw - 4 : gw - 6;    // gather warp index 0..4 (warps 4, 5, 8, 9, 10)
     const int gt = gi * 32 + (int)(threadIdx.x & 31), lane = gt & 31, qw = gt >> 3, l8 = lane & 7;
-    const float lsh = resize_scale(p.h, p.H, ARSEG_RESIZE_BILINEAR_AC), lsw = resize_scale(p.w, p.W, ARSEG_RESIZE_BILINEAR_AC);
     const char* const hrb = reinterpret_cast<const char*>(p.hr) + (p.hr_shared ? (size_t)0 : (size_t)n * p.H * p.W * 128);
     const char* const lrb = reinterpret_cast<const char*>(p.lr) + (size_t)n * p.h * p.w * 128;
-    const double rcp_w = 2.0 / (double)max(p.W - 1, 1), rcp_h = 2.0 / (double)max(p.H - 1, 1);
     const uint32_t hr_rs = (uint32_t)p.W * 128, lr_rs = (uint32_t)p.w * 128;
     constexpr uint32_t SCRATCH_OFF = (uint32_t)(Cf::HR_BYTES + Cf::LR_BYTES);
-    const int* const mvp = reinterpret_cast<const int*>(p.flow) + (size_t)n * p.H * p.W;
+    const uint4* const rec_hr = rec + (size_t)n * p.H * p.W;           // [N][H][W]
+    const uint4* const rec_lr = rec + (size_t)p.N * p.H * p.W;         // [H][W] (frame independent)
 
-    // the int16 MV pair of this thread's hr position of step g (loaded one step ahead of its record)
-    auto mv_of = [&](int g) -> int {
-        int h0, nh, l0, nl;
-        t_step_geom<K>(g, h0, nh, l0, nl);
-        if (!MVF || gt >= nh * Cf::HC) return 0;
-        const int rr = gt / Cf::HC, cc = gt - rr * Cf::HC;
-        const int fy = ya - Cf::R - Cf::PADR - 1 + h0 + rr, fx = x0 - Cf::R - 1 + cc;
-        return (fy >= 0 && fy < p.H && fx >= 0 && fx < p.W) ? __ldg(mvp + (size_t)fy * p.W + fx) : 0;
-    };
-    // gather record q of step g (one per G thread): posw = the 2x2 block's weights; posa = {block address (64 bit), row
-    // stride, ring byte offset of the destination position | (column & 7) << 28 for the lr ring's chunk swizzle}.
-    // Padded with no-op records (zero weights, scratch destination) to NJ positions per quarter-warp.
-    auto compute_pos = [&](int g, int mv) {
+    // record slot q of step g: destination ring offset and the global record it copies (nullptr: a zero record -- positions
+    // outside the image are the depthwise convolutions' zero padding; slots beyond the step's positions are no-ops)
+    auto slot_of = [&](int g, int q, uint32_t& dst) -> const uint4* {
         int h0, nh, l0, nl;
         t_step_geom<K>(g, h0, nh, l0, nl);
         const int nhp = nh * Cf::HC, npos = nhp + nl * TLC;
-        const int q = gt;
-        if (q >= Cf::PMAX) return;
-        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-        const char* src = hrb;
-        uint32_t rs = hr_rs, dst = SCRATCH_OFF;
+        dst = SCRATCH_OFF;
         if (q < nhp) {
             const int rr = q / Cf::HC, cc = q - rr * Cf::HC, row = h0 + rr;
             const int fy = ya - Cf::R - Cf::PADR - 1 + row, fx = x0 - Cf::R - 1 + cc;
-            const PosRec r = pos_hr<true>(p, n, fy, fx, rcp_w, rcp_h, MVF ? &mv : nullptr);
             dst = (uint32_t)(((row % THRR) * Cf::HC + cc) * 128);
-            if (r.info >= 0) {
-                int bx, by;
-                rec_block_of(r, p.W, p.H, w, bx, by);
-                src = hrb + ((size_t)by * p.W + bx) * 128;
-            }
-        } else if (q < npos) {
+            return (fy >= 0 && fy < p.H && fx >= 0 && fx < p.W) ? rec_hr + (size_t)fy * p.W + fx : nullptr;
+        }
+        if (q < npos) {
             const int q2 = q - nhp, rr = q2 / TLC, cc = q2 - rr * TLC, row = l0 + rr;
-            const PosRec r = pos_lr(p, lsh, lsw, ya - 1 + row, x0 - 1 + cc);
+            const int fy = ya - 1 + row, fx = x0 - 1 + cc;
             dst = (uint32_t)(Cf::HR_BYTES + ((row % TLRR) * TLC + cc) * 128) | ((uint32_t)(cc & 7) << 28);
-            if (r.info >= 0) {
-                int bx, by;
-                rec_block_of(r, p.w, p.h, w, bx, by);
-                src = lrb + ((size_t)by * p.w + bx) * 128;
-                rs = lr_rs;
+            return (fy >= 0 && fy < p.H && fx >= 0 && fx < p.W) ? rec_lr + (size_t)fy * p.W + fx : nullptr;
+        }
+        return nullptr;
+    };
+    constexpr int NR = (Cf::PMAX + TG_THREADS - 1) / TG_THREADS;       // records per thread and step (<= 2)
+    uint4 rnext[NR];
+    uint32_t dnext[NR];
+    auto fetch = [&](int g) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const int q = gt + r * TG_THREADS;
+            rnext[r] = make_uint4(0u, 0u, 0u, 0u);
+            dnext[r] = SCRATCH_OFF;
+            if (q < Cf::PMAX) {
+                const uint4* src = slot_of(g, q, dnext[r]);
+                if (src) rnext[r] = __ldg(src);
             }
         }
+    };
+    auto publish = [&](int g) {
         const int buf = (g + 1) & 1;
-        sm.posw[buf * Cf::PMAX + q] = w;
-        const unsigned long long a = reinterpret_cast<unsigned long long>(src);
-        sm.posa[buf * Cf::PMAX + q] = make_uint4((uint32_t)a, (uint32_t)(a >> 32), rs, dst);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const int q = gt + r * TG_THREADS;
+            if (q < Cf::PMAX) sm.posa[buf * Cf::PMAX + q] = make_uint4(rnext[r].x, rnext[r].y, rnext[r].z, dnext[r]);
+        }
     };
     uint4 tap[TJA][4];
     auto issue = [&](uint4 (&tp)[4], int buf, int j) {
         const uint4 id = sm.posa[buf * Cf::PMAX + qw + TNQW * j];
-        const char* a0 = reinterpret_cast<const char*>(((unsigned long long)id.y << 32) | id.x) + 16 * l8;
-        const char* a1 = a0 + id.z;
+        const bool lr = (id.z >> 31) != 0;
+        const char* a0 = (lr ? lrb : hrb) + (size_t)(id.z & 0x7fffffffu) * 128 + 16 * l8;
+        const char* a1 = a0 + (lr ? lr_rs : hr_rs);
         tp[0] = t_ldg128(a0);
         tp[1] = t_ldg128(a0 + 128);
         tp[2] = t_ldg128(a1);
         tp[3] = t_ldg128(a1 + 128);
     };
     auto commit = [&](const uint4 (&tp)[4], int buf, int j) {
-        const int i = buf * Cf::PMAX + qw + TNQW * j;
-        const float4 w = sm.posw[i];
-        const uint32_t d = sm.posa[i].w;
+        const uint4 id = sm.posa[buf * Cf::PMAX + qw + TNQW * j];
         const uint32_t* t0 = reinterpret_cast<const uint32_t*>(&tp[0]);
         const uint32_t* t1 = reinterpret_cast<const uint32_t*>(&tp[1]);
         const uint32_t* t2 = reinterpret_cast<const uint32_t*>(&tp[2]);
         const uint32_t* t3 = reinterpret_cast<const uint32_t*>(&tp[3]);
         // mixed-precision FMA (f16 x f16 + f32 -> f32, SASS FHFMA): the taps are consumed as they are, no f16 -> f32 conversions;
-        // the bilinear weights are rounded to f16 (<= 2^-12 relative, below the f16 rounding of the result itself)
-        const uint16_t w0 = __half_as_ushort(__float2half_rn(w.x)), w1 = __half_as_ushort(__float2half_rn(w.y));
-        const uint16_t w2 = __half_as_ushort(__float2half_rn(w.z)), w3 = __half_as_ushort(__float2half_rn(w.w));
+        // the bilinear weights are f16 (<= 2^-12 relative, below the f16 rounding of the result itself)
+        const uint16_t w0 = (uint16_t)(id.x & 0xffffu), w1 = (uint16_t)(id.x >> 16), w2 = (uint16_t)(id.y & 0xffffu), w3 = (uint16_t)(id.y >> 16);
         uint32_t o[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -343,42 +347,41 @@ __device__ __forceinline__ void t_g_role(const CreffMmaParams& p, const TSmem& s
             t_fhfma(vx, (uint16_t)(t3[e] & 0xffffu), w3); t_fhfma(vy, (uint16_t)(t3[e] >> 16), w3);
             o[e] = pack_h2_sat(vx, vy);
         }
+        const uint32_t d = id.w;
         t_sts128(sm.rings + (d & 0x0fffffffu) + (((uint32_t)l8 ^ (d >> 28)) << 4), make_uint4(o[0], o[1], o[2], o[3]));
     };
 
-    int mv_next = mv_of(-1);
-    // trip g = -2 only computes the records of step -1 (one instance of the record code: instruction-cache footprint)
+    fetch(-1);
+    publish(-1);
+    nbar_sync(TBAR_G, TG_THREADS);
 #pragma unroll 1
-    for (int g = -2; g < NH; ++g) {
+    for (int g = -1; g < NH; ++g) {
         const int buf = (g + 1) & 1;
-        const int mv_cur = mv_next;
-        if (g >= -1) {
-            // rolling pipeline: TJA positions' loads are always in flight while the oldest one is combined and stored
+        // rolling pipeline: TJA positions' loads are always in flight while the oldest one is combined and stored
 #pragma unroll
-            for (int j = 0; j < TJA; ++j) issue(tap[j], buf, j);
-            mv_next = g + 1 < NH ? mv_of(g + 1) : 0;                    // in flight during the gather loop
-            if (g >= 2) tbar_wait<true>(sm.ddone, g - 2, 2);                  // D half-step g-2 done: the hr / lr rows this step overwrites are read
-            {
-                // lr_up rows double as the residual: C takes the rows of tile i at the start of its step
-                const int num = 4 * (g - Cf::HP) + 5 - TLRR - 1;        // last overwritten lr row - 1
-                if (num >= 0) { const int im = num >> 3; tbar_wait<true>(sm.lrfree, im < S - 1 ? im : S - 1, 3); }
-            }
+        for (int j = 0; j < TJA; ++j) issue(tap[j], buf, j);
+        if (g + 1 < NH) fetch(g + 1);                               // the next step's records: in flight during the gather loop
+        if (g >= 2) tbar_wait<true>(sm.ddone, g - 2, 2);            // D half-step g-2 done: the hr / lr rows this step overwrites are read
+        {
+            // lr_up rows double as the residual: E takes the rows of tile i at the start of its step
+            const int num = 4 * (g - Cf::HP) + 5 - TLRR - 1;        // last overwritten lr row - 1
+            if (num >= 0) { const int im = num >> 3; tbar_wait<true>(sm.lrfree, im < S - 1 ? im : S - 1, 3); }
+        }
 #ifdef ARSEG_TTRACE
-            if (!(p.dbg & 4))
+        if (!(p.dbg & 4))
 #endif
 #pragma unroll 1
-            for (int j0 = 0; j0 < Cf::NJ; j0 += TJA) {
+        for (int j0 = 0; j0 < Cf::NJ; j0 += TJA) {
 #pragma unroll
-                for (int j = 0; j < TJA; ++j) {
-                    if (j0 + j < Cf::NJ) {
-                        commit(tap[j], buf, j0 + j);
-                        if (j0 + j + TJA < Cf::NJ) issue(tap[j], buf, j0 + j + TJA);
-                    }
+            for (int j = 0; j < TJA; ++j) {
+                if (j0 + j < Cf::NJ) {
+                    commit(tap[j], buf, j0 + j);
+                    if (j0 + j + TJA < Cf::NJ) issue(tap[j], buf, j0 + j + TJA);
                 }
             }
-            tbar_arrive(sm.gfull, g + 1);
         }
-        if (g + 1 < NH) compute_pos(g + 1, g >= -1 ? mv_next : mv_cur);
+        tbar_arrive(sm.gfull, g + 1);
+        if (g + 1 < NH) publish(g + 1);
         nbar_sync(TBAR_G, TG_THREADS);                              // records of step g+1 visible; everyone is done with those of step g-1
     }
 }
@@ -404,7 +407,7 @@ __device__ __forceinline__ int t_kv_last_reader(int h) {
 template <int K>
 __device__ __forceinline__ void t_d_role(const CreffMmaParams& p, const TSmem& sm, int x0, int ya, int NH, int S) {
     using Cf = TCfg<K>;
-    const int lane = threadIdx.x & 31, d = (threadIdx.x >> 5) == TQ_WARP ? 4 : (int)(threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31, dw = (int)(threadIdx.x >> 5), d = dw >= TQ_WARP0 ? 4 : dw, qhalf = dw - TQ_WARP0;
     const uint32_t lane_sub = (uint32_t)((lane & 3) * 4), lane_chunk = (uint32_t)(lane >> 2);
     if (d < 4) {
         // ---------------- K (d = 0, 1) or V (d = 2, 3): columns [c_lo, c_lo + ncol) of four K/V rows per half-step ----------------
@@ -493,17 +496,19 @@ __device__ __forceinline__ void t_d_role(const CreffMmaParams& p, const TSmem& s
 #pragma unroll
                 for (int i = 0; i < 6; ++i) ra[i] = lbase + (uint32_t)(((q0 + i) % TLRR) * (TLC * 128));
                 const uint32_t qo = sm.sQ + (uint32_t)(qy0 * TSW * 128);
+                // this warp's column half: output columns [8 qhalf, 8 qhalf + 8) from lr ring columns [8 qhalf, 8 qhalf + 10)
+                const int xlo = 8 * qhalf;
                 float2 win[6][3];
 #pragma unroll
                 for (int c = 0; c < 2; ++c)
 #pragma unroll
-                    for (int i = 0; i < 6; ++i) win[i][c] = t_h2f(t_lds32(ra[i] + c * 128 + lx[c]));
+                    for (int i = 0; i < 6; ++i) win[i][c] = t_h2f(t_lds32(ra[i] + (xlo + c) * 128 + lx[c]));     // (xlo + c) & 7 = c
 #pragma unroll 1
-                for (int x3 = 0; x3 < TSW; x3 += 3) {
+                for (int x3 = 0; x3 < TSW / 2; x3 += 3) {
 #pragma unroll
                     for (int u = 0; u < 3; ++u) {
-                        const int x = x3 + u;
-                        if (x < TSW) {
+                        if (x3 + u < TSW / 2) {
+                            const int x = xlo + x3 + u;
                             const int sa = u, sb = (u + 1) % 3, sc = (u + 2) % 3;
                             const uint32_t lin = (uint32_t)((x + 2) * 128) + (((lane_chunk ^ (uint32_t)((x + 2) & 7)) << 4) + lane_sub);
 #pragma unroll
@@ -532,23 +537,21 @@ __device__ __forceinline__ void t_d_role(const CreffMmaParams& p, const TSmem& s
 template <int K>
 __device__ __forceinline__ void t_issue_qk(const TSmem& sm, uint32_t tmem, int i) {
     using Cf = TCfg<K>;
-    // key rows [8i + PADR, + NKR) of the ring in chunks of <= 8 rows that do not cross the ring end (N = 24 * rows <= 192)
+    // key rows [8i + PADR, + NKR) of the ring, TWO rows (N = 48) per MMA: the same instruction shapes for every tile whatever
+    // the ring phase (chunks never straddle the ring end: even row counts), so a pixel's logits do not depend on which tile
+    // of which row segment computes them (bit-exact results across segmentations / frame counts)
     const int b0 = (8 * i + Cf::PADR) % Cf::KVR;
     const uint64_t dq = t_desc(sm.sQ), dk = t_desc(sm.sK);
-    int done = 0;
+    constexpr uint32_t ID = t_idesc(2 * TKP, 0);
+    constexpr uint32_t RING16 = (uint32_t)(Cf::KVR * TROWB) >> 4;
+    uint32_t off = (uint32_t)(b0 * (TROWB >> 4)), td = tmem;
 #pragma unroll 1
-    while (done < Cf::NKR) {
-        int rs = b0 + done;
-        rs = rs >= Cf::KVR ? rs - Cf::KVR : rs;
-        int nr = Cf::NKR - done;
-        nr = nr > 8 ? 8 : nr;
-        nr = rs + nr > Cf::KVR ? Cf::KVR - rs : nr;
-        const uint32_t id = t_idesc(nr * TKP, 0);
-        const uint64_t dkr = dk + (uint64_t)(rs * (TROWB >> 4));
-        const uint32_t td = tmem + (uint32_t)(done * TKP);
+    for (int r = 0; r < Cf::NKR; r += 2) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) t_mma_ss(dq + (uint64_t)(2 * k), dkr + (uint64_t)(2 * k), td, k != 0, id);
-        done += nr;
+        for (int k = 0; k < 4; ++k) t_mma_ss(dq + (uint64_t)(2 * k), dk + off + (uint64_t)(2 * k), td, k != 0, ID);
+        off += 2 * (TROWB >> 4);
+        off = off >= RING16 ? off - RING16 : off;
+        td += 2 * TKP;
     }
 }
 template <int K>
@@ -585,11 +588,13 @@ __device__ __forceinline__ bool t_elect() {
 }
 
 // The whole warp runs the control flow (warp-uniform operands live in uniform registers, which tcgen05.mma reads
-// directly); one elected lane issues.
+// directly); one elected lane issues.  Per tile: S = Q K^T -> (softmax warps) -> O = P V; then, in whichever order they
+// become possible, the classifier MMA of this tile (after the epilogue warps have written its input) and S of the NEXT
+// tile (its columns are free once P V has been issued -- the tensor pipe runs in order).
 template <int K, int NCP>
-__device__ __forceinline__ void t_m_role(const TSmem& sm, uint32_t tmem, int S) {
+__device__ __forceinline__ void t_m_role(const TSmem& sm, uint32_t tmem, int S, int dbg) {
     using Cf = TCfg<K>;
-    bool qk_ahead = false;          // S of the next tile already issued
+    bool qk_ahead = false;          // S of this tile already issued
 #pragma unroll 1
     for (int i = 0; i < S; ++i) {
         if (!qk_ahead) {
@@ -602,37 +607,152 @@ __device__ __forceinline__ void t_m_role(const TSmem& sm, uint32_t tmem, int S) 
         }
         qk_ahead = false;
         tbar_wait(sm.pfull, i, 7);                                   // P is in tensor memory
+        if (i >= 1) tbar_wait(sm.ofree, i - 1, 12);                  // the epilogue warps have read O of the previous tile
         TEV(0, i, 2);
         t_fence_after();
         if (t_elect()) { t_issue_pv<K>(sm, tmem, i); t_commit(sm.ofull, i); }
         __syncwarp();
         TEV(0, i, 3);
-        if (NCP > 0) {
-            tbar_wait(sm.afull, i, 8);                               // residual + O / sum is back in tensor memory (f16)
-            TEV(0, i, 4);
-            t_fence_after();
-            if (t_elect()) { t_issue_cls<K, NCP>(sm, tmem); t_commit(sm.lfull, i); }
-            __syncwarp();
-            TEV(0, i, 5);
-        }
-        // the S columns are free once P V has been issued (the tensor pipe runs in order): start the next tile's S early
-        if (i + 1 < S && tbar_test(sm.ddone, 2 * (i + 1) + Cf::HP + 1)) {
-            t_fence_after();
-            if (t_elect()) { t_issue_qk<K>(sm, tmem, i + 1); t_commit(sm.sfull, i + 1); }
-            __syncwarp();
-            qk_ahead = true;
+        bool need_cls = NCP > 0, need_qk = i + 1 < S;
+#ifdef ARSEG_TTRACE
+        if (dbg & 8) { need_qk = false; if (i >= 0) tbar_wait(sm.ofree, i, 12); }     // no overlap between tiles (debugging)
+#endif
+#pragma unroll 1
+        for (int spin = 0; need_cls || need_qk; ++spin) {
+            if (need_cls && tbar_test(sm.afull, i)) {                // residual + O / sum is back in tensor memory (f16)
+                TEV(0, i, 4);
+                t_fence_after();
+                if (t_elect()) { t_issue_cls<K, NCP>(sm, tmem); t_commit(sm.lfull, i); }
+                __syncwarp();
+                TEV(0, i, 5);
+                need_cls = false;
+            }
+            if (need_qk && tbar_test(sm.ddone, 2 * (i + 1) + Cf::HP + 1)) {
+                t_fence_after();
+                if (t_elect()) { t_issue_qk<K>(sm, tmem, i + 1); t_commit(sm.sfull, i + 1); }
+                __syncwarp();
+                need_qk = false;
+                qk_ahead = true;
+            }
+            if (spin > (1 << 22)) tbar_timeout(13, i);
+            if (spin >= 8) __nanosleep(40);
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// C role: softmax, residual, classifier epilogue.  Warp w owns TMEM lanes 32w .. 32w+31 = query rows 2w, 2w+1.
+// S role: softmax.  Warp of lane quarter cw owns TMEM lanes 32cw .. 32cw+31 = query rows 2cw, 2cw+1 of the tile.
 // ---------------------------------------------------------------------------------------------
-template <int K, int NCP>
-__device__ __forceinline__ void t_c_role(const CreffMmaParams& p, const TSmem& sm, uint32_t tmem, int n, int x0, int ya, int yb, int S) {
+__device__ __forceinline__ void t_ld_row(uint32_t ta, uint32_t* s) { t_ld16(ta, s); t_ld8(ta + 16, s + 16); }
+
+template <int K>
+__device__ __forceinline__ void t_s_role(const TSmem& sm, uint32_t tmem, int S) {
     using Cf = TCfg<K>;
     constexpr float LOG2E = 1.4426950408889634f;
-    const int lane = threadIdx.x & 31, cw = (threadIdx.x >> 5) - TC_W0;
+    static_assert((K + 1) % 2 == 0, "the row loops are unrolled by two");
+    const int lane = threadIdx.x & 31, cw = (int)(threadIdx.x >> 5) & 3;
+    const int b = lane >> 4, qx = lane & 15;
+    const uint32_t tq = tmem + ((uint32_t)(32 * cw) << 16);
+    // cbm[c]: the column mask of this lane's window (key column c is inside iff qx <= c < qx + K), kept in ONE register array:
+    // 0 / -inf during pass 1 (max of s + cbm), -max * log2(e) / -inf during pass 2 (ex2(s * log2e + cbm)); "+= ml" after pass 2
+    // restores exact zeros (-ml + ml), so a tile's arithmetic does not depend on the tiles before it (bit-exact row segments).
+    float cbm[Cf::KVC];
+#pragma unroll
+    for (int c = 0; c < Cf::KVC; ++c) cbm[c] = ((unsigned)(c - qx) < (unsigned)K) ? 0.f : -INFINITY;
+    // the warp reads key rows 2cw .. 2cw + K of the tile; the first is outside the window of its odd query row, the last outside that of the even one
+    const float rb_first = b ? -INFINITY : 0.f, rb_last = b ? 0.f : -INFINITY;
+    const uint32_t srow = tq + (uint32_t)(2 * cw * TKP);            // S columns of the warp's first key row
+    const uint32_t prow = tq + (uint32_t)(2 * cw * (TKP / 2));      // P columns of the warp's first key row
+
+    auto rowmax = [&](const uint32_t* s) -> float {
+        float m0 = -INFINITY, m1 = -INFINITY;                       // two chains
+#pragma unroll
+        for (int c = 0; c < Cf::KVC; c += 2) {
+            m0 = fmaxf(m0, __uint_as_float(s[c]) + cbm[c]);
+            if (c + 1 < Cf::KVC) m1 = fmaxf(m1, __uint_as_float(s[c + 1]) + cbm[c + 1 < Cf::KVC ? c + 1 : c]);
+        }
+        return fmaxf(m0, m1);
+    };
+    auto exprow = [&](const uint32_t* s, int j) {
+        const uint32_t keep = ((j == 0 && b) || (j == K && !b)) ? 0u : 0xffffffffu;
+        uint32_t pk[12];
+#pragma unroll
+        for (int c = 0; c < 24; c += 2) {
+            if (c < Cf::KVC) {
+                const float e0 = t_ex2(fmaf(__uint_as_float(s[c]), LOG2E, cbm[c]));
+                const float e1 = c + 1 < Cf::KVC ? t_ex2(fmaf(__uint_as_float(s[c + 1]), LOG2E, cbm[c + 1 < Cf::KVC ? c + 1 : c])) : 0.f;
+                pk[c >> 1] = pack_h2(e0, e1) & keep;
+            } else {
+                pk[c >> 1] = 0u;
+            }
+        }
+        t_st8(prow + j * (TKP / 2), pk);
+        t_st4(prow + j * (TKP / 2) + 8, pk[8], pk[9], pk[10], pk[11]);
+    };
+
+#pragma unroll 1
+    for (int i = 0; i < S; ++i) {
+        tbar_wait(sm.sfull, i, 9);
+        if (cw == 0) TEV(1, i, 1);
+        t_fence_after();
+        // ---------------- pass 1: the shift of the maximum (the next row's TMEM load is in flight while a row is reduced) ----------------
+        uint32_t sa[24], sb[24];
+        float d = -INFINITY;
+        t_ld_row(srow, sa);
+#pragma unroll 1
+        for (int j = 0; j <= K; j += 2) {
+            t_ld_wait();
+            t_ld_row(srow + (j + 1) * TKP, sb);
+            d = fmaxf(d, rowmax(sa) + (j == 0 ? rb_first : 0.f));
+            t_ld_wait();
+            if (j + 2 <= K) t_ld_row(srow + (j + 2) * TKP, sa); else t_ld_row(srow, sa);      // last trip: row 0 again, for pass 2
+            d = fmaxf(d, rowmax(sb) + (j + 1 == K ? rb_last : 0.f));
+        }
+        const float ml = d * LOG2E;
+#pragma unroll
+        for (int c = 0; c < Cf::KVC; ++c) cbm[c] -= ml;
+        if (cw == 0) TEV(1, i, 2);
+        // ---------------- pass 2: P = exp(s - max) as f16 pairs over the S columns already consumed ----------------
+#pragma unroll 1
+        for (int j = 0; j <= K; j += 2) {
+            t_ld_wait();
+            t_ld_row(srow + (j + 1) * TKP, sb);
+            exprow(sa, j);
+            t_ld_wait();
+            if (j + 2 <= K) t_ld_row(srow + (j + 2) * TKP, sa);
+            exprow(sb, j + 1);
+        }
+#pragma unroll
+        for (int c = 0; c < Cf::KVC; ++c) cbm[c] += ml;              // back to exact 0 / -inf
+        if (cw == 0) TEV(1, i, 3);
+        // P of the key rows outside the warp's range is zero (after the S reads: the P columns alias S): rows [0, 2cw) and
+        // (2cw + K, NKR) = 3cw + (9 - 3cw) chunks of 8 columns
+        {
+            const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            constexpr int NZ = (Cf::NKR - K - 1) * (TKP / 2) / 8;
+            static_assert((Cf::NKR - K - 1) * (TKP / 2) % 8 == 0 && (2 * (TKP / 2)) % 8 == 0, "zero fill in chunks of 8 columns");
+#pragma unroll 1
+            for (int t = 0; t < NZ; ++t) {
+                const int lo = 3 * cw;                               // chunks below the warp's rows (24 cw columns)
+                const uint32_t col = t < lo ? (uint32_t)(8 * t) : (uint32_t)((2 * cw + K + 1) * (TKP / 2) + 8 * (t - lo));
+                t_st8(tq + col, z);
+            }
+        }
+        t_st_wait();
+        t_fence_before();
+        tbar_arrive(sm.pfull, i);
+        if (cw == 0) TEV(1, i, 4);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// E role: residual, classifier input, log-softmax / argmax, stores.  Same lane ownership as S.
+// ---------------------------------------------------------------------------------------------
+template <int K, int NCP>
+__device__ __forceinline__ void t_e_role(const CreffMmaParams& p, const TSmem& sm, uint32_t tmem, int n, int x0, int ya, int yb, int S) {
+    using Cf = TCfg<K>;
+    constexpr float LOG2E = 1.4426950408889634f;
+    const int lane = threadIdx.x & 31, cw = (int)(threadIdx.x >> 5) & 3;
     const int b = lane >> 4, qx = lane & 15, qy = 2 * cw + b;
     const uint32_t tq = tmem + ((uint32_t)(32 * cw) << 16);
     const int W = p.W;
@@ -641,12 +761,6 @@ __device__ __forceinline__ void t_c_role(const CreffMmaParams& p, const TSmem& s
     float* const ol = p.out_logits ? p.out_logits + (size_t)n * p.ncls * plane : nullptr;
     float* const op = p.out_p ? p.out_p + (size_t)n * MC * plane : nullptr;
     uint8_t* const oa = p.out_argmax ? p.out_argmax + (size_t)n * plane : nullptr;
-    // column mask of this lane's window: key column c is inside iff qx <= c < qx + K
-    float cb[Cf::KVC];
-#pragma unroll
-    for (int c = 0; c < Cf::KVC; ++c) cb[c] = ((unsigned)(c - qx) < (unsigned)K) ? 0.f : -INFINITY;
-    // the warp reads key rows 2cw .. 2cw + K of the tile; the first is outside the window of its odd query row, the last outside that of the even one
-    const float rb_first = b ? -INFINITY : 0.f, rb_last = b ? 0.f : -INFINITY;
     const uint32_t res_col = (uint32_t)((1 + qx) * 128), res_sw = (uint32_t)((1 + qx) & 7);
     const uint32_t lbase = sm.rings + (uint32_t)Cf::HR_BYTES;
 
@@ -656,7 +770,7 @@ __device__ __forceinline__ void t_c_role(const CreffMmaParams& p, const TSmem& s
         // (a parity wait may only name a phase the barrier has already entered: every role's FIRST wait on a hand-off uses an
         // index < TNB and later ones advance by < TNB, so "tile ready" = ddone(2i + HP + 1) is used here, not gfull(2i + HP + 2))
         tbar_wait(sm.ddone, 2 * i + Cf::HP + 1, 1);
-        if (cw == 0) TEV(1, i, 0);
+        if (cw == 0) TEV(2, i, 0);
         uint4 res[8];
         {
             const uint32_t ra = lbase + (uint32_t)(((8 * i + 1 + qy) % TLRR) * (TLC * 128)) + res_col;
@@ -664,66 +778,9 @@ __device__ __forceinline__ void t_c_role(const CreffMmaParams& p, const TSmem& s
             for (int c = 0; c < 8; ++c) res[c] = t_lds128(ra + (((uint32_t)c ^ res_sw) << 4));
         }
         tbar_arrive(sm.lrfree, i);
-        // ---------------- softmax over the k x k window (model/attention.py:203) ----------------
-        tbar_wait(sm.sfull, i, 9);
-        if (cw == 0) TEV(1, i, 1);
-        t_fence_after();
-        const uint32_t srow = tq + (uint32_t)(2 * cw * TKP);        // S columns of the warp's first key row
-        float m = -INFINITY;
-#pragma unroll 1
-        for (int j = 0; j <= K; ++j) {                              // rolled: see the D role
-            uint32_t s[24];
-            t_ld16(srow + j * TKP, s);
-            t_ld8(srow + j * TKP + 16, s + 16);
-            t_ld_wait();
-            float rm = -INFINITY;
-#pragma unroll
-            for (int c = 0; c < Cf::KVC; ++c) rm = fmaxf(rm, __uint_as_float(s[c]) + cb[c]);
-            m = fmaxf(m, rm + (j == 0 ? rb_first : (j == K ? rb_last : 0.f)));
-        }
-        if (cw == 0) TEV(1, i, 2);
-        const float ml = m * LOG2E;
-        float cbm[Cf::KVC];
-#pragma unroll
-        for (int c = 0; c < Cf::KVC; ++c) cbm[c] = cb[c] - ml;
-        const uint32_t prow = tq + (uint32_t)(2 * cw * (TKP / 2));  // P columns of the warp's first key row
-#pragma unroll 1
-        for (int j = 0; j <= K; ++j) {
-            uint32_t s[24];
-            t_ld16(srow + j * TKP, s);
-            t_ld8(srow + j * TKP + 16, s + 16);
-            t_ld_wait();
-            const bool rowok = !((j == 0 && b) || (j == K && !b));
-            uint32_t pk[12];
-#pragma unroll
-            for (int c = 0; c < 24; c += 2) {
-                if (c < Cf::KVC) {
-                    const float e0 = t_ex2(fmaf(__uint_as_float(s[c]), LOG2E, cbm[c]));
-                    const float e1 = c + 1 < Cf::KVC ? t_ex2(fmaf(__uint_as_float(s[c + 1]), LOG2E, cbm[c + 1 < Cf::KVC ? c + 1 : c])) : 0.f;
-                    pk[c >> 1] = rowok ? pack_h2(e0, e1) : 0u;
-                } else {
-                    pk[c >> 1] = 0u;
-                }
-            }
-            t_st8(prow + j * (TKP / 2), pk);
-            t_st4(prow + j * (TKP / 2) + 8, pk[8], pk[9], pk[10], pk[11]);
-        }
-        if (cw == 0) TEV(1, i, 3);
-        // P of the key rows outside the warp's range is zero (written after the S reads: the P columns alias S)
-#pragma unroll 1
-        for (int r = 0; r < Cf::NKR; ++r) {
-            if (r < 2 * cw || r > 2 * cw + K) {
-                const uint32_t a = tq + (uint32_t)(r * (TKP / 2));
-                t_st4(a, 0u, 0u, 0u, 0u); t_st4(a + 4, 0u, 0u, 0u, 0u); t_st4(a + 8, 0u, 0u, 0u, 0u);
-            }
-        }
-        t_st_wait();
-        t_fence_before();
-        tbar_arrive(sm.pfull, i);
-        if (cw == 0) TEV(1, i, 4);
         // ---------------- fused = lr_up + O / sum (model/attention.py:207,210) ----------------
         tbar_wait(sm.ofull, i, 10);
-        if (cw == 0) TEV(1, i, 5);
+        if (cw == 0) TEV(2, i, 5);
         t_fence_after();
         const int py = ya + 8 * i + qy;
         const bool ok = py < yb && px < W;
@@ -735,6 +792,7 @@ __device__ __forceinline__ void t_c_role(const CreffMmaParams& p, const TSmem& s
             uint32_t o[32];
             t_ld32(tq + Cf::COL_O + 32 * hf, o);
             t_ld_wait();
+            if (hf == 1 && !op) { t_fence_before(); tbar_arrive(sm.ofree, i); }       // O and the row sum are in registers
             const float inv = t_rcp(__uint_as_float(su));
             uint32_t pk[16];
 #pragma unroll
@@ -763,29 +821,29 @@ __device__ __forceinline__ void t_c_role(const CreffMmaParams& p, const TSmem& s
                 const uint32_t* rr = reinterpret_cast<const uint32_t*>(&res[0]);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    // res[q8] holds channels 8 q8 .. 8 q8 + 7 as four f16 pairs (dynamic q8: select by a rolled copy below)
-                    const float2 r2 = t_h2f(rr[e]);
+                    const float2 r2 = t_h2f(rr[e]);                            // res[0] = channels 8 q8 .. 8 q8 + 7 (rotated below)
                     if (ok) {
                         o_ptr[(size_t)(2 * e) * plane] = fmaf(__uint_as_float(o[2 * e]), inv, r2.x);
                         o_ptr[(size_t)(2 * e + 1) * plane] = fmaf(__uint_as_float(o[2 * e + 1]), inv, r2.y);
                     }
                 }
                 o_ptr += 8 * plane;
-                // rotate the residual registers so that res[0] is the next 8-channel group
                 const uint4 t0 = res[0];
 #pragma unroll
                 for (int c = 0; c < 7; ++c) res[c] = res[c + 1];
                 res[7] = t0;
             }
+            t_fence_before();
+            tbar_arrive(sm.ofree, i);
         }
         if (NCP == 0) continue;
         t_st_wait();
         t_fence_before();
         tbar_arrive(sm.afull, i);
-        if (cw == 0) TEV(1, i, 6);
+        if (cw == 0) TEV(2, i, 6);
         // ---------------- classifier (model/pspnet.py:226), log-softmax (:229), argmax (evaluation.py:204) ----------------
         tbar_wait(sm.lfull, i, 11);
-        if (cw == 0) TEV(1, i, 7);
+        if (cw == 0) TEV(2, i, 7);
         t_fence_after();
         constexpr int NCPA = NCP > 0 ? NCP : 16;
         uint32_t lg[NCPA];
@@ -816,15 +874,42 @@ __device__ __forceinline__ void t_c_role(const CreffMmaParams& p, const TSmem& s
             }
             if (oa) oa[off] = (uint8_t)am;
         }
-        if (cw == 0) TEV(1, i, 8);
+        if (cw == 0) TEV(2, i, 8);
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// gather records, once per pixel: [N][H][W] for the MV-warped keyframe feature, then [H][W] for lr_up
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) creff_tc_rec_kernel(CreffMmaParams p, uint4* __restrict__ rec) {
+    const long long plane = (long long)p.H * p.W, total = (long long)(p.N + 1) * plane;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int n = (int)(i / plane);
+    const int fy = (int)((i - (long long)n * plane) / p.W), fx = (int)(i % p.W);
+    PosRec r;
+    int Ws, Hs;
+    if (n < p.N) { r = pos_hr(p, n, fy, fx); Ws = p.W; Hs = p.H; }
+    else {
+        r = pos_lr(p, resize_scale(p.h, p.H, ARSEG_RESIZE_BILINEAR_AC), resize_scale(p.w, p.W, ARSEG_RESIZE_BILINEAR_AC), fy, fx);
+        Ws = p.w; Hs = p.h;
+    }
+    uint4 o = make_uint4(0u, 0u, n < p.N ? 0u : 0x80000000u, 0u);
+    if (r.info >= 0) {
+        float4 w; int bx, by;
+        rec_block_of(r, Ws, Hs, w, bx, by);
+        o.x = pack_h2(w.x, w.y);
+        o.y = pack_h2(w.z, w.w);
+        o.z |= (uint32_t)(by * Ws + bx);
+    }
+    rec[i] = o;
 }
 
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
-template <int K, int NCP, bool MVF>
-__global__ void __launch_bounds__(TTHREADS, 1) creff_tc_kernel(CreffMmaParams p) {
+template <int K, int NCP>
+__global__ void __launch_bounds__(TTHREADS, 1) creff_tc_kernel(CreffMmaParams p, const uint4* __restrict__ rec) {
     using Cf = TCfg<K>;
     extern __shared__ __align__(1024) uint8_t tsm_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tsm_raw) + 1023) & ~(uintptr_t)1023);
@@ -837,12 +922,11 @@ __global__ void __launch_bounds__(TTHREADS, 1) creff_tc_kernel(CreffMmaParams p)
     uint8_t* pRec = pRings + Cf::HR_BYTES + Cf::LR_BYTES + Cf::SCRATCH_BYTES;
     TSmem sm;
     sm.sK = s_u32(pK); sm.sV = s_u32(pV); sm.sQ = s_u32(pQ); sm.sW = s_u32(pW); sm.sOnes = s_u32(pOnes); sm.rings = s_u32(pRings);
-    sm.posw = reinterpret_cast<float4*>(pRec);
-    sm.posa = reinterpret_cast<uint4*>(pRec + (size_t)2 * Cf::PMAX * 16);
+    sm.posa = reinterpret_cast<uint4*>(pRec);
     sm.s_bc = reinterpret_cast<float*>(pRec + Cf::REC_BYTES);
     sm.gfull = reinterpret_cast<uint64_t*>(sm.s_bc + TNCLS);
     sm.ddone = sm.gfull + TNB; sm.lrfree = sm.ddone + TNB; sm.sfull = sm.lrfree + TNB; sm.pfull = sm.sfull + TNB;
-    sm.ofull = sm.pfull + TNB; sm.afull = sm.ofull + TNB; sm.lfull = sm.afull + TNB;
+    sm.ofull = sm.pfull + TNB; sm.ofree = sm.ofull + TNB; sm.afull = sm.ofree + TNB; sm.lfull = sm.afull + TNB;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm.lfull + TNB);
 
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -859,7 +943,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) creff_tc_kernel(CreffMmaParams p)
         for (int i = 0; i < TNB; ++i) {
             tbar_init(sm.gfull + i, TG_WARPS); tbar_init(sm.ddone + i, TD_WARPS); tbar_init(sm.lrfree + i, TC_WARPS);
             tbar_init(sm.sfull + i, 1); tbar_init(sm.pfull + i, TC_WARPS); tbar_init(sm.ofull + i, 1);
-            tbar_init(sm.afull + i, TC_WARPS); tbar_init(sm.lfull + i, 1);
+            tbar_init(sm.afull + i, TC_WARPS); tbar_init(sm.lfull + i, 1); tbar_init(sm.ofree + i, TC_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -883,16 +967,14 @@ __global__ void __launch_bounds__(TTHREADS, 1) creff_tc_kernel(CreffMmaParams p)
     t_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    // register file re-balance (warpgroup-aligned): the softmax / epilogue warps take what the producers do not need
-    if (warp >= TC_W0) asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
-    else asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
 #ifdef ARSEG_TTRACE
     const long long t_role = clock64();
 #endif
-    if (warp >= TC_W0) t_c_role<K, NCP>(p, sm, tmem, n, x0, ya, yb, S);
-    else if (warp == TM_WARP) t_m_role<K, NCP>(sm, tmem, S);
-    else if (warp < 4 || warp == TQ_WARP) t_d_role<K>(p, sm, x0, ya, NH, S);
-    else t_g_role<K, MVF>(p, sm, n, x0, ya, NH, S);
+    if (warp >= TS_W0) t_s_role<K>(sm, tmem, S);
+    else if (warp >= TE_W0) t_e_role<K, NCP>(p, sm, tmem, n, x0, ya, yb, S);
+    else if (warp == TM_WARP) t_m_role<K, NCP>(sm, tmem, S, p.dbg);
+    else if (warp < 4 || warp == TQ_WARP0 || warp == TQ_WARP0 + 1) t_d_role<K>(p, sm, x0, ya, NH, S);
+    else t_g_role<K>(p, sm, rec, n, x0, ya, NH, S);
 #ifdef ARSEG_TTRACE
     if (blockIdx.x == TTRACE_CTA && (tid & 31) == 0) { g_ttrace[warp * 16 + 15] += clock64() - t_role; g_ttrace[warp * 16 + 14] += S; }
 #endif
@@ -905,10 +987,10 @@ __global__ void __launch_bounds__(TTHREADS, 1) creff_tc_kernel(CreffMmaParams p)
     }
 }
 
-template <int K, int NCP, bool MVF>
-static int creff_tc_launch_n(CreffMmaParams& p, cudaStream_t st) {
+template <int K, int NCP>
+static int creff_tc_launch_n(CreffMmaParams& p, void* ws, size_t ws_bytes, cudaStream_t st) {
     using Cf = TCfg<K>;
-    auto kern = creff_tc_kernel<K, NCP, MVF>;
+    auto kern = creff_tc_kernel<K, NCP>;
     // per device, written once per process: an idempotent attribute, so the unsynchronised flag is a benign race between
     // nn.DataParallel worker threads
     static bool configured[64] = {false};
@@ -917,6 +999,14 @@ static int creff_tc_launch_n(CreffMmaParams& p, cudaStream_t st) {
     if (dev < 0 || dev >= 64 || !configured[dev]) {
         ARSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cf::SMEM));
         if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    ARSEG_REQUIRE(ws && ws_bytes >= creff_tc_workspace_bytes(p.N, p.H, p.W) && ((uintptr_t)ws % 16) == 0,
+                  "creff_tc: needs a 16-byte aligned workspace of %zu bytes (arseg_creff_workspace_bytes)", creff_tc_workspace_bytes(p.N, p.H, p.W));
+    uint4* rec = reinterpret_cast<uint4*>(ws);
+    {
+        const long long total = (long long)(p.N + 1) * p.H * p.W;
+        creff_tc_rec_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, st>>>(p, rec);
+        ARSEG_CHECK_LAUNCH("creff_tc_rec");
     }
     p.ncols = ceil_div(p.W, TSW);
     { const char* d = getenv("ARSEG_CREFF_DBG"); p.dbg = d ? atoi(d) : 0; }      // -DARSEG_TTRACE builds only
@@ -931,31 +1021,26 @@ static int creff_tc_launch_n(CreffMmaParams& p, cudaStream_t st) {
     p.nseg = ceil_div(p.H, p.seg_rows);
     const long long blocks = (long long)p.N * p.ncols * p.nseg;
     ARSEG_REQUIRE(blocks > 0 && blocks < 2147483647LL, "creff_tc: grid too large");
-    kern<<<(unsigned)blocks, TTHREADS, Cf::SMEM, st>>>(p);
+    kern<<<(unsigned)blocks, TTHREADS, Cf::SMEM, st>>>(p, rec);
     ARSEG_CHECK_LAUNCH("creff_tc");
     return ARSEG_OK;
 }
 
 template <int K>
-static int creff_tc_launch_k(CreffMmaParams& p, cudaStream_t st) {
-    const bool mvf = p.flow && p.flow_dtype == ARSEG_I16 && p.Hm == p.H && p.Wm == p.W;
-    if (mvf) {
-        if (!p.wcls) return creff_tc_launch_n<K, 0, true>(p, st);
-        if (p.ncls <= 16) return creff_tc_launch_n<K, 16, true>(p, st);
-        return creff_tc_launch_n<K, 32, true>(p, st);
-    }
-    if (!p.wcls) return creff_tc_launch_n<K, 0, false>(p, st);
-    if (p.ncls <= 16) return creff_tc_launch_n<K, 16, false>(p, st);
-    return creff_tc_launch_n<K, 32, false>(p, st);
+static int creff_tc_launch_k(CreffMmaParams& p, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (!p.wcls) return creff_tc_launch_n<K, 0>(p, ws, ws_bytes, st);
+    if (p.ncls <= 16) return creff_tc_launch_n<K, 16>(p, ws, ws_bytes, st);
+    return creff_tc_launch_n<K, 32>(p, ws, ws_bytes, st);
 }
 
-// hr and lr are f16 NHWC ([.,H,W,64] / [N,h,w,64]); k in {3, 5, 7}
-int creff_tc_launch(CreffMmaParams& p, int k, cudaStream_t st) {
+// hr and lr are f16 NHWC ([.,H,W,64] / [N,h,w,64]); k in {3, 5, 7}; ws = the gather records (creff_tc_workspace_bytes)
+int creff_tc_launch(CreffMmaParams& p, int k, void* ws, size_t ws_bytes, cudaStream_t st) {
     if (p.H < 2 || p.W < 2 || p.h < 2 || p.w < 2) ARSEG_UNSUPPORTED("creff_tc: maps must be at least 2x2 (hr %dx%d, lr %dx%d)", p.H, p.W, p.h, p.w);
+    ARSEG_REQUIRE((long long)p.H * p.W < (1LL << 31) && (long long)p.h * p.w < (1LL << 31), "creff_tc: map too large");
     switch (k) {
-        case 3: return creff_tc_launch_k<3>(p, st);
-        case 5: return creff_tc_launch_k<5>(p, st);
-        case 7: return creff_tc_launch_k<7>(p, st);
+        case 3: return creff_tc_launch_k<3>(p, ws, ws_bytes, st);
+        case 5: return creff_tc_launch_k<5>(p, ws, ws_bytes, st);
+        case 7: return creff_tc_launch_k<7>(p, ws, ws_bytes, st);
         default: ARSEG_UNSUPPORTED("creff_tc: window k=%d (3, 5, 7)", k);
     }
 }
@@ -963,12 +1048,12 @@ int creff_tc_launch(CreffMmaParams& p, int k, cudaStream_t st) {
 }  // namespace arseg
 #ifdef ARSEG_TTRACE
 extern "C" int arseg_debug_creff_tc_events(long long* host) {
-    cudaMemcpyFromSymbol(host, arseg::g_tev, sizeof(long long) * 2 * 64 * 12);
-    return 2 * 64 * 12;
+    cudaMemcpyFromSymbol(host, arseg::g_tev, sizeof(long long) * 3 * 64 * 12);
+    return 3 * 64 * 12;
 }
 extern "C" int arseg_debug_creff_tc_trace(long long* host, int reset) {
-    cudaMemcpyFromSymbol(host, arseg::g_ttrace, sizeof(long long) * 256);
-    if (reset) { long long z[256] = {0}; cudaMemcpyToSymbol(arseg::g_ttrace, z, sizeof(z)); }
-    return 256;
+    cudaMemcpyFromSymbol(host, arseg::g_ttrace, sizeof(long long) * 512);
+    if (reset) { long long z[512] = {0}; cudaMemcpyToSymbol(arseg::g_ttrace, z, sizeof(z)); }
+    return 512;
 }
 #endif

