@@ -693,6 +693,8 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParam
     const size_t smem = (size_t)STAGES * (TC_A_STAGE + BLOCK_N * TC_ROW_BYTES) + (2 * STAGES + 2 * TC_NACC) * 8 + 16 + 2 * (size_t)p.cout_pad * 4 + 1024;
     ARSEG_REQUIRE(smem <= 232448, "conv_tc: Cout=%d too large for the scale/shift staging", p.Cout);
     auto kern = conv_tc_kernel<T, BLOCK_N, STAGES>;
+    // per device, written once per process: an idempotent attribute, so the unsynchronised flag is a benign race between
+    // nn.DataParallel worker threads (the worst case is a redundant cudaFuncSetAttribute)
     static bool configured[64] = {false};
     int dev = 0;
     ARSEG_CUDA(cudaGetDevice(&dev));
@@ -731,7 +733,7 @@ static int launch_tch(const CUtensorMap& ma, const CUtensorMap& mb, TchParams& h
     }
     const size_t smem = fixed + (size_t)hp.sa * hp.a_stage + (size_t)hp.sb * b_stage;
     auto kern = conv_tc_halo_kernel<T, BLOCK_N>;
-    static bool configured[64] = {false};
+    static bool configured[64] = {false};     // benign race, see launch_tc
     int dev = 0;
     ARSEG_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !configured[dev]) {
@@ -761,7 +763,10 @@ int conv_tc_launch(const arseg_conv_desc* d, cudaStream_t st) {
     p.N = d->N; p.Ho = (d->Hi - 1) / d->stride + 1; p.Wo = (d->Wi - 1) / d->stride + 1; p.Cin = d->Cin; p.Cout = d->Cout; p.KH = d->KH; p.KW = d->KW;
     p.out_f32 = (d->out_f32 && d->dtype != ARSEG_F32) ? 1 : 0;
     p.pad = d->pad; p.dil = d->dil; p.ocs = d->out_cstride; p.oco = d->out_coff; p.act = d->act; p.slope = d->prelu_slope;
-    const bool halo = d->stride == 1 && d->KH == 3 && d->KW == 3 && d->pad == d->dil && d->dil >= 1 && d->dil <= 8 && env_int("ARSEG_TC_HALO", 1) != 0;
+    // the halo box is TCH_WH = 16 pixels wide and the tap columns reach tx + 2 * dil <= 7 + 2 * dil: dilation <= 4 (larger
+    // dilations take the per-tap kernel)
+    const bool halo = d->stride == 1 && d->KH == 3 && d->KW == 3 && d->pad == d->dil && d->dil >= 1 && TCH_TW + 2 * d->dil <= TCH_WH &&
+                      env_int("ARSEG_TC_HALO", 1) != 0;
     if (halo) { p.TH = TCH_TH; p.TW = TCH_TW; } else pick_tile(p.Ho, p.Wo, p.TH, p.TW);
     p.tiles_x = ceil_div(p.Wo, p.TW); p.tiles_y = ceil_div(p.Ho, p.TH);
     p.kchunks = d->Cin / bk;

@@ -28,12 +28,13 @@ int sm_count() {
 // ------------------------------------------------------------------------------------------
 // NCHW <-> NHWC (per image: transpose of a C x (H*W) matrix) through a 32x33 smem tile
 // ------------------------------------------------------------------------------------------
-template <typename TI, typename TO>
+// ROWS_ON_X: the row-tile index is blockIdx.x (the long axis of either direction: H*W tiles)
+template <typename TI, typename TO, bool ROWS_ON_X = false>
 __global__ void transpose_kernel(const TI* __restrict__ src, TO* __restrict__ dst, int rows, int cols) {
     // src: [n][rows][cols] -> dst: [n][cols][rows]
     __shared__ float tile[32][33];
     const size_t base = (size_t)blockIdx.z * rows * cols;
-    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int c0 = (ROWS_ON_X ? blockIdx.y : blockIdx.x) * 32, r0 = (ROWS_ON_X ? blockIdx.x : blockIdx.y) * 32;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         int r = r0 + i, c = c0 + threadIdx.x;
         if (r < rows && c < cols) tile[i][threadIdx.x] = to_f32(src[base + (size_t)r * cols + c]);
@@ -424,14 +425,15 @@ int arseg_nchw_to_nhwc(const float* src, void* dst, int dst_dtype, int N, int C,
 
 int arseg_nhwc_to_nchw(const void* src, int src_dtype, float* dst, int N, int C, int H, int W, arseg_stream_t stream) {
     ARSEG_REQUIRE(src && dst && N > 0 && C > 0 && H > 0 && W > 0, "nhwc_to_nchw: bad args");
-    dim3 grid(ceil_div(C, 32), ceil_div(H * W, 32), N), block(32, 8);
+    // the pixel-tile index goes on grid.x (2^31 - 1 blocks): 1024 x 2048 is 65536 tiles, one more than grid.y allows
+    dim3 grid(ceil_div(H * W, 32), ceil_div(C, 32), N), block(32, 8);
     ARSEG_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "nhwc_to_nchw: dims too large");
     if (src_dtype == ARSEG_F32)
-        transpose_kernel<float, float><<<grid, block, 0, as_stream(stream)>>>((const float*)src, dst, H * W, C);
+        transpose_kernel<float, float, true><<<grid, block, 0, as_stream(stream)>>>((const float*)src, dst, H * W, C);
     else if (src_dtype == ARSEG_BF16)
-        transpose_kernel<__nv_bfloat16, float><<<grid, block, 0, as_stream(stream)>>>((const __nv_bfloat16*)src, dst, H * W, C);
+        transpose_kernel<__nv_bfloat16, float, true><<<grid, block, 0, as_stream(stream)>>>((const __nv_bfloat16*)src, dst, H * W, C);
     else if (src_dtype == ARSEG_F16)
-        transpose_kernel<__half, float><<<grid, block, 0, as_stream(stream)>>>((const __half*)src, dst, H * W, C);
+        transpose_kernel<__half, float, true><<<grid, block, 0, as_stream(stream)>>>((const __half*)src, dst, H * W, C);
     else ARSEG_UNSUPPORTED("nhwc_to_nchw: dtype %d", src_dtype);
     ARSEG_CHECK_LAUNCH("nhwc_to_nchw");
     return ARSEG_OK;

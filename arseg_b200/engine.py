@@ -70,6 +70,8 @@ class Plan:
     # -- helpers -------------------------------------------------------------------------------
     def dev(self, t: torch.Tensor, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
         t = t.detach().to(device=self.device, dtype=dtype or t.dtype).contiguous()
+        if t.data_ptr() % 16:       # e.g. a DataParallel replica's parameter: a view into a coalesced broadcast buffer
+            t = t.clone()           # (the kernels read weights with 16-byte vector loads)
         self.keep.append(t)
         return t
 

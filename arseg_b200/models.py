@@ -76,7 +76,9 @@ class MyAttention(nn.Module):
 
     def forward(self, hr_feat: torch.Tensor, lr_feat: torch.Tensor) -> torch.Tensor:
         from . import ops
-        sd = self.state_dict()
+        sd = {k: getattr(getattr(self, k.split(".")[0]), k.split(".")[1]) for k in
+              ("lr_query_conv.weight", "lr_query_conv.bias", "hr_key_conv.weight", "hr_key_conv.bias", "hr_value_conv.weight",
+               "hr_value_conv.bias")}                      # attribute access works on DataParallel replicas too
         out_p, _, _ = ops.creff_fused(
             hr_feat.contiguous().float(), lr_feat.contiguous().float(),
             *[sd[k].reshape(-1).contiguous() for k in ("lr_query_conv.weight", "lr_query_conv.bias", "hr_key_conv.weight",
@@ -94,10 +96,30 @@ class _PlannedNet(nn.Module):
         self._plans: Dict[tuple, tuple] = {}
 
     def _version(self) -> int:
-        return sum(t._version for t in list(self.parameters()) + list(self.buffers()))
+        # nn.DataParallel replicas (evaluation.py:41,54,173) get fresh broadcast copies on every forward: their tensors'
+        # _version counters say nothing, so the weight generation (bumped by load_state_dict / .to()) is part of the key
+        return getattr(self, "_wgen", 0) + sum(t._version for t in self._sd().values())
 
     def _sd(self) -> Dict[str, torch.Tensor]:
-        return {k: v.detach() for k, v in self.state_dict().items()}
+        """name -> tensor for every parameter and buffer.  Not state_dict(): a replica made by
+        nn.parallel.replicate keeps its parameter copies as plain attributes (`_parameters` is empty), so the tensors are
+        collected from `_parameters`, the instance dict and `_buffers` of every sub-module."""
+        out: Dict[str, torch.Tensor] = {}
+        for prefix, m in self.named_modules():
+            names = list(m._parameters.keys()) + [k for k, v in m.__dict__.items() if isinstance(v, torch.Tensor)] + list(m._buffers.keys())
+            for k in names:
+                v = m._parameters.get(k)
+                if v is None:
+                    v = m.__dict__.get(k)
+                if v is None:
+                    v = m._buffers.get(k)
+                if isinstance(v, torch.Tensor):
+                    out[(prefix + "." if prefix else "") + k] = v.detach()
+        return out
+
+    def load_state_dict(self, *a, **k):
+        self._wgen = getattr(self, "_wgen", 0) + 1
+        return super().load_state_dict(*a, **k)
 
     def _get_plan(self, kind: str, shapes: tuple, device: torch.device, build):
         prec = self.precision or default_precision()
@@ -116,6 +138,7 @@ class _PlannedNet(nn.Module):
 
     def _apply(self, fn, *a, **k):  # .cuda()/.to(): cached plans hold device buffers of the old placement
         self._plans = {}
+        self._wgen = getattr(self, "_wgen", 0) + 1
         return super()._apply(fn, *a, **k)
 
 

@@ -30,6 +30,14 @@ def _chk_cuda(name: str, *ts: torch.Tensor) -> None:
             raise RuntimeError("%s: expected a contiguous tensor" % name)
 
 
+def _chk_f32(name: str, *ts: torch.Tensor) -> None:
+    """The kernels behind these wrappers read fp32: any other dtype would be reinterpreted silently, so it raises (the
+    localAttention wrappers do the same, as the upstream extension does)."""
+    for t in ts:
+        if t is not None and t.dtype != torch.float32:
+            raise RuntimeError("%s: expected a float32 tensor, got %s" % (name, t.dtype))
+
+
 def dtype_code(dt: torch.dtype) -> int:
     return _TORCH2ARSEG[dt]
 
@@ -116,6 +124,7 @@ def warp_feature(feature: torch.Tensor, flow: torch.Tensor) -> torch.Tensor:
 def resize_nchw(x: torch.Tensor, size, mode: int) -> torch.Tensor:
     x = x.contiguous()
     _chk_cuda("resize_nchw", x)
+    _chk_f32("resize_nchw", x)
     N, Cc, H, W = x.shape
     out = torch.empty((N, Cc, size[0], size[1]), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
@@ -139,6 +148,7 @@ def resize_nhwc(x: torch.Tensor, size, mode: int, out: Optional[torch.Tensor] = 
 def resize_argmax(logits: torch.Tensor, size, mode: int, want_logits: bool = False):
     logits = logits.contiguous()
     _chk_cuda("resize_argmax", logits)
+    _chk_f32("resize_argmax", logits)
     N, K, H, W = logits.shape
     pred = torch.empty((N, size[0], size[1]), dtype=torch.uint8, device=logits.device)
     up = torch.empty((N, K, size[0], size[1]), dtype=torch.float32, device=logits.device) if want_logits else None
@@ -164,6 +174,7 @@ def confusion_hist(pred: torch.Tensor, label: torch.Tensor, n_classes: int, igno
 def nchw_to_nhwc(x: torch.Tensor, dtype: torch.dtype = torch.float32) -> torch.Tensor:
     x = x.contiguous()
     _chk_cuda("nchw_to_nhwc", x)
+    _chk_f32("nchw_to_nhwc", x)
     N, Cc, H, W = x.shape
     out = torch.empty((N, H, W, Cc), dtype=dtype, device=x.device)
     with torch.cuda.device(x.device):
@@ -184,6 +195,9 @@ def conv2d_nhwc(x, w, scale=None, shift=None, residual=None, stride=1, pad=0, di
                 engine=L.CONV_SIMT_F32, out=None, out_coff=0):
     """x [N,H,W,Cin] NHWC, w [Cout,KH,KW,Cin]; returns NHWC [N,Ho,Wo,Cout] (or writes a channel slice of `out`)."""
     _chk_cuda("conv2d_nhwc", x, w, scale, shift, residual, out)
+    _chk_f32("conv2d_nhwc (scale / shift)", scale, shift)
+    if residual is not None and residual.dtype != x.dtype:
+        raise RuntimeError("conv2d_nhwc: residual dtype %s != activation dtype %s" % (residual.dtype, x.dtype))
     N, Hi, Wi, Cin = x.shape
     Cout, KH, KW, Cin2 = w.shape
     assert Cin == Cin2 and x.dtype == w.dtype
@@ -202,6 +216,7 @@ def conv2d_nhwc(x, w, scale=None, shift=None, residual=None, stride=1, pad=0, di
 def conv_stem(x_nchw, w_oihw, scale, shift, dtype=torch.float32):
     """conv1 7x7 s2 p3 + folded BN + ReLU (model/extractors.py:112-114): NCHW fp32 [N,3,H,W] -> NHWC [N,Ho,Wo,Cout]."""
     _chk_cuda("conv_stem", x_nchw, w_oihw, scale, shift)
+    _chk_f32("conv_stem", x_nchw, w_oihw, scale, shift)
     N, Ci, H, W = x_nchw.shape
     Cout = w_oihw.shape[0]
     assert Ci == 3 and tuple(w_oihw.shape[1:]) == (3, 7, 7)
@@ -222,6 +237,13 @@ def creff_fused(hr, lr, wq, bq, wk, bk, wv, bv, k, flow=None, flow_hw=None, wcls
     (tensor-core window attention, TF32-class error, C = 64 m, NHWC hr and lr; C = 64 with fp16 hr AND fp16 lr runs the
     tcgen05 / TMEM engine, k <= 7)."""
     _chk_cuda("creff_fused", hr, lr, wq, bq, wk, bk, wv, bv, flow, wcls, bcls)
+    _chk_f32("creff_fused (depthwise / classifier weights)", wq, bq, wk, bk, wv, bv, wcls, bcls)
+    if hr.dtype not in (torch.float32, torch.float16) or (hr.dtype == torch.float16 and hr_layout != L.NHWC):
+        raise RuntimeError("creff_fused: hr must be float32, or float16 NHWC (tcgen05 engine); got %s" % hr.dtype)
+    if lr_layout == L.NCHW and lr.dtype != torch.float32:
+        raise RuntimeError("creff_fused: an NCHW lr must be float32, got %s" % lr.dtype)
+    if flow is not None and flow.dtype not in (torch.int16, torch.float32, torch.float64):
+        raise RuntimeError("creff_fused: flow must be int16 (quarter-pel), float32 or float64, got %s" % flow.dtype)
     if hr_layout == L.NHWC:
         Nh, H, W, Cc = hr.shape
     else:

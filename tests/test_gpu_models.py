@@ -194,3 +194,88 @@ def test_split_keyframe_engine_matches_single_graph():
     torch.cuda.synchronize()
     assert torch.equal(got, want)
     assert torch.equal(two.step(), want)
+
+
+# ---------------------------------------------------------------- full-shape parity (BASELINE configs[0..3] shapes)
+# One frame at the benchmarked resolutions through the captured engine against the oracle's literal
+# evaluation.py:176-204 step (CPU, a few seconds per architecture, cached across the precisions): tile-edge, ring-wrap
+# and 32-bit index behaviour at 720x960 / 1024x2048 that the 64x96 goldens cannot reach.
+_FULL = {"camvid-psp18": (720, 960, 1, 64), "camvid-bise18": (720, 960, 8, 256), "cityscapes-psp18": (1024, 2048, 8, 512)}
+_FULL_CACHE = {}
+
+
+def _full_case(arch):
+    if arch not in _FULL_CACHE:
+        H, W, stride, C = _FULL[arch]
+        net = models.models_fuse[arch]()
+        sd = synth.synth_state_dict(net.state_dict(), 4)
+        imgs = synth.synth_frame(1, H, W, 2)
+        ref_p = synth.synth_feature(1, C, H // stride, W // stride, 1)
+        mv = synth.synth_mv_int16(H, W, 3, distance=7)
+        preds, logits, fused, lr_p = O.nonkey_step(arch, sd, imgs, ref_p, synth.mv_to_flow(mv), 0.5)
+        _FULL_CACHE[arch] = (sd, imgs, ref_p, mv, preds, logits, fused, lr_p)
+    return _FULL_CACHE[arch]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "f16"])
+@pytest.mark.parametrize("arch", list(_FULL))
+def test_full_shape_engine_matches_oracle(arch, precision):
+    H, W, stride, C = _FULL[arch]
+    sd, imgs, ref_p, mv, preds, logits, fused, lr_p = _full_case(arch)
+    eng = ev.NonKeyEngine(arch, sd, 1, H, W, 0.5, precision, want_logits=True, want_p=True, device=DEV)
+    eng.set_inputs(imgs.to(DEV), torch.from_numpy(mv).unsqueeze(0).to(DEV), ref_p.to(DEV))
+    got = eng.step().cpu()
+    torch.cuda.synchronize()
+    tmax, trms, targ = TOL[precision]
+    assert tuple(got.shape) == (1, H, W)
+    assert rel_err(eng.fused_p, fused) < max(tmax, 1e-4), rel_err(eng.fused_p, fused)
+    assert rms_err(eng.fused_p, fused) < max(trms, 5e-5)
+    mism = float((got.long() != preds).float().mean())
+    assert mism <= targ, mism
+    if arch == "camvid-psp18":          # logits at frame resolution come straight out of the fused kernel
+        assert rel_err(eng.logits, logits) < max(tmax, 1e-4)
+    del eng
+    torch.cuda.empty_cache()
+
+
+def test_full_shape_tcgen05_creff_matches_oracle(monkeypatch):
+    """BASELINE configs[1] shapes through the opt-in tcgen05 CReFF engine (ARSEG_CREFF_TC=1) of the f16 plan."""
+    monkeypatch.setenv("ARSEG_CREFF_TC", "1")
+    arch = "camvid-psp18"
+    H, W, stride, C = _FULL[arch]
+    sd, imgs, ref_p, mv, preds, logits, fused, lr_p = _full_case(arch)
+    eng = ev.NonKeyEngine(arch, sd, 1, H, W, 0.5, "f16", want_logits=True, want_p=True, device=DEV)
+    assert any(nm.endswith("_tc") for nm in eng.plan.names), eng.plan.names
+    eng.set_inputs(imgs.to(DEV), torch.from_numpy(mv).unsqueeze(0).to(DEV), ref_p.to(DEV))
+    got = eng.step().cpu()
+    torch.cuda.synchronize()
+    tmax, trms, targ = TOL["f16"]
+    assert rel_err(eng.fused_p, fused) < tmax and rms_err(eng.fused_p, fused) < trms
+    assert rel_err(eng.logits, logits) < tmax
+    assert float((got.long() != preds).float().mean()) <= targ
+
+
+def test_dropin_models_run_as_dataparallel_replicas():
+    """evaluation.py:41,54 wrap every net in nn.DataParallel and :173 calls the keyframe net through it: with more than one
+    visible GPU the forward runs on replicas whose parameters are plain attributes (no state_dict entries)."""
+    g = load_golden("camvid_psp18_s05")
+    arch, _, sd, imgs, ref_p, mv, flow, scale = case_setup(g)
+    net = _net(arch, sd, "fp32")
+    x = torch.nn.functional.interpolate(imgs, synth.lr_size(imgs.shape[2], imgs.shape[3], scale), mode="bilinear", align_corners=True).to(DEV)
+    want = net.forward_phase1(x)
+    replica = torch.nn.parallel.replicate(net, [0, 0])[1]
+    assert len(replica.state_dict()) < len(net.state_dict())        # the situation the fix is for
+    got = replica.forward_phase1(x)
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    out_r, fused_r = replica.forward_phase2(got[-1], ref_p.to(DEV))
+    out_n, fused_n = net.forward_phase2(want[-1], ref_p.to(DEV))
+    assert torch.equal(out_r, out_n) and torch.equal(fused_r, fused_n)
+    hr = models.models[arch]()
+    hr.load_state_dict(synth.synth_state_dict(hr.state_dict(), 4))
+    hr.precision = "fp32"
+    hr = hr.to(DEV).eval()
+    yr = torch.nn.parallel.replicate(hr, [0, 0])[1](imgs.to(DEV))
+    yn = hr(imgs.to(DEV))
+    for a, b in zip(yr, yn):
+        assert torch.equal(a, b)

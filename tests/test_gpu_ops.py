@@ -614,3 +614,37 @@ def test_creff_mma_rejects_unsupported():
     with pytest.raises(L.ArsegError):
         ops.creff_fused(ops.nchw_to_nhwc(hr.to(DEV)), ops.nchw_to_nhwc(lr.to(DEV)), *creff_args(sd), 7, want_logits=False,
                         lr_layout=L.NHWC, hr_layout=L.NHWC, engine=L.CREFF_MMA_F16)
+
+
+def test_transpose_cityscapes_full_resolution():
+    """1024 x 2048 = 65536 pixel tiles: one more than grid.y allows (the BiSeNet heads transpose the x8 up-sampled logits)."""
+    x = rnd(1, 1024, 2048, 3, seed=7).to(DEV)
+    y = ops.nhwc_to_nchw(x)
+    assert torch.equal(y, x.permute(0, 3, 1, 2).contiguous())
+    assert torch.equal(ops.nchw_to_nhwc(y), x)
+
+
+def test_conv_tcgen05_dilation_beyond_the_halo_box():
+    """dilation 6: tap columns reach tx + 12 > the 16-pixel halo box -> the per-tap kernel must run (and match)."""
+    Cin, Cout, H, W, dil = 64, 64, 20, 28, 6
+    x, w = rnd(1, H, W, Cin, seed=90) * 0.5, rnd(Cout, 3, 3, Cin, seed=91) * 0.05
+    ref = F.conv2d(x.permute(0, 3, 1, 2), w.permute(0, 3, 1, 2), padding=dil, dilation=dil).permute(0, 2, 3, 1)
+    got = ops.conv2d_nhwc(x.to(DEV), w.to(DEV), pad=dil, dil=dil, engine=L.CONV_TC_TF32)
+    assert rel_err(got, ref) < 2e-3, rel_err(got, ref)
+
+
+def test_wrappers_reject_wrong_dtypes():
+    x16 = rnd(1, 3, 8, 8, seed=1).half().to(DEV)
+    with pytest.raises(RuntimeError):
+        ops.resize_nchw(x16, (4, 4), L.RESIZE_BILINEAR_AC)
+    with pytest.raises(RuntimeError):
+        ops.nchw_to_nhwc(x16)
+    with pytest.raises(RuntimeError):
+        ops.resize_argmax(x16, (16, 16), L.RESIZE_BILINEAR_AC)
+    sd = creff_sd(64)
+    hr, lr = rnd(1, 64, 16, 16, seed=1).to(DEV), rnd(1, 64, 8, 8, seed=2).to(DEV)
+    args = creff_args(sd)
+    with pytest.raises(RuntimeError):
+        ops.creff_fused(hr, lr, args[0].double(), *args[1:], 7, want_logits=False)
+    with pytest.raises(RuntimeError):
+        ops.creff_fused(hr.double(), lr, *args, 7, want_logits=False)
