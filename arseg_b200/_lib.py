@@ -51,6 +51,9 @@ _PROTOS = {
     "arseg_resize_argmax_nchw": ([vp, vp, vp] + [ci] * 7 + [vp], ci),
     "arseg_log_softmax_nchw": ([vp, vp, ci, ci, ci, ci, vp], ci),
     "arseg_confusion_hist":([vp, vp, vp, C.c_longlong, ci, ci, vp], ci),
+    "arseg_frame_ingest_u8": ([vp, C.POINTER(cf), C.POINTER(cf), vp, ci, ci, ci, ci, ci, ci, vp], ci),
+    "arseg_merge_motion_workspace_bytes": ([ci, ci, ci], C.c_size_t),
+    "arseg_merge_motion": ([vp, vp, C.c_size_t, vp, ci, ci, ci, vp], ci),
     "arseg_nchw_to_nhwc": ([vp, vp, ci, ci, ci, ci, ci, vp], ci),
     "arseg_nhwc_to_nchw": ([vp, ci, vp, ci, ci, ci, ci, vp], ci),
     "arseg_conv_stem7x7s2": ([vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp], ci),

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
 LIB_PATH = os.path.join(OUT_DIR, "libarseg_sm100a.so")
-SOURCES = ["ops_basic.cu", "conv_simt.cu", "conv_tc.cu", "local_attention.cu", "creff.cu", "creff_march.cu", "post.cu", "pyramid.cu", "stem_mma.cu", "creff_wide.cu", "creff_tc.cu"]
+SOURCES = ["ops_basic.cu", "conv_simt.cu", "conv_tc.cu", "local_attention.cu", "creff.cu", "creff_march.cu", "post.cu", "pyramid.cu", "stem_mma.cu", "creff_wide.cu", "creff_tc.cu", "ingest.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("ARSEG_NVCC_EXTRA", "").split()

@@ -65,6 +65,7 @@ class Plan:
         self.parts: Optional[List[torch.cuda.CUDAGraph]] = None    # split capture: [phase 1, CReFF + post]
         self.split_at: Optional[int] = None
         self.conv_flops = 0                # 2*MACs of conv/linear layers as executed
+        self.step_flops: List[int] = []    # the same, per launch (0 for launches that are not contractions)
         self.n_launches = 0
 
     # -- helpers -------------------------------------------------------------------------------
@@ -80,9 +81,11 @@ class Plan:
         self.keep.append(t)
         return t
 
-    def _add(self, name: str, fn: Callable[[int], int]) -> None:
+    def _add(self, name: str, fn: Callable[[int], int], flops: int = 0) -> None:
         self.steps.append(fn)
         self.names.append(name)
+        self.step_flops.append(int(flops))
+        self.conv_flops += int(flops)
         self.n_launches += 1
 
     def conv_weight(self, w: torch.Tensor) -> torch.Tensor:
@@ -116,8 +119,7 @@ class Plan:
         self.keep.append(d)
         fn = self.lib.arseg_conv2d_nhwc
         self._add("%s[%s %dx%d %d->%d @%dx%d]" % (name, {1: "simt", 2: "tf32", 3: "bf16", 4: "f16"}[engine], KH, KW, Cin, Cout, Ho, Wo),
-                  lambda s, d=d: fn(C.byref(d), s))
-        self.conv_flops += 2 * N * Ho * Wo * Cout * Cin * KH * KW
+                  lambda s, d=d: fn(C.byref(d), s), flops=2 * N * Ho * Wo * Cout * Cin * KH * KW)
         return out
 
     def stem(self, x_nchw: torch.Tensor, w_oihw: torch.Tensor, scale, shift, name="stem") -> torch.Tensor:
@@ -130,8 +132,7 @@ class Plan:
         fn = self.lib.arseg_conv_stem7x7s2
         args = (x_nchw.data_ptr(), w.data_ptr(), sc.data_ptr(), sh.data_ptr(), out.data_ptr(), dtype_code(self.act_dtype),
                 N, H, W, Cout)
-        self._add(name, lambda s: fn(*args, s))
-        self.conv_flops += 2 * N * Ho * Wo * Cout * 147
+        self._add(name, lambda s: fn(*args, s), flops=2 * N * Ho * Wo * Cout * 147)
         return out
 
     def maxpool(self, x: torch.Tensor) -> torch.Tensor:
@@ -191,9 +192,8 @@ class Plan:
         s_off, f_off = (0, nlev * Cout) if stages_first else (Cf, 0)
         a3 = (stage.data_ptr(), f.data_ptr(), out.data_ptr(), dtype_code(f.dtype), N, H, W, Cout, Cf, s_off, f_off, mode, cbins, nlev)
         self._add(name + ".pool", lambda s: f1(*a1, s))
-        self._add(name + ".conv1x1", lambda s: f2(*a2, s))
+        self._add(name + ".conv1x1", lambda s: f2(*a2, s), flops=2 * N * B * Cout * Cf)
         self._add(name + ".upsample_concat", lambda s: f3(*a3, s))
-        self.conv_flops += 2 * N * B * Cout * Cf
         return out
 
     def gmaxpool(self, x: torch.Tensor) -> torch.Tensor:
@@ -212,8 +212,7 @@ class Plan:
         out = self.empty((N, M), torch.float32)
         fn = self.lib.arseg_linear_f32
         args = (x.data_ptr(), wd.data_ptr(), bd.data_ptr() if bd is not None else None, out.data_ptr(), N, K, M, int(relu))
-        self._add(name, lambda s: fn(*args, s))
-        self.conv_flops += 2 * N * K * M
+        self._add(name, lambda s: fn(*args, s), flops=2 * N * K * M)
         return out
 
     def gate(self, feat: torch.Tensor, gate: torch.Tensor, gs, gb, add_identity=False, add_chan=None, add_pix=None,
@@ -230,9 +229,32 @@ class Plan:
         self._add(name, lambda s: fn(*args, s))
         return out
 
-    def to_nchw(self, x: torch.Tensor, name="nhwc_to_nchw") -> torch.Tensor:
+    def frame_ingest_u8(self, frames: torch.Tensor, Ho: int, Wo: int, mean, std, name="frame_ingest_u8") -> torch.Tensor:
+        """uint8 HWC frames -> ToTensor + Normalize + bilinear (align_corners=True) resize, fp32 NCHW (csrc/ingest.cu)."""
+        N, Hi, Wi, _ = frames.shape
+        out = self.empty((N, 3, Ho, Wo), torch.float32)
+        m, s_ = (C.c_float * 3)(*mean), (C.c_float * 3)(*std)
+        self.keep += [m, s_]
+        fn = self.lib.arseg_frame_ingest_u8
+        args = (frames.data_ptr(), m, s_, out.data_ptr(), N, Hi, Wi, Ho, Wo, L.RESIZE_BILINEAR_AC)
+        self._add(name, lambda s: fn(*args, s))
+        return out
+
+    def to_nhwc(self, x: torch.Tensor, dtype: Optional[torch.dtype] = None, name="nchw_to_nhwc") -> torch.Tensor:
+        """fp32 NCHW -> NHWC of `dtype` (default: the plan's activation dtype)."""
+        N, Cc, H, W = x.shape
+        out = self.empty((N, H, W, Cc), dtype or self.act_dtype)
+        fn = self.lib.arseg_nchw_to_nhwc
+        args = (x.data_ptr(), out.data_ptr(), dtype_code(out.dtype), N, Cc, H, W)
+        self._add(name, lambda s: fn(*args, s))
+        return out
+
+    def to_nchw(self, x: torch.Tensor, name="nhwc_to_nchw", out: Optional[torch.Tensor] = None) -> torch.Tensor:
         N, H, W, Cc = x.shape
-        out = self.empty((N, Cc, H, W), torch.float32)
+        if out is None:
+            out = self.empty((N, Cc, H, W), torch.float32)
+        elif tuple(out.shape) != (N, Cc, H, W) or out.dtype != torch.float32 or not out.is_contiguous():
+            raise ValueError("to_nchw: `out` must be a contiguous fp32 [%d,%d,%d,%d] tensor" % (N, Cc, H, W))
         fn = self.lib.arseg_nhwc_to_nchw
         args = (x.data_ptr(), dtype_code(x.dtype), out.data_ptr(), N, Cc, H, W)
         self._add(name, lambda s: fn(*args, s))

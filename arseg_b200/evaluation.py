@@ -71,7 +71,10 @@ class NonKeyEngine:
 
     def __init__(self, arch: str, sd: Dict[str, torch.Tensor], n_frames: int, H: int, W: int, scale: float = 0.5,
                  precision: str = "tf32", k: int = 7, device="cuda:0", want_logits: bool = False, want_p: bool = False,
-                 graph: bool = True, split_keyframe: bool = False):
+                 graph: bool = True, split_keyframe: bool = False, uint8_frames: bool = False,
+                 mean=ops.CAMVID_MEAN, std=ops.CAMVID_STD):
+        """uint8_frames: `imgs` is uint8 HWC [N,H,W,3] (decoded frames); ToTensor + Normalize(mean, std)
+        (dataset/camvid.py:182-185) are fused into the LR down-scale kernel -- a quarter of the host->device bytes."""
         if arch not in ARCH_INFO:
             raise KeyError(arch)
         self.arch, self.N, self.H, self.W, self.scale, self.k = arch, n_frames, H, W, scale, k
@@ -83,11 +86,15 @@ class NonKeyEngine:
         with torch.no_grad(), torch.cuda.device(self.device):
             pl = E.Plan(self.device, precision)
             self.plan = pl
-            self.imgs = pl.empty((n_frames, 3, H, W), torch.float32)
+            self.uint8_frames = uint8_frames
+            self.imgs = pl.empty((n_frames, H, W, 3), torch.uint8) if uint8_frames else pl.empty((n_frames, 3, H, W), torch.float32)
             self.mv = pl.empty((n_frames, H, W, 2), torch.int16)
             self.ref_p = pl.empty((1, C_, self.Hf, self.Wf), torch.float32)
             self.imgs.zero_(); self.mv.zero_(); self.ref_p.zero_()
-            x = pl.resize_nchw(self.imgs, self.h, self.w, L.RESIZE_BILINEAR_AC, name="frame_downscale")   # evaluation.py:186-188
+            if uint8_frames:
+                x = pl.frame_ingest_u8(self.imgs, self.h, self.w, mean, std)                              # dataset/camvid.py:182-185 + evaluation.py:186-188
+            else:
+                x = pl.resize_nchw(self.imgs, self.h, self.w, L.RESIZE_BILINEAR_AC, name="frame_downscale")   # evaluation.py:186-188
             if arch == "camvid-psp18":
                 _, p = E.build_psp_phase1(pl, sd, x, "", aux=False)
                 fin, logsm = "final_conv.", True
@@ -153,6 +160,50 @@ class NonKeyEngine:
 
     def host_pipeline(self) -> "HostPipeline":
         return HostPipeline(self)
+
+
+class KeyFrameEngine:
+    """The HR keyframe branch of a GOP as one captured step: `highres_net(ref_imgs)[-1]` of
+    evaluation.py:173-174 = the feature p the non-keyframes fuse (model/pspnet.py:76-100, model/bisenet.py:438-461,
+    model/pspnet_semseg.py:184-219 without the heads evaluation.py never reads).
+
+    Input: `img` fp32 [1,3,H,W] (or uint8 HWC with uint8_frames).  Output: `p` fp32 NCHW [1,C,H/stride,W/stride] -- pass
+    `out=` (e.g. a NonKeyEngine's `ref_p`) to have the step write the feature where its consumer reads it."""
+
+    def __init__(self, arch: str, sd: Dict[str, torch.Tensor], H: int, W: int, precision: str = "tf32", device="cuda:0",
+                 out: Optional[torch.Tensor] = None, graph: bool = True, uint8_frames: bool = False,
+                 mean=ops.CAMVID_MEAN, std=ops.CAMVID_STD):
+        if arch not in ARCH_INFO:
+            raise KeyError(arch)
+        C_, stride, _ = ARCH_INFO[arch]
+        self.arch, self.H, self.W, self.C = arch, H, W, C_
+        self.device = torch.device(device)
+        with torch.no_grad(), torch.cuda.device(self.device):
+            pl = E.Plan(self.device, precision)
+            self.plan = pl
+            if uint8_frames:
+                self.img = pl.empty((1, H, W, 3), torch.uint8)
+                self.img.zero_()
+                x = pl.frame_ingest_u8(self.img, H, W, mean, std)
+            else:
+                self.img = pl.empty((1, 3, H, W), torch.float32)
+                self.img.zero_()
+                x = self.img
+            if arch == "camvid-psp18":
+                _, p = E.build_psp_phase1(pl, sd, x, "", aux=False)
+            elif arch == "cityscapes-psp18":
+                _, p = E.build_semseg_phase1(pl, sd, x, "")
+            else:
+                _, _, p = E.build_bisenet_phase1(pl, sd, x, "", aux=False)
+            self.p = pl.to_nchw(p, name="p_to_nchw", out=out)
+            if graph:
+                pl.capture()
+        self.conv_flops = pl.conv_flops
+        self.launches_per_step = pl.n_launches
+
+    def step(self) -> torch.Tensor:
+        self.plan.run()
+        return self.p
 
 
 class HostPipeline:

@@ -105,7 +105,7 @@ class _PlannedNet(nn.Module):
         nn.parallel.replicate keeps its parameter copies as plain attributes (`_parameters` is empty), so the tensors are
         collected from `_parameters`, the instance dict and `_buffers` of every sub-module."""
         out: Dict[str, torch.Tensor] = {}
-        for prefix, m in self.named_modules():
+        for prefix, m in self.named_modules(remove_duplicate=False):     # aliases (final_conv = cls.4 / conv_out.conv_out) keep both names
             names = list(m._parameters.keys()) + [k for k, v in m.__dict__.items() if isinstance(v, torch.Tensor)] + list(m._buffers.keys())
             for k in names:
                 v = m._parameters.get(k)
@@ -120,6 +120,13 @@ class _PlannedNet(nn.Module):
     def load_state_dict(self, *a, **k):
         self._wgen = getattr(self, "_wgen", 0) + 1
         return super().load_state_dict(*a, **k)
+
+    static_outputs = False     # True: forwards return the plan's own output buffers (valid until the next call) instead of clones
+
+    def _out(self, t):
+        if t is None or self.static_outputs:
+            return t
+        return t.clone()
 
     def _get_plan(self, kind: str, shapes: tuple, device: torch.device, build):
         prec = self.precision or default_precision()
@@ -153,7 +160,12 @@ def _run_phase2(net: _PlannedNet, p: torch.Tensor, ref_p: torch.Tensor, *, final
     def build(pl: E.Plan, sd):
         hr = pl.empty((N, Cc, H, W), torch.float32)
         lr = pl.empty(tuple(p.shape), torch.float32)
-        out_p, out_l, _ = pl.creff(hr, lr, sd, "fuse_attention.", k, lr_layout=L.NCHW,
+        lr_in, lr_layout = lr, L.NCHW
+        if pl.precision != "fp32" and Cc % 64 == 0:
+            # the tensor-core CReFF engines take NHWC operands: one transpose launch for the LR feature (the keyframe
+            # feature's is inside Plan.creff), instead of falling back to the exact SIMT kernel (8x slower at 720x960)
+            lr_in, lr_layout = pl.to_nhwc(lr, name="lr_nchw_to_nhwc"), L.NHWC
+        out_p, out_l, _ = pl.creff(hr, lr_in, sd, "fuse_attention.", k, lr_layout=lr_layout,
                                    wcls=sd[final_prefix + "weight"], bcls=sd[final_prefix + "bias"],
                                    log_softmax=log_softmax)
         if up is not None:
@@ -164,6 +176,10 @@ def _run_phase2(net: _PlannedNet, p: torch.Tensor, ref_p: torch.Tensor, *, final
     hr.copy_(ref_p)
     lr.copy_(p)
     pl.run()
+    if getattr(net, "static_outputs", False):
+        # the plan's own output buffers: valid until the next forward_phase2 of this module on this shape (the contract
+        # of a CUDA-graph static output); saves two device copies (210 MB at 720x960) per call
+        return out_l, out_p
     return out_l.clone(), out_p.clone()
 
 
@@ -206,7 +222,8 @@ class _PSPBase(_PlannedNet):
         pl, (xin, cls, p_nchw, logp) = self._get_plan("hr" if head else "phase1", (N, H, W), x.device, build)
         xin.copy_(x)
         pl.run()
-        return (logp.clone() if logp is not None else None), cls.clone(), p_nchw.clone()
+        c = self._out
+        return c(logp), c(cls), c(p_nchw)
 
 
 class PSPNet(_PSPBase):
@@ -304,7 +321,8 @@ class PSPNetWithFuse_Cityscapes(_PlannedNet):
         pl, (xin, x3, p, out, aux) = self._get_plan("hr" if full else "phase1", (N, H, W), x.device, build)
         xin.copy_(x)
         pl.run()
-        return x3.clone(), p.clone(), (out.clone() if out is not None else None), (aux.clone() if aux is not None else None)
+        c = self._out
+        return c(x3), c(p), c(out), c(aux)
 
     def forward_phase1(self, x):
         x3, p, _, _ = self._trunk(x, full=False)
@@ -388,7 +406,7 @@ class _BiSeBase(_PlannedNet):
         pl, (xin, o16, o32, mid, out) = self._get_plan("hr" if head else "phase1", (N, H, W), x.device, build)
         xin.copy_(x)
         pl.run()
-        c = lambda t: t.clone() if t is not None else None
+        c = self._out
         return c(out), c(o16), c(o32), c(mid)
 
 

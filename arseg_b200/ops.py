@@ -171,6 +171,43 @@ def confusion_hist(pred: torch.Tensor, label: torch.Tensor, n_classes: int, igno
     return hist
 
 
+CAMVID_MEAN, CAMVID_STD = (0.39068785, 0.40521392, 0.41434407), (0.29652068, 0.30514979, 0.30080369)   # dataset/camvid.py:184
+
+
+def frame_ingest_u8(frames: torch.Tensor, size, mean=CAMVID_MEAN, std=CAMVID_STD, mode: int = L.RESIZE_BILINEAR_AC,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """uint8 HWC frames [N,H,W,3] -> ToTensor + Normalize (dataset/camvid.py:182-185) -> bilinear resize to `size`
+    (evaluation.py:186-188), fp32 NCHW, one kernel."""
+    _chk_cuda("frame_ingest_u8", frames, out)
+    if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[-1] != 3:
+        raise RuntimeError("frame_ingest_u8: expected uint8 [N,H,W,3] frames")
+    N, Hi, Wi, _ = frames.shape
+    Ho, Wo = int(size[0]), int(size[1])
+    if out is None:
+        out = torch.empty((N, 3, Ho, Wo), dtype=torch.float32, device=frames.device)
+    m, s_ = (C.c_float * 3)(*mean), (C.c_float * 3)(*std)
+    with torch.cuda.device(frames.device):
+        L.check(L.load().arseg_frame_ingest_u8(_p(frames), m, s_, _p(out), N, Hi, Wi, Ho, Wo, mode, _stream()), "frame_ingest_u8")
+    return out
+
+
+def merge_motion(maps: torch.Tensor) -> torch.Tensor:
+    """mergeMotion (pre-process/generate_compressed_dataset_camvid.py:6-56) on the device: decoder maps int16 [F,H,W,3]
+    (mvx, mvy quarter-pel, refIdx; frames 1..F of a GOP) -> merged quarter-pel MV fields int16 [F,H,W,2] pointing to the keyframe
+    (plane F-1 = the `.bin` of the frame at keyframe distance F, dataset/camvid.py:624-626)."""
+    _chk_cuda("merge_motion", maps)
+    if maps.dtype != torch.int16 or maps.dim() != 4 or maps.shape[-1] != 3:
+        raise RuntimeError("merge_motion: expected int16 [F,H,W,3] decoder maps")
+    Fn, H, W, _ = maps.shape
+    out = torch.empty((Fn, H, W, 2), dtype=torch.int16, device=maps.device)
+    with torch.cuda.device(maps.device):
+        lib = L.load()
+        need = int(lib.arseg_merge_motion_workspace_bytes(Fn, H, W))
+        ws = torch.empty(need, dtype=torch.uint8, device=maps.device)
+        L.check(lib.arseg_merge_motion(_p(maps), _p(ws), need, _p(out), Fn, H, W, _stream()), "merge_motion")
+    return out
+
+
 def nchw_to_nhwc(x: torch.Tensor, dtype: torch.dtype = torch.float32) -> torch.Tensor:
     x = x.contiguous()
     _chk_cuda("nchw_to_nhwc", x)

@@ -124,3 +124,25 @@ def mv_to_flow(mv: np.ndarray) -> torch.Tensor:
 def lr_size(h: int, w: int, scale: float) -> Sequence[int]:
     """evaluation.py:186-187 -- int() truncation of the float product (0.7*720 -> 503)."""
     return [int(h * scale), int(w * scale)]
+
+
+def synth_decoder_maps(F: int, H: int, W: int, seed: int) -> np.ndarray:
+    """Per-frame HEVC MV maps as the patched dec265 dumps them (`test_%03d.bin`, short[H][W][3] = mvx, mvy quarter-pel,
+    refIdx; pre-process/libde265 de265.cc:927-1040): block-constant on a 16x16 grid with a few 8x8 splits, quarter-pel
+    (NOT only integer-pel) vectors, refIdx in {0,1,2}, ~10 % intra blocks (refIdx -1) and a few out-of-range refIdx values."""
+    rng = np.random.default_rng(seed)
+    out = np.zeros((F, H, W, 3), dtype=np.int16)
+    for f in range(F):
+        for bs in (16, 8):
+            by, bx = (H + bs - 1) // bs, (W + bs - 1) // bs
+            mv = np.stack([rng.integers(-96, 97, (by, bx)), rng.integers(-48, 49, (by, bx)), rng.integers(0, 3, (by, bx))], -1)
+            intra = rng.random((by, bx)) < 0.10
+            mv[intra] = (0, 0, -1)
+            mv[rng.random((by, bx)) < 0.02, 2] = 90
+            full = np.repeat(np.repeat(mv, bs, 0), bs, 1)[:H, :W]
+            if bs == 16:
+                out[f] = full
+            else:
+                split = np.repeat(np.repeat(rng.random((by, bx)) < 0.15, bs, 0), bs, 1)[:H, :W]
+                out[f][split] = full[split]
+    return out

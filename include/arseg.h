@@ -84,6 +84,19 @@ int arseg_log_softmax_nchw(const float* in, float* out, int N, int ncls, int H, 
 int arseg_confusion_hist(const uint8_t* pred, const int64_t* label, long long* hist,
                          long long npix, int ncls, int ignore_label, arseg_stream_t stream);
 
+/* Frame ingest: uint8 HWC frames [N,Hi,Wi,3] (decoded PNG / video) -> transforms.ToTensor + Normalize(mean, std)
+ * (dataset/camvid.py:182-185; dataset/cityscapes.py:88-93) -> bilinear resize to [Ho,Wo] (evaluation.py:186-188 uses
+ * align_corners=True = ARSEG_RESIZE_BILINEAR_AC), fp32 NCHW [N,3,Ho,Wo].  mean / std: HOST float[3], read during the call. */
+int arseg_frame_ingest_u8(const uint8_t* src, const float* mean, const float* stdv, float* dst, int N, int Hi, int Wi,
+                          int Ho, int Wo, int mode, arseg_stream_t stream);
+/* mergeMotion(workspace_dir, 0, F) (pre-process/generate_compressed_dataset_camvid.py:6-56): chains the per-frame MV maps
+ * of the patched HEVC decoder (maps int16 [F,H,W,3] = mvx, mvy quarter-pel, refIdx of frames 1..F; frame 0 = the keyframe)
+ * back to the keyframe.  out int16 [F,H,W,2] = the merged quarter-pel MV field of every frame 1..F (frame F's plane is the
+ * `.bin` the dataset loads, dataset/camvid.py:624-626).  workspace: >= arseg_merge_motion_workspace_bytes(F,H,W) bytes. */
+size_t arseg_merge_motion_workspace_bytes(int F, int H, int W);
+int arseg_merge_motion(const int16_t* maps, void* workspace, size_t workspace_bytes, int16_t* out, int F, int H, int W,
+                       arseg_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * 3. Layout conversion at the API edge
  * ---------------------------------------------------------------------------------------------- */

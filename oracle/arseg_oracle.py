@@ -504,3 +504,43 @@ def confusion_hist(preds: torch.Tensor, label: torch.Tensor, n_classes: int, ign
     keep = label != ignore_label
     return torch.bincount(label[keep] * n_classes + preds[keep], minlength=n_classes ** 2
                           ).view(n_classes, n_classes).float()
+
+
+# ----------------------------------------------------------------------------------------------
+# data formats either side of the path
+# ----------------------------------------------------------------------------------------------
+def ingest_u8(frames_u8: torch.Tensor, mean, std, size) -> torch.Tensor:
+    """uint8 HWC frames [N,H,W,3] -> transforms.ToTensor + Normalize (dataset/camvid.py:182-185) -> the LR down-scale of
+    evaluation.py:186-188 (bilinear, align_corners=True)."""
+    x = frames_u8.permute(0, 3, 1, 2).to(torch.float32).div(255)                    # ToTensor
+    m = torch.tensor(mean, dtype=torch.float32).view(1, 3, 1, 1)
+    s = torch.tensor(std, dtype=torch.float32).view(1, 3, 1, 1)
+    x = (x - m) / s                                                                  # Normalize
+    return F.interpolate(x, list(size), mode="bilinear", align_corners=True)
+
+
+def merge_motion(maps):
+    """mergeMotion(workspace_dir, 0, F) (pre-process/generate_compressed_dataset_camvid.py:6-56) on in-memory decoder maps.
+
+    maps: int16 [F,H,W,3] = (mvx, mvy quarter-pel, refIdx) of frames 1..F as dumped by the patched dec265 (`test_%03d.bin`).
+    Returns int32 [H,W,F+1,2] exactly like the reference (plane 0 stays -1; planes 1..F = merged quarter-pel MVs)."""
+    import numpy as np
+    maps = np.asarray(maps)
+    Fn, h, w, _ = maps.shape
+    max_ref_num = 3                                                                  # :10
+    dp = np.ones([h, w, Fn + 1, 3], dtype=np.int32) * -1                             # :12
+    k1, j1 = np.meshgrid(range(w), range(h))                                         # :24
+    for f1 in range(1, Fn + 1):
+        flow = maps[f1 - 1].astype(np.int16).copy()
+        intra = np.logical_or(flow[..., 2] < 0, flow[..., 2] >= max_ref_num)         # :20
+        flow[intra] = 0                                                              # :21-22
+        j2 = np.clip(j1 + np.round(flow[..., 1] / 4).astype(int), 0, h - 1)          # :25, :33 (np.round: half to even)
+        k2 = np.clip(k1 + np.round(flow[..., 0] / 4).astype(int), 0, w - 1)          # :26, :34
+        f2 = np.maximum(0, f1 - flow[..., 2].astype(int) - 1)                        # :27
+        parent = dp[j2, k2, f2]                                                      # [h,w,3]
+        father = np.stack([k2, j2, f2], axis=-1).astype(np.int32)
+        # :37-48 (the `== 90` branch is dead: refIdx 90 was zeroed by the intra mask above)
+        dp[:, :, f1] = np.where((parent[..., 2] != -1)[..., None], parent, father)
+    dp[:, :, 1:, 0] = (dp[:, :, 1:, 0] - k1[..., None]) * 4                          # :53
+    dp[:, :, 1:, 1] = (dp[:, :, 1:, 1] - j1[..., None]) * 4                          # :54
+    return dp[:, :, :, :2]

@@ -117,3 +117,29 @@ def test_module_prefixed_checkpoint_loads():
     net = models.models_fuse["camvid-psp18"]()
     sd = {"module." + k: v for k, v in synth.synth_state_dict(net.state_dict(), 4).items()}
     torch.nn.DataParallel(net).load_state_dict(sd)
+
+
+def test_merge_motion_oracle_matches_reference_golden():
+    """oracle.merge_motion against the golden recorded from the unmodified reference's mergeMotion
+    (pre-process/generate_compressed_dataset_camvid.py:6-56; tests/golden/make_merge_motion_golden.py), 720x960, 4 frames."""
+    import os
+    import zlib
+    import numpy as np
+    from arseg_b200 import synth
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "merge_motion.npz"))
+    Fn, H, W = int(g["F"]), int(g["H"]), int(g["W"])
+    out = O.merge_motion(synth.synth_decoder_maps(Fn, H, W, int(g["seed"])))
+    assert out.shape == (H, W, Fn + 1, 2) and (out[:, :, 0] == -1).all()
+    assert np.array_equal(out[:, :, Fn].astype(np.int16), g["last"])
+    for f in range(Fn + 1):
+        assert zlib.crc32(np.ascontiguousarray(out[:, :, f].astype(np.int16)).tobytes()) == int(g["crcs"][f])
+
+
+def test_ingest_u8_oracle_is_totensor_normalize_interpolate():
+    import torch
+    g = torch.Generator().manual_seed(3)
+    fr = torch.randint(0, 256, (1, 10, 12, 3), generator=g, dtype=torch.uint8)
+    out = O.ingest_u8(fr, (0.39068785, 0.40521392, 0.41434407), (0.29652068, 0.30514979, 0.30080369), (10, 12))
+    want = (fr.permute(0, 3, 1, 2).float() / 255 - torch.tensor([0.39068785, 0.40521392, 0.41434407]).view(1, 3, 1, 1)) / \
+        torch.tensor([0.29652068, 0.30514979, 0.30080369]).view(1, 3, 1, 1)
+    assert torch.allclose(out, want, atol=1e-6)

@@ -279,3 +279,121 @@ def test_dropin_models_run_as_dataparallel_replicas():
     yn = hr(imgs.to(DEV))
     for a, b in zip(yr, yn):
         assert torch.equal(a, b)
+
+
+# ---------------------------------------------------------------- drop-in `localAttention` module, as the reference imports it
+def test_import_localAttention_through_the_reference_wrappers():
+    """`dropin/` on sys.path makes `import localAttention` resolve to this repo; the reference's autograd wrappers
+    similarFunction / weightingFunction (model/attention.py:13-53, restated here) then run forward AND backward on the sm_100a
+    kernels.  Checked against the oracle ops under torch autograd."""
+    import importlib
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.modules.pop("localAttention", None)
+    sys.path.insert(0, os.path.join(root, "dropin"))
+    try:
+        la = importlib.import_module("localAttention")
+    finally:
+        sys.path.pop(0)
+    assert os.path.dirname(la.__file__).startswith(os.path.join(root, "dropin"))
+
+    class similarFunction(torch.autograd.Function):          # model/attention.py:13-30
+        @staticmethod
+        def forward(ctx, x_ori, x_loc, kH, kW):
+            ctx.save_for_backward(x_ori, x_loc)
+            ctx.kHW = (kH, kW)
+            return la.similar_forward(x_ori, x_loc, kH, kW)
+
+        @staticmethod
+        def backward(ctx, grad_outputs):
+            x_ori, x_loc = ctx.saved_tensors
+            kH, kW = ctx.kHW
+            return (la.similar_backward(x_loc, grad_outputs, kH, kW, True), la.similar_backward(x_ori, grad_outputs, kH, kW, False),
+                    None, None)
+
+    class weightingFunction(torch.autograd.Function):        # model/attention.py:33-50
+        @staticmethod
+        def forward(ctx, x_ori, x_weight, kH, kW):
+            ctx.save_for_backward(x_ori, x_weight)
+            ctx.kHW = (kH, kW)
+            return la.weighting_forward(x_ori, x_weight, kH, kW)
+
+        @staticmethod
+        def backward(ctx, grad_outputs):
+            x_ori, x_weight = ctx.saved_tensors
+            kH, kW = ctx.kHW
+            return la.weighting_backward_ori(x_weight, grad_outputs, kH, kW), la.weighting_backward_weight(x_ori, grad_outputs, kH, kW), None, None
+
+    g = torch.Generator().manual_seed(31)
+    q, kk, v = (torch.randn(2, 16, 11, 13, generator=g) for _ in range(3))
+    kH = kW = 5
+    with torch.enable_grad():
+        # MyAttention.forward's core (model/attention.py:199-207) on the GPU through the wrappers
+        qg, kg, vg = (t.clone().to(DEV).requires_grad_(True) for t in (q, kk, v))
+        a = torch.softmax(similarFunction.apply(qg, kg, kH, kW), dim=3)
+        o = weightingFunction.apply(vg, a, kH, kW)
+        (o * o).sum().backward()
+        # the same with the oracle ops (differentiable torch restatements) on the CPU
+        qc, kc, vc = (t.clone().requires_grad_(True) for t in (q, kk, v))
+        ac = torch.softmax(O.similar_forward(qc, kc, kH, kW), dim=3)
+        oc = O.weighting_forward(vc, ac, kH, kW)
+        (oc * oc).sum().backward()
+    assert rel_err(o, oc) < 1e-5
+    for got, want in ((qg.grad, qc.grad), (kg.grad, kc.grad), (vg.grad, vc.grad)):
+        assert rel_err(got, want) < 1e-4
+
+
+# ---------------------------------------------------------------- HR keyframe branch in the engine, uint8 ingest
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "f16"])
+@pytest.mark.parametrize("arch,H,W", [("camvid-psp18", 64, 96), ("camvid-bise18", 96, 128), ("cityscapes-psp18", 64, 128)])
+def test_keyframe_engine_matches_oracle(arch, H, W, precision):
+    """KeyFrameEngine (captured HR forward up to p) == highres_net(ref_imgs)[-1] of evaluation.py:173-174 (oracle)."""
+    net = models.models[arch]()
+    sd = synth.synth_state_dict(net.state_dict(), 4)
+    x = synth.synth_frame(1, H, W, 2)
+    ref = {"camvid-psp18": O.pspnet_hr, "camvid-bise18": O.bisenet_hr, "cityscapes-psp18": O.semseg_hr}[arch](sd, x)[-1]
+    eng = ev.KeyFrameEngine(arch, sd, H, W, precision, device=DEV)
+    eng.img.copy_(x.to(DEV))
+    p = eng.step()
+    tmax, trms, _ = TOL[precision]
+    assert tuple(p.shape) == tuple(ref.shape)
+    assert rel_err(p, ref) < max(tmax, 1e-4) and rms_err(p, ref) < max(trms, 5e-5)
+
+
+def test_keyframe_engine_full_shape_feeds_the_nonkey_engine():
+    """720x960 PSPNet-18 keyframe in the f16 plan against the oracle, written straight into a NonKeyEngine's keyframe-feature
+    buffer (whole-GOP path: HR forward + 11 non-keyframes)."""
+    arch, H, W = "camvid-psp18", 720, 960
+    net = models.models[arch]()
+    sd = synth.synth_state_dict(net.state_dict(), 4)
+    x = synth.synth_frame(1, H, W, 2)
+    ref = O.pspnet_hr(sd, x)[-1]
+    nk = ev.NonKeyEngine(arch, synth.synth_state_dict(models.models_fuse[arch]().state_dict(), 4), 1, H, W, 0.5, "f16", device=DEV)
+    kf = ev.KeyFrameEngine(arch, sd, H, W, "f16", device=DEV, out=nk.ref_p)
+    kf.img.copy_(x.to(DEV))
+    p = kf.step()
+    assert p.data_ptr() == nk.ref_p.data_ptr()
+    tmax, trms, _ = TOL["f16"]
+    assert rel_err(p, ref) < tmax and rms_err(p, ref) < trms
+    nk.step()
+    torch.cuda.synchronize()
+
+
+def test_uint8_frame_ingest_engine_matches_float_engine():
+    """uint8 HWC frames + on-device ToTensor / Normalize (dataset/camvid.py:182-185) == the fp32 engine fed with the frames
+    normalised on the host the way the dataset does."""
+    g = load_golden("camvid_psp18_s05")
+    arch, _, sd, imgs, ref_p, mv, flow, scale = case_setup(g)
+    H, W = imgs.shape[-2:]
+    gen = torch.Generator().manual_seed(12)
+    u8 = torch.randint(0, 256, (2, H, W, 3), generator=gen, dtype=torch.uint8)
+    f32 = O.ingest_u8(u8, ops.CAMVID_MEAN, ops.CAMVID_STD, (H, W))        # ToTensor + Normalize at full resolution
+    mvs = torch.from_numpy(np.stack([mv, synth.synth_mv_int16(H, W, 77, distance=3)]))
+    a = ev.NonKeyEngine(arch, sd, 2, H, W, scale, "fp32", device=DEV, want_logits=True)
+    b = ev.NonKeyEngine(arch, sd, 2, H, W, scale, "fp32", device=DEV, want_logits=True, uint8_frames=True)
+    a.set_inputs(f32.to(DEV), mvs.to(DEV), ref_p.to(DEV))
+    b.set_inputs(u8.to(DEV), mvs.to(DEV), ref_p.to(DEV))
+    pa, pb = a.step().clone(), b.step().clone()
+    assert rel_err(b.logits, a.logits) < 1e-5
+    assert float((pa != pb).float().mean()) < 1e-3

@@ -3,6 +3,8 @@
 Tolerances (stated per test): exact-arithmetic fp32 kernels agree with the CPU fp32 reference up to
 summation order -> 2e-5 relative to the tensor's max magnitude; TF32 tensor-core convs 2e-3; bf16 2e-2.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -648,3 +650,40 @@ def test_wrappers_reject_wrong_dtypes():
         ops.creff_fused(hr, lr, args[0].double(), *args[1:], 7, want_logits=False)
     with pytest.raises(RuntimeError):
         ops.creff_fused(hr.double(), lr, *args, 7, want_logits=False)
+
+
+# ---------------------------------------------------------------- data formats either side of the path
+@pytest.mark.parametrize("Hi,Wi,Ho,Wo", [(72, 96, 36, 48), (72, 96, 50, 67), (33, 41, 33, 41)])
+def test_frame_ingest_u8(Hi, Wi, Ho, Wo):
+    """uint8 HWC -> ToTensor + Normalize (dataset/camvid.py:182-185) -> LR down-scale (evaluation.py:186-188) in one kernel."""
+    g = torch.Generator().manual_seed(9)
+    fr = torch.randint(0, 256, (2, Hi, Wi, 3), generator=g, dtype=torch.uint8)
+    ref = O.ingest_u8(fr, ops.CAMVID_MEAN, ops.CAMVID_STD, (Ho, Wo))
+    got = ops.frame_ingest_u8(fr.to(DEV), (Ho, Wo))
+    assert rel_err(got, ref) < 1e-6
+
+
+@pytest.mark.parametrize("Fn,H,W", [(1, 16, 24), (5, 37, 53), (11, 64, 96)])
+def test_merge_motion_matches_oracle(Fn, H, W):
+    """GPU mergeMotion == the oracle's restatement of generate_compressed_dataset_camvid.py:6-56, bit for bit (integers)."""
+    from arseg_b200 import synth
+    maps = synth.synth_decoder_maps(Fn, H, W, 21)
+    ref = O.merge_motion(maps)                                  # [H,W,F+1,2] int32
+    got = ops.merge_motion(torch.from_numpy(maps).to(DEV)).cpu().numpy()
+    for f in range(1, Fn + 1):
+        assert np.array_equal(got[f - 1], ref[:, :, f].astype(np.int16)), f
+
+
+def test_merge_motion_matches_reference_golden():
+    """720x960, 4 frames: the golden recorded from the UNMODIFIED reference function (tests/golden/make_merge_motion_golden.py)."""
+    import zlib
+    from arseg_b200 import synth
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "merge_motion.npz"))
+    Fn, H, W = int(g["F"]), int(g["H"]), int(g["W"])
+    maps = synth.synth_decoder_maps(Fn, H, W, int(g["seed"]))
+    got = ops.merge_motion(torch.from_numpy(maps).to(DEV)).cpu().numpy()
+    assert np.array_equal(got[Fn - 1], g["last"])
+    for f in range(1, Fn + 1):
+        assert zlib.crc32(np.ascontiguousarray(got[f - 1]).tobytes()) == int(g["crcs"][f])
+    # the merged field is the MV input of the non-keyframe path: integer-pel multiples, pointing inside the frame
+    assert (got % 4 == 0).all()
