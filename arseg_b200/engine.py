@@ -478,11 +478,13 @@ def build_psp_phase1(pl: Plan, sd: SD, x_nchw: torch.Tensor, p: str = "", sizes=
         Nn, hh, ww, _ = t.shape
         t = pl.resize(t, 2 * hh, 2 * ww, L.RESIZE_BILINEAR, name=u + "upsample")
         sc, sh = fold_bn(sd, p + u + "conv.1.", sd[p + u + "conv.0.bias"])
-        # up_3 produces the LR feature p (the residual of the CReFF kernel): f16 in the 'f16' plan (11-bit significand, the
-        # tcgen05 CReFF engine's operand type), fp32 in the 'bf16' plan
+        # up_3 produces the LR feature p (the residual of the CReFF kernel): kept fp32 in 16-bit plans -- the march engine gathers
+        # it fastest as fp32 (3.33 ms per 11 frames, 4.39 ms from an f16 feature) -- except for the opt-in tcgen05 CReFF engine,
+        # whose operands are f16
+        tc_creff = pl.precision == "f16" and os.environ.get("ARSEG_CREFF_TC", "0") == "1"
         t = pl.conv(t, sd[p + u + "conv.0.weight"], sc, sh, pad=1, act=L.ACT_PRELU,
                     slope=float(sd[p + u + "conv.2.weight"].reshape(-1)[0]), name=u + "conv",
-                    out_f32=(u == "up_3." and pl.precision != "f16"))
+                    out_f32=(u == "up_3." and not tc_creff))
     cls = None
     if aux:                                                         # model/pspnet.py:215-217
         a = pl.gmaxpool(x3)

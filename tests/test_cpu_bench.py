@@ -15,13 +15,27 @@ def _bench():
 
 
 def test_algorithmic_bytes_match_survey_8d():
-    """176.9 + 44.2 + 2.8 + 176.9 + 33.2 = 434.0 MB per frame (CamVid-PSP, AR-0.5x), and the bytes the engine
-    has to move when the fused p is not materialised (fp32 LR feature, log-probs + u8 class map out)."""
+    """176.9 + 44.2 + 2.8 + 176.9 + 33.2 = 434.0 MB per frame (CamVid-PSP, AR-0.5x); the bytes ONE launch has to
+    move count the keyframe feature once per launch (the 11 frames of a GOP share it) and no fused-p write."""
     b = _bench()
-    assert abs(b.CREFF_BYTES_FULL / 1e6 - 434.0) < 0.5
-    moved = b.creff_bytes(4, write_p=False, write_logits=True)
-    assert abs(moved / 1e6 - (176.9 + 44.2 + 2.8 + 33.2 + 0.7)) < 0.5
-    assert b.creff_bytes(4, True, True) - moved == 64 * 720 * 960 * 4
+    lr_numel, logits_numel = 64 * 360 * 480, 12 * 720 * 960
+    assert abs(b.creff_bytes_survey_8d(lr_numel, logits_numel) / 1e6 - 434.0) < 0.5
+    one = b.creff_bytes_moved(1, 4, lr_numel, 4, logits_numel, write_p=False)
+    assert abs(one / 1e6 - (176.9 + 44.2 + 2.8 + 33.2 + 0.7)) < 0.5
+    eleven = b.creff_bytes_moved(11, 4, lr_numel, 4, logits_numel, write_p=False)
+    assert abs(eleven / 1e6 - (176.9 + 11 * (44.2 + 2.8 + 33.2 + 0.7))) < 1.0          # 1.07 GB: what ncu measures as DRAM traffic
+    assert b.creff_bytes_moved(1, 4, lr_numel, 4, logits_numel, True) - one == 64 * 720 * 960 * 4
+    # f16 LR feature (the f16 plan) and f16 keyframe feature (tcgen05 engine) halve those terms
+    assert one - b.creff_bytes_moved(1, 2, lr_numel, 2, logits_numel, False) == (64 * 720 * 960 + lr_numel) * 2
+
+
+def test_workloads_cover_baseline_configs():
+    b = _bench()
+    assert set(b.WORKLOADS) == {"camvid-psp18", "camvid-bise18", "cityscapes-psp18"}
+    b.set_workload("cityscapes-psp18")
+    assert (b.H, b.W, b.C_P, b.STRIDE_P, b.N_CLS) == (1024, 2048, 512, 8, 19) and "1024x2048" in b.metric_name()
+    b.set_workload("camvid-psp18")
+    assert "720x960" in b.metric_name()
 
 
 def test_peaks_come_from_measured_file_when_present():
