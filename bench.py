@@ -44,7 +44,8 @@ def set_workload(name: str) -> None:
 
 
 def metric_name() -> str:
-    return "non-keyframe frames/sec @%dx%d GOP12 (%s)" % (H, W, WL_LABEL.split(" GOP-12 ")[0] + " " + WL_LABEL.split(" GOP-12 ")[1])
+    dataset = WL_LABEL.split(" ")[0]                              # "CamVid" / "Cityscapes"
+    return "non-keyframe frames/sec @%dx%d GOP12 (%s %s)" % (H, W, dataset, WL_LABEL.split(" GOP-12 ")[1])
 
 
 def creff_bytes_survey_8d(lr_numel_per_frame: int, logits_numel_per_frame: int) -> int:
@@ -220,6 +221,12 @@ def main():
                 "e2e": {"value": r["fps"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
+
+    # stdout carries exactly ONE line (the JSON): whatever libraries print while initialising (e.g. NCCL's version banner)
+    # goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -475,7 +482,10 @@ def main():
         line["alt_precision"] = {"precision": args.alt_precision, "dtype": dnames[args.alt_precision], "value": round(alt_r["value"], 2),
                                  "ms_per_step": round(alt_r["ms"] / args.steps, 4), "e2e": round(alt_r["e2e"], 2),
                                  "creff_ms": a_creff["ms_per_launch"], "conv_tflops": a_conv["achieved"], "conv_frac": a_conv["frac"]}
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    print(json.dumps(line), flush=True)
+    os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
