@@ -233,7 +233,15 @@ __device__ __forceinline__ void t_fhfma(float& acc, uint16_t a, uint16_t b) {
     asm("fma.rn.f32.f16 %0, %1, %2, %0;" : "+f"(acc) : "h"(a), "h"(b));
 }
 __device__ __forceinline__ float2 t_h2f(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
+#ifdef ARSEG_TC_NOALLOC
+__device__ __forceinline__ uint4 t_ldg128(const char* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+#else
 __device__ __forceinline__ uint4 t_ldg128(const char* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+#endif
 
 struct TSmem {
     uint32_t sK, sV, sQ, sW, sOnes, rings;       // shared-window addresses; rings = hr ring, lr ring, scratch
@@ -998,6 +1006,9 @@ static int creff_tc_launch_n(CreffMmaParams& p, void* ws, size_t ws_bytes, cudaS
     ARSEG_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !configured[dev]) {
         ARSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cf::SMEM));
+        // keep what is left of the 228 KB as L1: the gather's memory-level parallelism is bounded by the L1 lines its
+        // outstanding misses can allocate
+        ARSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)((Cf::SMEM + 1024) * 100 / (228 * 1024)) + 1));
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     ARSEG_REQUIRE(ws && ws_bytes >= creff_tc_workspace_bytes(p.N, p.H, p.W) && ((uintptr_t)ws % 16) == 0,

@@ -262,29 +262,40 @@ class Plan:
 
     def creff(self, hr: torch.Tensor, lr: torch.Tensor, sd: SD, prefix: str, k: int, *, flow: Optional[torch.Tensor] = None,
               hr_shared=False, lr_layout=L.NHWC, wcls=None, bcls=None, log_softmax=False, want_p=True, want_logits=True,
-              want_argmax=False, name="creff_fused", engine=None):
+              want_argmax=False, name="creff_fused", engine=None, hr_layout=L.NCHW):
         """Fused MV-warp + CReFF (+ classifier).  hr NCHW fp32 [1|N,C,H,W]; lr [N,h,w,C] NHWC (or NCHW fp32).
         engine None: exact fp32 SIMT kernel in 'fp32' plans; tensor-core window attention (f16 operands, fp32
         accumulate) in 'tf32'/'f16'/'bf16' plans when C is a multiple of 64 (hr is first converted to NHWC by one transpose
         launch; C = 64: column-marching engine, C > 64: the two-launch wide engine with a plan-owned workspace)."""
-        _, Cc, H, W = hr.shape
+        if hr_layout == L.NHWC:         # the keyframe feature already in the internal layout (fp32 [1|N,H,W,C]): no transpose launch
+            _, H, W, Cc = hr.shape
+        else:
+            _, Cc, H, W = hr.shape
         if engine is None:
             mma_ok = (self.precision != "fp32" and Cc % 64 == 0 and Cc <= 1024 and lr_layout == L.NHWC and k in (3, 5, 7, 9)
                       and (wcls is None or wcls.shape[0] <= 32) and min(H, W) >= 2)
             engine = L.CREFF_MMA_F16 if mma_ok else L.CREFF_EXACT_F32
-        hr_layout = L.NCHW
+        hr_in_nhwc = hr_layout == L.NHWC
         # C = 64 with an f16 LR feature (the 'f16' plan): ARSEG_CREFF_TC=1 converts the keyframe feature to f16 NHWC as well and
         # runs the tcgen05 / TMEM engine (csrc/creff_tc.cu, k <= 7).  Default = the mma.sync march engine: measured faster on
         # B200 (3.33 vs 4.1 ms per 11 frames, DESIGN.md section 3.1 -- both are bound by their gather / depthwise producer roles)
         tc = (engine == L.CREFF_MMA_F16 and Cc == 64 and k <= 7 and lr_layout == L.NHWC and lr.dtype == torch.float16
               and os.environ.get("ARSEG_CREFF_TC", "0") == "1")
         if engine == L.CREFF_MMA_F16:
-            hr_nhwc = self.empty((hr.shape[0], H, W, Cc), torch.float16 if tc else torch.float32)
-            fn_t = self.lib.arseg_nchw_to_nhwc
-            targs = (hr.data_ptr(), hr_nhwc.data_ptr(), L.F16 if tc else L.F32, hr.shape[0], Cc, H, W)
-            self._add("hr_nchw_to_nhwc", lambda s: fn_t(*targs, s))
-            hr, hr_layout = hr_nhwc, L.NHWC
+            if hr_in_nhwc and not tc:
+                if hr.dtype != torch.float32:
+                    raise ValueError("creff: an NHWC keyframe feature must be fp32")
+            elif hr_in_nhwc:
+                raise ValueError("creff: the tcgen05 engine takes the keyframe feature as NCHW fp32 (it converts to f16 NHWC itself)")
+            else:
+                hr_nhwc = self.empty((hr.shape[0], H, W, Cc), torch.float16 if tc else torch.float32)
+                fn_t = self.lib.arseg_nchw_to_nhwc
+                targs = (hr.data_ptr(), hr_nhwc.data_ptr(), L.F16 if tc else L.F32, hr.shape[0], Cc, H, W)
+                self._add("hr_nchw_to_nhwc", lambda s: fn_t(*targs, s))
+                hr, hr_layout = hr_nhwc, L.NHWC
             name = name + ("_tc" if tc else "_mma")
+        elif hr_in_nhwc:
+            raise ValueError("creff: the exact fp32 engine takes the keyframe feature as NCHW")
         if lr_layout == L.NHWC:
             N, h, w, _ = lr.shape
         else:

@@ -72,9 +72,12 @@ class NonKeyEngine:
     def __init__(self, arch: str, sd: Dict[str, torch.Tensor], n_frames: int, H: int, W: int, scale: float = 0.5,
                  precision: str = "tf32", k: int = 7, device="cuda:0", want_logits: bool = False, want_p: bool = False,
                  graph: bool = True, split_keyframe: bool = False, uint8_frames: bool = False,
-                 mean=ops.CAMVID_MEAN, std=ops.CAMVID_STD):
+                 mean=ops.CAMVID_MEAN, std=ops.CAMVID_STD, ref_nhwc: Optional[torch.Tensor] = None):
         """uint8_frames: `imgs` is uint8 HWC [N,H,W,3] (decoded frames); ToTensor + Normalize(mean, std)
-        (dataset/camvid.py:182-185) are fused into the LR down-scale kernel -- a quarter of the host->device bytes."""
+        (dataset/camvid.py:182-185) are fused into the LR down-scale kernel -- a quarter of the host->device bytes.
+        ref_nhwc: the keyframe feature as an fp32 NHWC [1,Hf,Wf,C] device tensor in the internal layout (e.g. a
+        KeyFrameEngine's `p_nhwc`): the step reads it in place, without the per-GOP NCHW -> NHWC transpose launch.  `ref_p`
+        (the API-layout buffer) is then None."""
         if arch not in ARCH_INFO:
             raise KeyError(arch)
         self.arch, self.N, self.H, self.W, self.scale, self.k = arch, n_frames, H, W, scale, k
@@ -89,8 +92,15 @@ class NonKeyEngine:
             self.uint8_frames = uint8_frames
             self.imgs = pl.empty((n_frames, H, W, 3), torch.uint8) if uint8_frames else pl.empty((n_frames, 3, H, W), torch.float32)
             self.mv = pl.empty((n_frames, H, W, 2), torch.int16)
-            self.ref_p = pl.empty((1, C_, self.Hf, self.Wf), torch.float32)
-            self.imgs.zero_(); self.mv.zero_(); self.ref_p.zero_()
+            self.ref_nhwc = ref_nhwc
+            if ref_nhwc is not None:
+                if tuple(ref_nhwc.shape) != (1, self.Hf, self.Wf, C_) or ref_nhwc.dtype != torch.float32 or not ref_nhwc.is_contiguous():
+                    raise ValueError("ref_nhwc must be a contiguous fp32 [1,%d,%d,%d] tensor" % (self.Hf, self.Wf, C_))
+                self.ref_p = None
+            else:
+                self.ref_p = pl.empty((1, C_, self.Hf, self.Wf), torch.float32)
+                self.ref_p.zero_()
+            self.imgs.zero_(); self.mv.zero_()
             if uint8_frames:
                 x = pl.frame_ingest_u8(self.imgs, self.h, self.w, mean, std)                              # dataset/camvid.py:182-185 + evaluation.py:186-188
             else:
@@ -106,7 +116,8 @@ class NonKeyEngine:
                 fin, logsm = "conv_out.conv_out.", False
             self.lr_p = p
             direct = arch == "camvid-psp18"     # logits already at frame resolution: argmax inside the kernel
-            out_p, out_l, out_a = pl.creff(self.ref_p, p, sd, "fuse_attention.", k, flow=self.mv, hr_shared=True,
+            out_p, out_l, out_a = pl.creff(self.ref_p if ref_nhwc is None else ref_nhwc, p, sd, "fuse_attention.", k, flow=self.mv,
+                                           hr_shared=True, hr_layout=L.NCHW if ref_nhwc is None else L.NHWC,
                                            lr_layout=L.NHWC, wcls=sd[fin + "weight"], bcls=sd[fin + "bias"],
                                            log_softmax=logsm, want_p=want_p, want_logits=(want_logits or not direct),
                                            want_argmax=direct)
@@ -131,10 +142,16 @@ class NonKeyEngine:
         self.conv_flops_per_frame = pl.conv_flops / n_frames
         self.launches_per_step = pl.n_launches
 
-    def set_inputs(self, imgs: torch.Tensor, mv: torch.Tensor, ref_p: torch.Tensor) -> None:
+    def set_inputs(self, imgs: torch.Tensor, mv: torch.Tensor, ref_p: Optional[torch.Tensor]) -> None:
+        """ref_p: the keyframe feature fp32 NCHW [1,C,Hf,Wf] (None leaves it as it is; with ref_nhwc it is transposed into that buffer)."""
         self.imgs.copy_(imgs, non_blocking=True)
         self.mv.copy_(mv, non_blocking=True)
-        self.ref_p.copy_(ref_p, non_blocking=True)
+        if ref_p is None:
+            return
+        if self.ref_nhwc is not None:
+            self.ref_nhwc.copy_(ref_p.to(self.ref_nhwc.device).permute(0, 2, 3, 1), non_blocking=True)
+        else:
+            self.ref_p.copy_(ref_p, non_blocking=True)
 
     def step(self) -> torch.Tensor:
         """One pass over the N non-keyframes with inputs already resident in HBM."""
@@ -172,7 +189,7 @@ class KeyFrameEngine:
 
     def __init__(self, arch: str, sd: Dict[str, torch.Tensor], H: int, W: int, precision: str = "tf32", device="cuda:0",
                  out: Optional[torch.Tensor] = None, graph: bool = True, uint8_frames: bool = False,
-                 mean=ops.CAMVID_MEAN, std=ops.CAMVID_STD):
+                 mean=ops.CAMVID_MEAN, std=ops.CAMVID_STD, api_layout: bool = True):
         if arch not in ARCH_INFO:
             raise KeyError(arch)
         C_, stride, _ = ARCH_INFO[arch]
@@ -195,7 +212,10 @@ class KeyFrameEngine:
                 _, p = E.build_semseg_phase1(pl, sd, x, "")
             else:
                 _, _, p = E.build_bisenet_phase1(pl, sd, x, "", aux=False)
-            self.p = pl.to_nchw(p, name="p_to_nchw", out=out)
+            # the feature in the internal layout: fp32 NHWC for CamVid-PSP in every plan (up_3 writes fp32) -> a NonKeyEngine
+            # built with ref_nhwc=self.p_nhwc reads it in place; api_layout=False then skips the NCHW copy altogether
+            self.p_nhwc = p if p.dtype == torch.float32 else None
+            self.p = pl.to_nchw(p, name="p_to_nchw", out=out) if (api_layout or self.p_nhwc is None) else None
             if graph:
                 pl.capture()
         self.conv_flops = pl.conv_flops
@@ -203,7 +223,7 @@ class KeyFrameEngine:
 
     def step(self) -> torch.Tensor:
         self.plan.run()
-        return self.p
+        return self.p if self.p is not None else self.p_nhwc
 
 
 class HostPipeline:

@@ -283,14 +283,18 @@ def main():
         pins = [(fr.pin_memory(), mv.pin_memory(), torch.empty((n_local, H, W), dtype=torch.uint8).pin_memory()),
                 (fr.flip(0).contiguous().pin_memory(), mv.flip(0).contiguous().pin_memory(),
                  torch.empty((n_local, H, W), dtype=torch.uint8).pin_memory())]
+        # the keyframe feature is resident in the engine's internal layout (fp32 NHWC, what the keyframe engine produces): the
+        # tensor-core CReFF engines read it in place; the exact fp32 plan keeps the API layout (NCHW)
+        ref_buf = None if precision == "fp32" else torch.empty((1, H // STRIDE_P, W // STRIDE_P, C_P), dtype=torch.float32, device=dev)
         eng = ev.NonKeyEngine(ARCH, sd, n_local, H, W, SCALE, precision, K_WIN, device=dev, want_logits=True,
-                              split_keyframe=frame_mode, uint8_frames=True)
+                              split_keyframe=frame_mode, uint8_frames=True, ref_nhwc=ref_buf)
         eng.set_inputs(fr.to(dev), mv.to(dev), ref_p.to(dev))
+        ref_dev = eng.ref_nhwc if eng.ref_nhwc is not None else eng.ref_p
         bc_stream = torch.cuda.Stream(dev) if frame_mode else None
 
         def bcast_ref():
             if frame_mode:
-                dist.broadcast(eng.ref_p, src=0)     # keyframe feature, once per GOP (ncclBroadcast over NVLink)
+                dist.broadcast(ref_dev, src=0)       # keyframe feature, once per GOP (ncclBroadcast over NVLink)
 
         def dev_step():
             if not frame_mode:
@@ -301,7 +305,7 @@ def main():
             main = torch.cuda.current_stream()
             bc_stream.wait_stream(main)              # the previous GOP's CReFF has finished reading the feature
             with torch.cuda.stream(bc_stream):
-                dist.broadcast(eng.ref_p, src=0)
+                dist.broadcast(ref_dev, src=0)
             eng.step_phase1()
             main.wait_stream(bc_stream)
             eng.step_phase2()
@@ -447,7 +451,8 @@ def main():
                    "frames_per_step_per_rank": main_r["n_local"], "shard": "gop (every rank owns whole GOPs; no data-path collective)",
                    "precision": args.precision,
                    "l2": "256 MiB buffer written between timed steps (L2 flush)",
-                   "inputs": "uint8 HWC frames (ToTensor + Normalize fused into the LR down-scale kernel), int16 MV fields, keyframe feature resident",
+                   "inputs": "uint8 HWC frames (ToTensor + Normalize fused into the LR down-scale kernel), int16 MV fields, keyframe feature "
+                             "resident in the engine's internal layout (fp32 NHWC, as the keyframe engine writes it)",
                    "outputs": "log-prob maps fp32 + argmax class maps uint8; fused p is not materialised (evaluation.py:193 discards it)"},
         "e2e": {"value": round(main_r["e2e"], 2), "unit": UNIT, "h2d_bytes_per_step": main_r["h2d"],
                 "d2h_bytes_per_step": main_r["d2h"], "ms_per_step": round(main_r["ms_e2e"] / args.steps, 4),
@@ -516,17 +521,34 @@ def run_extras(args, eng, sd, frames_u8, key_u8, mvs, ref_p, dev, l2_flush, time
     out["parity"] = par
     # ---- whole GOP
     sd_hr = synth.synth_state_dict(models.models[ARCH]().state_dict(), 4)
-    kf = ev.KeyFrameEngine(ARCH, sd_hr, H, W, args.precision, device=dev, out=eng.ref_p, uint8_frames=True)
+    kf = ev.KeyFrameEngine(ARCH, sd_hr, H, W, args.precision, device=dev, uint8_frames=True, api_layout=False)
     kf.img.copy_(key_u8.to(dev))
+    if kf.p_nhwc is not None and args.precision != "fp32":
+        # the keyframe engine's feature buffer IS the non-keyframe engine's keyframe-feature input (internal fp32 NHWC layout)
+        nk = ev.NonKeyEngine(ARCH, sd, N_FRAMES, H, W, SCALE, args.precision, K_WIN, device=dev, uint8_frames=True, ref_nhwc=kf.p_nhwc)
+    else:
+        kf = ev.KeyFrameEngine(ARCH, sd_hr, H, W, args.precision, device=dev, uint8_frames=True)
+        kf.img.copy_(key_u8.to(dev))
+        nk = ev.NonKeyEngine(ARCH, sd, N_FRAMES, H, W, SCALE, args.precision, K_WIN, device=dev, uint8_frames=True)
+        kf_out = kf.p
+    nk.set_inputs(frames_u8.to(dev), mvs.to(dev), None)
+
+    def gop_step():
+        kf.step()
+        if nk.ref_nhwc is None:
+            nk.ref_p.copy_(kf_out, non_blocking=True)
+        nk.step()
+
     for _ in range(3):
-        kf.step(); eng.step()
-    ms_gop = timed_steps(lambda: (kf.step(), eng.step()), args.steps) / args.steps
+        gop_step()
+    ms_gop = timed_steps(gop_step, args.steps) / args.steps
     ms_kf = timed_steps(lambda: kf.step(), args.steps) / args.steps
     out["gop"] = {"value": round(GOP / (ms_gop * 1e-3), 2), "unit": "frames/s (all 12 frames of a GOP: HR keyframe forward + 11 non-keyframes)",
                   "ms_per_gop": round(ms_gop, 4), "ms_keyframe": round(ms_kf, 4), "keyframe_launches": kf.launches_per_step,
+                  "launches_per_gop": kf.launches_per_step + nk.launches_per_step,
                   "keyframe_conv_tflops": round(kf.conv_flops / (ms_kf * 1e-3) / 1e12, 1)}
-    eng.set_inputs(frames_u8.to(dev), mvs.to(dev), ref_p.to(dev))
-    del kf
+    del kf, nk
+    torch.cuda.empty_cache()
     # ---- literal drop-in API, one frame at a time
     net = models.models_fuse[ARCH]()
     net.load_state_dict(sd)

@@ -380,6 +380,23 @@ def test_keyframe_engine_full_shape_feeds_the_nonkey_engine():
     torch.cuda.synchronize()
 
 
+def test_nonkey_engine_reads_the_keyframe_feature_in_nhwc():
+    """ref_nhwc: the keyframe feature in the internal fp32 NHWC layout is read in place -- same class maps and logits as the
+    API-layout (NCHW) engine, one launch less."""
+    g = load_golden("camvid_psp18_s05")
+    arch, _, sd, imgs, ref_p, mv, flow, scale = case_setup(g)
+    H, W = imgs.shape[-2:]
+    mvd = torch.from_numpy(mv).unsqueeze(0).to(DEV)
+    a = ev.NonKeyEngine(arch, sd, 1, H, W, scale, "f16", device=DEV, want_logits=True)
+    buf = torch.empty((1, H, W, ref_p.shape[1]), dtype=torch.float32, device=DEV)
+    b = ev.NonKeyEngine(arch, sd, 1, H, W, scale, "f16", device=DEV, want_logits=True, ref_nhwc=buf)
+    a.set_inputs(imgs.to(DEV), mvd, ref_p.to(DEV))
+    b.set_inputs(imgs.to(DEV), mvd, ref_p.to(DEV))
+    assert b.launches_per_step == a.launches_per_step - 1
+    pa, pb = a.step().clone(), b.step().clone()
+    assert torch.equal(pa, pb) and torch.equal(a.logits, b.logits)
+
+
 def test_uint8_frame_ingest_engine_matches_float_engine():
     """uint8 HWC frames + on-device ToTensor / Normalize (dataset/camvid.py:182-185) == the fp32 engine fed with the frames
     normalised on the host the way the dataset does."""
