@@ -78,10 +78,21 @@ __device__ __forceinline__ void xbar_init(uint64_t* bar, uint32_t count) {
 // one arrival per WARP (barrier counts = warps of the producing role): a waiter parked in try_wait is woken by every
 // arrival on its barrier, so per-thread arrivals make every waiting warp spin through 32x more wake-ups.  __syncwarp
 // orders the lanes' shared-memory accesses before the elected lane's release-arrive.
+// -DARSEG_ARRIVE_ALL (compute-sanitizer racecheck builds): every lane arrives (barrier counts x 32).  racecheck orders only the
+// accesses of threads that arrive themselves; it does not follow the __syncwarp -> elected-lane release-arrive chain.
+#ifdef ARSEG_ARRIVE_ALL
+constexpr uint32_t XARRIVALS = 32;
+#else
+constexpr uint32_t XARRIVALS = 1;
+#endif
 __device__ __forceinline__ void xbar_arrive(uint64_t* bars, int step) {
+#ifdef ARSEG_ARRIVE_ALL
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(bars + ((step + 1) & (XNB - 1)))) : "memory");
+#else
     __syncwarp();
     if ((threadIdx.x & 31) == 0)
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(bars + ((step + 1) & (XNB - 1)))) : "memory");
+#endif
 }
 __device__ __forceinline__ void xbar_wait(uint64_t* bars, int step) {
     const uint32_t addr = s_u32(bars + ((step + 1) & (XNB - 1)));
@@ -808,10 +819,10 @@ __global__ void __launch_bounds__(XTHREADS, 1) creff_march_kernel(CreffMmaParams
 
     if (tid == 0) {
         for (int i = 0; i < XNB; ++i) {
-            xbar_init(sm.gfull + i, XG_WARPS);
-            xbar_init(sm.ddone + i, XD_WARPS);
-            xbar_init(sm.cdone + i, XC_WARPS);
-            xbar_init(sm.qlempty + i, XC_WARPS);
+            xbar_init(sm.gfull + i, XG_WARPS * XARRIVALS);
+            xbar_init(sm.ddone + i, XD_WARPS * XARRIVALS);
+            xbar_init(sm.cdone + i, XC_WARPS * XARRIVALS);
+            xbar_init(sm.qlempty + i, XC_WARPS * XARRIVALS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }

@@ -91,10 +91,20 @@ __device__ __forceinline__ void tbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count));
 }
 // hand-off barriers are indexed by a step counter >= 0: slot idx & 3, phase parity (idx / 4) & 1
+// -DARSEG_ARRIVE_ALL: see creff_march.cu (racecheck builds)
+#ifdef ARSEG_ARRIVE_ALL
+constexpr uint32_t TARRIVALS = 32;
+#else
+constexpr uint32_t TARRIVALS = 1;
+#endif
 __device__ __forceinline__ void tbar_arrive(uint64_t* bars, int idx) {
+#ifdef ARSEG_ARRIVE_ALL
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(bars + (idx & (TNB - 1)))) : "memory");
+#else
     __syncwarp();
     if ((threadIdx.x & 31) == 0)
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(bars + (idx & (TNB - 1)))) : "memory");
+#endif
 }
 __device__ __forceinline__ bool tbar_test(uint64_t* bars, int idx) {
     uint32_t ok;
@@ -949,9 +959,9 @@ __global__ void __launch_bounds__(TTHREADS, 1) creff_tc_kernel(CreffMmaParams p,
 
     if (tid == 0) {
         for (int i = 0; i < TNB; ++i) {
-            tbar_init(sm.gfull + i, TG_WARPS); tbar_init(sm.ddone + i, TD_WARPS); tbar_init(sm.lrfree + i, TC_WARPS);
-            tbar_init(sm.sfull + i, 1); tbar_init(sm.pfull + i, TC_WARPS); tbar_init(sm.ofull + i, 1);
-            tbar_init(sm.afull + i, TC_WARPS); tbar_init(sm.lfull + i, 1); tbar_init(sm.ofree + i, TC_WARPS);
+            tbar_init(sm.gfull + i, TG_WARPS * TARRIVALS); tbar_init(sm.ddone + i, TD_WARPS * TARRIVALS); tbar_init(sm.lrfree + i, TC_WARPS * TARRIVALS);
+            tbar_init(sm.sfull + i, 1); tbar_init(sm.pfull + i, TC_WARPS * TARRIVALS); tbar_init(sm.ofull + i, 1);
+            tbar_init(sm.afull + i, TC_WARPS * TARRIVALS); tbar_init(sm.lfull + i, 1); tbar_init(sm.ofree + i, TC_WARPS * TARRIVALS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
