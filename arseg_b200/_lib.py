@@ -17,8 +17,9 @@ ACT_NONE, ACT_RELU, ACT_PRELU = 0, 1, 2
 RESIZE_BILINEAR, RESIZE_BILINEAR_AC, RESIZE_NEAREST = 0, 1, 2
 NCHW, NHWC = 0, 1
 CONV_SIMT_F32, CONV_TC_TF32, CONV_TC_BF16, CONV_TC_F16 = 1, 2, 3, 4
-CREFF_EXACT_F32, CREFF_MMA_F16 = 0, 1
-ABI_VERSION = 5
+CREFF_EXACT_F32, CREFF_MMA_F16, CREFF_TCGEN05 = 0, 1, 2
+CREFF_PHASE_ALL, CREFF_PHASE_PREPASS, CREFF_PHASE_MAIN = 0, 1, 2
+ABI_VERSION = 6
 
 vp, ci, cf = C.c_void_p, C.c_int, C.c_float
 
@@ -35,7 +36,7 @@ class CreffArgs(C.Structure):
                 ("lr", vp), ("lr_layout", ci), ("lr_dtype", ci), ("h", ci), ("w", ci),
                 ("wq", vp), ("bq", vp), ("wk", vp), ("bk", vp), ("wv", vp), ("bv", vp), ("wcls", vp), ("bcls", vp),
                 ("ncls", ci), ("log_softmax", ci), ("out_p", vp), ("out_logits", vp), ("out_argmax", vp),
-                ("N", ci), ("C", ci), ("H", ci), ("W", ci), ("k", ci), ("workspace", vp), ("workspace_bytes", C.c_size_t), ("hr_dtype", ci)]
+                ("N", ci), ("C", ci), ("H", ci), ("W", ci), ("k", ci), ("workspace", vp), ("workspace_bytes", C.c_size_t), ("hr_dtype", ci), ("phase", ci)]
 
 
 _PROTOS = {

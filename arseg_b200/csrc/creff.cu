@@ -318,11 +318,15 @@ static int creff_launch_k(const CreffParams& p, int layout, int dtype, cudaStrea
 }
 
 bool creff_mma_supported(const arseg_creff_args* a);
+// the tcgen05 engine: asked for by name, or (ABI 5 behaviour) ARSEG_CREFF_MMA_F16 with an f16 keyframe feature
+static inline bool creff_uses_tc(const arseg_creff_args* a) {
+    return a->engine == ARSEG_CREFF_TCGEN05 || (a->engine == ARSEG_CREFF_MMA_F16 && a->C == 64 && a->hr_dtype == ARSEG_F16);
+}
 int creff_mma_launch(const arseg_creff_args* a, cudaStream_t st);
 bool creff_wide_supported(const arseg_creff_args* a);                                   // creff_wide.cu
 int creff_wide_launch(const arseg_creff_args* a, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t creff_wide_workspace_bytes(int N, int C, int H, int W);
-size_t creff_tc_workspace_bytes(int N, int H, int W);                                   // creff_tc.cu
+size_t creff_tc_workspace_bytes(int N, int H, int W, int k);                                   // creff_tc.cu
 
 }  // namespace arseg
 
@@ -346,9 +350,16 @@ extern "C" int arseg_creff_fused_fwd(const arseg_creff_args* a, arseg_stream_t s
     else ARSEG_REQUIRE(a->lr_dtype == ARSEG_F32 || a->lr_dtype == ARSEG_BF16 || a->lr_dtype == ARSEG_F16, "creff: lr dtype %d", a->lr_dtype);
     ARSEG_REQUIRE(a->hr_dtype == ARSEG_F32 || a->hr_dtype == ARSEG_F16, "creff: hr dtype %d", a->hr_dtype);
     if (a->hr_dtype == ARSEG_F16)
-        ARSEG_REQUIRE(a->engine == ARSEG_CREFF_MMA_F16 && a->hr_layout == ARSEG_NHWC && a->C == 64,
-                      "creff: an f16 keyframe feature needs the tensor-core engine, NHWC and C = 64");
+        ARSEG_REQUIRE((a->engine == ARSEG_CREFF_MMA_F16 || a->engine == ARSEG_CREFF_TCGEN05) && a->hr_layout == ARSEG_NHWC && a->C == 64,
+                      "creff: an f16 keyframe feature needs the tcgen05 engine, NHWC and C = 64");
+    ARSEG_REQUIRE(a->phase == ARSEG_CREFF_PHASE_ALL || a->phase == ARSEG_CREFF_PHASE_PREPASS || a->phase == ARSEG_CREFF_PHASE_MAIN, "creff: phase %d", a->phase);
     cudaStream_t st = as_stream(stream);
+    if (creff_uses_tc(a)) {
+        if (!creff_mma_supported(a) || a->lr_dtype != ARSEG_F16 || a->k > 7)
+            ARSEG_UNSUPPORTED("creff: the tcgen05 engine needs C = 64 (got %d), NHWC hr, NHWC f16 lr (dtype %d), k in {3,5,7} (got %d), ncls <= 32", a->C, a->lr_dtype, a->k);
+        return creff_mma_launch(a, st);
+    }
+    if (a->phase == ARSEG_CREFF_PHASE_PREPASS) return ARSEG_OK;      // only the tcgen05 engine has a pre-pass
     if (a->engine == ARSEG_CREFF_MMA_F16) {
         if (creff_wide_supported(a)) return creff_wide_launch(a, a->workspace, a->workspace_bytes, st);
         if (!creff_mma_supported(a))
@@ -373,8 +384,9 @@ extern "C" int arseg_creff_fused_fwd(const arseg_creff_args* a, arseg_stream_t s
 }
 
 extern "C" size_t arseg_creff_workspace_bytes(const arseg_creff_args* a) {
-    if (!a || a->engine != ARSEG_CREFF_MMA_F16) return 0;
-    if (a->C == 64 && a->hr_dtype == ARSEG_F16) return creff_tc_workspace_bytes(a->N, a->H, a->W);   // per-pixel gather records
+    if (!a) return 0;
+    if (creff_uses_tc(a)) return creff_tc_workspace_bytes(a->N, a->H, a->W, a->k);   // lr_up gather records + MV-warped keyframe rows
+    if (a->engine != ARSEG_CREFF_MMA_F16) return 0;
     if (!creff_wide_supported(a)) return 0;
     return creff_wide_workspace_bytes(a->N, a->C, a->H, a->W);
 }

@@ -918,10 +918,10 @@ bool creff_mma_supported(const arseg_creff_args* a) {
            (!a->wcls || a->ncls <= 32) && ((size_t)a->H * a->W < (1u << 29)) && ((size_t)a->h * a->w < (1u << 29));
 }
 
-int creff_tc_launch(CreffMmaParams& p, int k, void* ws, size_t ws_bytes, cudaStream_t st);   // creff_tc.cu
+int creff_tc_launch(CreffMmaParams& p, int k, int hr_dtype, int phase, void* ws, size_t ws_bytes, cudaStream_t st);   // creff_tc.cu
 
-// ARSEG_CREFF_MMA_F16 at C = 64: f16 keyframe feature + f16 LR feature -> the tcgen05 engine (creff_tc.cu, k <= 7);
-// fp32 keyframe feature -> the column-marching mma.sync engine of this file (any LR dtype, k <= 9).
+// C = 64: ARSEG_CREFF_TCGEN05 (or ARSEG_CREFF_MMA_F16 with an f16 keyframe feature) -> the tcgen05 engine (creff_tc.cu, f16 LR
+// feature, k <= 7); ARSEG_CREFF_MMA_F16 -> the column-marching mma.sync engine of this file (any LR dtype, k <= 9).
 int creff_mma_launch(const arseg_creff_args* a, cudaStream_t st) {
     CreffMmaParams p;
     p.hr = reinterpret_cast<const float*>(a->hr); p.hr_shared = a->hr_shared; p.flow = a->flow; p.flow_dtype = a->flow_dtype; p.Hm = a->Hm; p.Wm = a->Wm;
@@ -929,10 +929,10 @@ int creff_mma_launch(const arseg_creff_args* a, cudaStream_t st) {
     p.wq = a->wq; p.bq = a->bq; p.wk = a->wk; p.bk = a->bk; p.wv = a->wv; p.bv = a->bv; p.wcls = a->wcls; p.bcls = a->bcls;
     p.ncls = a->ncls; p.log_softmax = a->log_softmax; p.out_p = a->out_p; p.out_logits = a->out_logits;
     p.out_argmax = a->out_argmax; p.N = a->N; p.C = a->C; p.H = a->H; p.W = a->W;
-    if (a->hr_dtype == ARSEG_F16) {
+    if (a->engine == ARSEG_CREFF_TCGEN05 || a->hr_dtype == ARSEG_F16) {
         if (a->lr_dtype != ARSEG_F16 || a->k > 7)
-            ARSEG_UNSUPPORTED("creff: an f16 keyframe feature selects the tcgen05 engine, which needs an f16 LR feature and k <= 7 (lr dtype %d, k = %d)", a->lr_dtype, a->k);
-        return creff_tc_launch(p, a->k, a->workspace, a->workspace_bytes, st);
+            ARSEG_UNSUPPORTED("creff: the tcgen05 engine needs an f16 LR feature and k <= 7 (lr dtype %d, k = %d)", a->lr_dtype, a->k);
+        return creff_tc_launch(p, a->k, a->hr_dtype, a->phase, a->workspace, a->workspace_bytes, st);
     }
     return creff_march_launch(p, a->k, a->lr_dtype, st);
 }

@@ -17,8 +17,12 @@
 //     The row sums come from one more MMA against a ones tile, the residual lr_up + O / sum is formed in registers,
 //     goes back to TMEM as f16 and is the A operand of the classifier MMA.
 //   * Producer roles as in the march engine, handing rows over through mbarriers:
-//       G (6 warps): bilinear gather of the MV-warped keyframe rows and the lr_up rows (quarter-warp per position,
-//                    8 channels = 16 bytes per lane, f16 sources, mixed-precision FHFMA) into f16 row rings;
+//       W (pre-pass kernel, creff_tc_warp_kernel): the MV warp of the keyframe feature (bilinear gather, f16, mixed-precision
+//                    FHFMA) written ONCE per frame to a zero-bordered f16 NHWC workspace -- a latency-bound gather belongs in a
+//                    full-occupancy kernel, not in five warps of a one-CTA-per-SM engine;
+//       G (5 warps): one thread streams the warped rows into the f16 row ring with cp.async.bulk (3 KB per row, completion
+//                    counted on the row hand-off mbarrier); the warps gather the lr_up rows (quarter-warp per position, 8
+//                    channels = 16 bytes per lane);
 //       D (6 warps): depthwise 3x3 convolutions (FFMA2): two K warps, two V warps (4 rows x half the columns each),
 //                    two Q warps; K, V -> rings, Q -> the A tile;
 //       M (1 warp):  MMA issue (one elected lane);
@@ -30,14 +34,15 @@
 namespace arseg {
 
 constexpr int TSW = 16;                    // strip width (pixels)
-// 20 warps, no register re-balancing (640 threads x 96 registers).  Scheduler = warp id % 4 = TMEM lane quarter.  The roles are
-// spread so that the FMA-pipe work of a tile (K / V warp 60k lane-ops, Q half 40k, G 18k, S + E 13k) is even across the four
-// schedulers, and the latency-critical chain M -> S -> M -> E has the highest warp ids (the arbiter prefers them):
-//   0 K0  1 K1  2 V0  3 V1 | 4 G0  5 G1  6 Qa  7 Qb | 8 G2  9 G3  10 G4  11 M | 12..15 E | 16..19 S
+// 20 warps, no register re-balancing (640 threads x 96 registers).  Scheduler = warp id % 4 = TMEM lane quarter.  The depthwise
+// warps are latency-bound (dependent FFMA2 chains: ncu shows them issuing a quarter of the time), so they get the most warps --
+// two per scheduler -- and the latency-critical chain M -> S -> M -> E has the highest warp ids (the arbiter prefers them):
+//   0 K0  1 K1  2 K2  3 V0 | 4 V1  5 V2  6 Qa  7 Qb | 8 G0  9 G1  10 G2  11 M | 12..15 E | 16..19 S
 constexpr int TTHREADS = 640;
-constexpr int TD_WARPS = 6;                // K0 K1 V0 V1 Qa Qb
+constexpr int TD_WARPS = 8;                // K0 K1 K2 V0 V1 V2 Qa Qb
+constexpr int TKV_SPLIT = 3;               // column thirds of a K / V row
 constexpr int TQ_WARP0 = 6;                // warps 6, 7: the two column halves of Q
-constexpr int TG_WARPS = 5;                // warps 4, 5, 8, 9, 10
+constexpr int TG_WARP0 = 8, TG_WARPS = 3;  // warps 8, 9, 10
 constexpr int TM_WARP = 11;                // MMA issuer (and TMEM allocator)
 constexpr int TE_W0 = 12, TS_W0 = 16, TC_WARPS = 4;   // epilogue warps 12..15, softmax warps 16..19 (lane quarter = warp % 4)
 constexpr int TG_THREADS = 32 * TG_WARPS;
@@ -45,11 +50,12 @@ constexpr int TNQW = 4 * TG_WARPS;         // gather quarter-warps: one position
 constexpr int TJA = 4;                     // gather positions in flight per quarter-warp
 constexpr int TKP = 24;                    // keys per K/V ring row
 constexpr int TROWB = TKP * 128;           // bytes per K/V ring row
-constexpr int THRR = 10, TLRR = 18;        // warped-hr / lr_up ring rows
+constexpr int THRR = 10, TLRR = 16;        // warped-hr / lr_up ring rows
 constexpr int TLC = TSW + 2;               // lr_up ring columns
 constexpr int TNB = 4;                     // mbarriers per hand-off (indexed by step & 3)
 constexpr int TBAR_G = 1;                  // named barrier of the G group
 constexpr int TNCLS = 32;                  // classifier rows staged (>= ncls)
+constexpr int TWB_DEFAULT = 8;             // workspace rows per band of the MV-warp pre-pass
 
 template <int K> struct TCfg {
     static constexpr int R = K / 2;
@@ -58,12 +64,17 @@ template <int K> struct TCfg {
     static constexpr int HP = (2 * R + PADR) / 4;                  // half-steps before the first query row
     static constexpr int KVC = TSW + 2 * R;                        // K/V ring columns in use (<= TKP)
     static constexpr int HC = KVC + 2;                             // warped-hr ring columns
-    static constexpr int KVR = NKR + 4;                            // K/V ring rows
+    // K/V ring rows: a tile's window + the 8 new rows of the NEXT tile, so that the depthwise warps never wait for P V of the
+    // current tile before producing the next one (with NKR + 4 rows the second half-step of tile i+1 overwrote rows tile i
+    // still reads: D, S = Q K^T, softmax and P V ran strictly one after the other, 14.7k cycles per tile instead of ~11k)
+    static constexpr int KVR = NKR + 8;
     static constexpr int NK = NKR * TKP;                           // S columns
-    static constexpr int NITEM = 4 * HC + 4 * TLC;                 // gather positions of a step
+    static constexpr int NITEM = 4 * TLC;                          // lr_up gather positions of a step
+    static constexpr int PT = R + PADR + 1, PB = 8 + R, PX = R + 1;   // zero border of the warped-keyframe workspace (rows above / below, columns left)
+    static constexpr uint32_t HROW_BYTES = HC * 128;               // one warped-hr ring row = one bulk copy
     static constexpr int NJ = (NITEM + TNQW - 1) / TNQW;
     static constexpr int PMAX = NJ * TNQW;                         // padded with no-op records
-    static constexpr int KVC1 = (KVC + 1) / 2;                     // columns of the first K / V warp
+    static constexpr int KVC3 = (KVC + TKV_SPLIT - 1) / TKV_SPLIT; // columns of a K / V warp (the last one takes what is left)
     static constexpr uint32_t COL_O = NK, COL_SUM = NK + 64, COL_A = NK + 80, COL_L = NK + 112;
     static constexpr size_t KV_BYTES = (size_t)KVR * TROWB;
     static constexpr size_t Q_BYTES = 128 * 128;
@@ -78,11 +89,20 @@ template <int K> struct TCfg {
     static_assert(KVC <= TKP, "window too wide for the key pitch");
     static_assert(NKR % 2 == 0 && KVR % 2 == 0 && PADR % 2 == 0, "even row counts: a 16-key MMA step never straddles the ring end");
     static_assert(COL_L + TNCLS <= 512, "tensor memory columns");
-    static_assert(PMAX <= 2 * TG_THREADS && 4 * HC <= TG_THREADS, "at most two gather records per G thread, the MV-dependent ones in the first pass");
+    static_assert(PMAX <= 2 * TG_THREADS, "at most two gather records per G thread");
     static_assert(SMEM <= 232448, "shared memory budget");
 };
 
-size_t creff_tc_workspace_bytes(int N, int H, int W) { return (size_t)(N + 1) * H * W * sizeof(uint4); }
+// workspace = [H][W] lr_up gather records (16 bytes) | [N][Hp][Wp][64] f16 MV-warped keyframe feature with a zero border
+// (Hp = PT + H + PB rows, Wp = 16 * ceil(W / 16) + HC - 16 columns: every ring row of every strip is one in-bounds 128-byte
+// aligned run of HC pixels)
+template <int K> __host__ __device__ constexpr int t_hp(int H) { return TCfg<K>::PT + H + TCfg<K>::PB; }
+template <int K> __host__ __device__ constexpr int t_wp(int W) { return (W + TSW - 1) / TSW * TSW + TCfg<K>::HC - TSW; }
+static size_t t_rec_bytes(int H, int W) { return ((size_t)H * W * sizeof(uint4) + 1023) / 1024 * 1024; }
+size_t creff_tc_workspace_bytes(int N, int H, int W, int k) {
+    const size_t px = k <= 3 ? (size_t)t_hp<3>(H) * t_wp<3>(W) : k <= 5 ? (size_t)t_hp<5>(H) * t_wp<5>(W) : (size_t)t_hp<7>(H) * t_wp<7>(W);
+    return t_rec_bytes(H, W) + (size_t)N * px * 128;
+}
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -275,37 +295,35 @@ __device__ __forceinline__ void t_step_geom(int g, int& h0, int& nh, int& l0, in
     else { l0 = 0; nl = 0; }
 }
 
-// The per-position gather records (2x2 source block + four bilinear weights; for the keyframe feature this is the f64 MV
-// arithmetic of evaluation.py:177-183 + the grid_sample geometry of :61-87) are computed once per pixel by
+// Warped-hr rows: bulk copies from the pre-pass workspace (ring row r <-> workspace row ya + r, columns x0 .. x0 + HC).
+// lr_up rows: the per-position gather records (2x2 source block + four bilinear weights) are computed once per pixel by
 // creff_tc_rec_kernel into the caller's workspace; the G warps only copy the records of the next step into shared memory
 // (one 16-byte load per thread, in flight during the gather loop) and stream the taps.
+__device__ __forceinline__ void t_bulk_row(uint32_t dst, const char* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 template <int K>
-__device__ __forceinline__ void t_g_role(const CreffMmaParams& p, const TSmem& sm, const uint4* __restrict__ rec, int n, int x0, int ya, int NH, int S) {
+__device__ __forceinline__ void t_g_role(const CreffMmaParams& p, const TSmem& sm, const uint4* __restrict__ rec, const char* __restrict__ warped,
+                                         int n, int x0, int ya, int NH, int S) {
     using Cf = TCfg<K>;
-    const int gw = (int)(threadIdx.x >> 5), gi = gw < TQ_WARP0 ? gw - 4 : gw - 6;    // gather warp index 0..4 (warps 4, 5, 8, 9, 10)
-    const int gt = gi * 32 + (int)(threadIdx.x & 31), lane = gt & 31, qw = gt >> 3, l8 = lane & 7;
-    const char* const hrb = reinterpret_cast<const char*>(p.hr) + (p.hr_shared ? (size_t)0 : (size_t)n * p.H * p.W * 128);
+    const int gt = (int)threadIdx.x - 32 * TG_WARP0, lane = gt & 31, qw = gt >> 3, l8 = lane & 7;    // thread / quarter-warp index inside the G group
     const char* const lrb = reinterpret_cast<const char*>(p.lr) + (size_t)n * p.h * p.w * 128;
-    const uint32_t hr_rs = (uint32_t)p.W * 128, lr_rs = (uint32_t)p.w * 128;
+    const uint32_t lr_rs = (uint32_t)p.w * 128;
     constexpr uint32_t SCRATCH_OFF = (uint32_t)(Cf::HR_BYTES + Cf::LR_BYTES);
-    const uint4* const rec_hr = rec + (size_t)n * p.H * p.W;           // [N][H][W]
-    const uint4* const rec_lr = rec + (size_t)p.N * p.H * p.W;         // [H][W] (frame independent)
+    const uint4* const rec_lr = rec;                                   // [H][W] (frame independent)
+    const size_t wrow = (size_t)t_wp<K>(p.W) * 128;                    // workspace row pitch
+    const char* const wsrc = warped + ((size_t)n * t_hp<K>(p.H) + ya) * wrow + (size_t)x0 * 128;
 
     // record slot q of step g: destination ring offset and the global record it copies (nullptr: a zero record -- positions
     // outside the image are the depthwise convolutions' zero padding; slots beyond the step's positions are no-ops)
     auto slot_of = [&](int g, int q, uint32_t& dst) -> const uint4* {
         int h0, nh, l0, nl;
         t_step_geom<K>(g, h0, nh, l0, nl);
-        const int nhp = nh * Cf::HC, npos = nhp + nl * TLC;
+        const int npos = nl * TLC;
         dst = SCRATCH_OFF;
-        if (q < nhp) {
-            const int rr = q / Cf::HC, cc = q - rr * Cf::HC, row = h0 + rr;
-            const int fy = ya - Cf::R - Cf::PADR - 1 + row, fx = x0 - Cf::R - 1 + cc;
-            dst = (uint32_t)(((row % THRR) * Cf::HC + cc) * 128);
-            return (fy >= 0 && fy < p.H && fx >= 0 && fx < p.W) ? rec_hr + (size_t)fy * p.W + fx : nullptr;
-        }
         if (q < npos) {
-            const int q2 = q - nhp, rr = q2 / TLC, cc = q2 - rr * TLC, row = l0 + rr;
+            const int rr = q / TLC, cc = q - rr * TLC, row = l0 + rr;
             const int fy = ya - 1 + row, fx = x0 - 1 + cc;
             dst = (uint32_t)(Cf::HR_BYTES + ((row % TLRR) * TLC + cc) * 128) | ((uint32_t)(cc & 7) << 28);
             return (fy >= 0 && fy < p.H && fx >= 0 && fx < p.W) ? rec_lr + (size_t)fy * p.W + fx : nullptr;
@@ -338,9 +356,8 @@ __device__ __forceinline__ void t_g_role(const CreffMmaParams& p, const TSmem& s
     uint4 tap[TJA][4];
     auto issue = [&](uint4 (&tp)[4], int buf, int j) {
         const uint4 id = sm.posa[buf * Cf::PMAX + qw + TNQW * j];
-        const bool lr = (id.z >> 31) != 0;
-        const char* a0 = (lr ? lrb : hrb) + (size_t)(id.z & 0x7fffffffu) * 128 + 16 * l8;
-        const char* a1 = a0 + (lr ? lr_rs : hr_rs);
+        const char* a0 = lrb + (size_t)(id.z & 0x7fffffffu) * 128 + 16 * l8;
+        const char* a1 = a0 + lr_rs;
         tp[0] = t_ldg128(a0);
         tp[1] = t_ldg128(a0 + 128);
         tp[2] = t_ldg128(a1);
@@ -385,6 +402,15 @@ __device__ __forceinline__ void t_g_role(const CreffMmaParams& p, const TSmem& s
             const int num = 4 * (g - Cf::HP) + 5 - TLRR - 1;        // last overwritten lr row - 1
             if (num >= 0) { const int im = num >> 3; tbar_wait<true>(sm.lrfree, im < S - 1 ? im : S - 1, 3); }
         }
+        if (gt == 0) {
+            // the step's warped-hr rows: one bulk copy each, completing on the step's hand-off barrier
+            int h0, nh, l0, nl;
+            t_step_geom<K>(g, h0, nh, l0, nl);
+            const uint32_t bar = s_u32(sm.gfull + ((g + 1) & (TNB - 1)));
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)nh * Cf::HROW_BYTES) : "memory");
+            for (int r = 0; r < nh; ++r)
+                t_bulk_row(sm.rings + (uint32_t)((h0 + r) % THRR) * Cf::HROW_BYTES, wsrc + (size_t)(h0 + r) * wrow, Cf::HROW_BYTES, bar);
+        }
 #ifdef ARSEG_TTRACE
         if (!(p.dbg & 4))
 #endif
@@ -425,12 +451,12 @@ __device__ __forceinline__ int t_kv_last_reader(int h) {
 template <int K>
 __device__ __forceinline__ void t_d_role(const CreffMmaParams& p, const TSmem& sm, int x0, int ya, int NH, int S) {
     using Cf = TCfg<K>;
-    const int lane = threadIdx.x & 31, dw = (int)(threadIdx.x >> 5), d = dw >= TQ_WARP0 ? 4 : dw, qhalf = dw - TQ_WARP0;
+    const int lane = threadIdx.x & 31, dw = (int)(threadIdx.x >> 5), qhalf = dw - TQ_WARP0;
     const uint32_t lane_sub = (uint32_t)((lane & 3) * 4), lane_chunk = (uint32_t)(lane >> 2);
-    if (d < 4) {
-        // ---------------- K (d = 0, 1) or V (d = 2, 3): columns [c_lo, c_lo + ncol) of four K/V rows per half-step ----------------
-        const int isv = d >> 1, half = d & 1;
-        const int c_lo = half ? Cf::KVC1 : 0, ncol = half ? Cf::KVC - Cf::KVC1 : Cf::KVC1;
+    if (dw < TQ_WARP0) {
+        // ---------------- K (warps 0..2) or V (3..5): columns [c_lo, c_lo + ncol) of four K/V rows per half-step ----------------
+        const int isv = dw / TKV_SPLIT, part = dw % TKV_SPLIT;
+        const int c_lo = part * Cf::KVC3, ncol = min(Cf::KVC3, Cf::KVC - c_lo);
         float2 w[10];
         {
             const float* wp = isv ? p.wv : p.wk;
@@ -897,37 +923,145 @@ __device__ __forceinline__ void t_e_role(const CreffMmaParams& p, const TSmem& s
 }
 
 // ---------------------------------------------------------------------------------------------
-// gather records, once per pixel: [N][H][W] for the MV-warped keyframe feature, then [H][W] for lr_up
+// pre-pass 1: lr_up gather records, once per pixel ([H][W], frame independent)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) creff_tc_rec_kernel(CreffMmaParams p, uint4* __restrict__ rec) {
-    const long long plane = (long long)p.H * p.W, total = (long long)(p.N + 1) * plane;
+    const long long total = (long long)p.H * p.W;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
-    const int n = (int)(i / plane);
-    const int fy = (int)((i - (long long)n * plane) / p.W), fx = (int)(i % p.W);
-    PosRec r;
-    int Ws, Hs;
-    if (n < p.N) { r = pos_hr(p, n, fy, fx); Ws = p.W; Hs = p.H; }
-    else {
-        r = pos_lr(p, resize_scale(p.h, p.H, ARSEG_RESIZE_BILINEAR_AC), resize_scale(p.w, p.W, ARSEG_RESIZE_BILINEAR_AC), fy, fx);
-        Ws = p.w; Hs = p.h;
-    }
-    uint4 o = make_uint4(0u, 0u, n < p.N ? 0u : 0x80000000u, 0u);
+    const int fy = (int)(i / p.W), fx = (int)(i % p.W);
+    const PosRec r = pos_lr(p, resize_scale(p.h, p.H, ARSEG_RESIZE_BILINEAR_AC), resize_scale(p.w, p.W, ARSEG_RESIZE_BILINEAR_AC), fy, fx);
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
     if (r.info >= 0) {
         float4 w; int bx, by;
-        rec_block_of(r, Ws, Hs, w, bx, by);
+        rec_block_of(r, p.w, p.h, w, bx, by);
         o.x = pack_h2(w.x, w.y);
         o.y = pack_h2(w.z, w.w);
-        o.z |= (uint32_t)(by * Ws + bx);
+        o.z = (uint32_t)(by * p.w + bx);
     }
     rec[i] = o;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pre-pass 2: the MV warp of the keyframe feature (evaluation.py:177-183 MV rescale, :61-87 grid_sample geometry; f64 position
+// arithmetic as in pos_hr) into the zero-bordered f16 workspace [N][Hp][Wp][64].  A warp owns 32 consecutive workspace pixels:
+// every lane derives ONE pixel's 2x2 source block + weights, then the warp walks the 32 pixels four at a time (8 lanes x 16
+// bytes per pixel, fully coalesced 512-byte stores; the 4 x 8 tap loads of a lane are all in flight together).
+// ---------------------------------------------------------------------------------------------
+template <int K, bool HR32>
+__global__ void __launch_bounds__(256) creff_tc_warp_kernel(CreffMmaParams p, uint4* __restrict__ dst, int TWB) {
+    using Cf = TCfg<K>;
+    constexpr int PXB = HR32 ? 256 : 128;          // bytes per source pixel
+    constexpr int NB = HR32 ? 2 : 4;               // quads of pixels per pass: 16 tap loads (16 bytes each) per lane in flight
+    const int Hp = t_hp<K>(p.H), Wp = t_wp<K>(p.W);
+    const long long plane = (long long)Hp * Wp;
+    const int lane = threadIdx.x & 31, l8 = lane & 7;
+    // work order: bands of TWB workspace rows, and inside a band the N frames one after the other -- the frames of a GOP read the
+    // same keyframe rows (displaced by their MVs), so a band of the keyframe feature is fetched from DRAM once and then served
+    // by L2 (frame-major order streamed the whole feature, 177 MB in fp32 = more than L2, once per frame)
+    const int gpc = (TWB * Wp + 31) / 32;                                   // 32-pixel groups per (band, frame) chunk
+    const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long chunk = wg / gpc;
+    const int band = (int)(chunk / p.N), n = (int)(chunk % p.N);
+    const int r0 = band * TWB;
+    if (r0 >= Hp) return;
+    const int npx = min(TWB, Hp - r0) * Wp;                                 // pixels of this chunk
+    const int j0 = (int)(wg % gpc) * 32;
+    if (j0 >= npx) return;
+    const long long base = (long long)n * plane + (long long)r0 * Wp + j0;  // first workspace pixel of the warp
+    const int nval = min(32, npx - j0);
+    float4 wf = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t src = 0xffffffffu;
+    if (lane < nval) {
+        const int j = j0 + lane;
+        const int fy = r0 + j / Wp - Cf::PT, fx = j % Wp - Cf::PX;
+        // info < 0 outside the image (depthwise zero padding) and for samples with no tap inside; the grid normalisation is an
+        // f64 multiply, as in the march engine (creff_march.cu)
+        const PosRec r = pos_hr<true>(p, n, fy, fx, 2.0 / (double)max(p.W - 1, 1), 2.0 / (double)max(p.H - 1, 1));
+        if (r.info >= 0) {
+            int bx, by;
+            rec_block_of(r, p.W, p.H, wf, bx, by);
+            src = (uint32_t)((p.hr_shared ? 0 : n) * (p.H * p.W) + by * p.W + bx);
+        }
+    }
+    // f16 source: the taps are consumed as they are by mixed-precision FMAs (f16 x f16 + f32 -> f32, SASS FHFMA) with f16 bilinear
+    // weights (<= 2^-12 relative, below the f16 rounding of the result itself); fp32 source: plain fp32 FMAs
+    const uint32_t wxy = pack_h2(wf.x, wf.y), wzw = pack_h2(wf.z, wf.w);
+    const char* const hrb = reinterpret_cast<const char*>(p.hr) + (PXB / 8) * l8;
+    const uint32_t hr_rs = (uint32_t)p.W * PXB;
+#pragma unroll 1
+    for (int pass = 0; pass < 8 / NB; ++pass) {
+        uint4 tap[NB][HR32 ? 8 : 4];
+        float4 wq[NB];
+#pragma unroll
+        for (int it = 0; it < NB; ++it) {
+            const int sl = (pass * NB + it) * 4 + (lane >> 3);
+            if (HR32) {
+                wq[it].x = __shfl_sync(0xffffffffu, wf.x, sl); wq[it].y = __shfl_sync(0xffffffffu, wf.y, sl);
+                wq[it].z = __shfl_sync(0xffffffffu, wf.z, sl); wq[it].w = __shfl_sync(0xffffffffu, wf.w, sl);
+            } else {
+                wq[it].x = __uint_as_float(__shfl_sync(0xffffffffu, wxy, sl));
+                wq[it].y = __uint_as_float(__shfl_sync(0xffffffffu, wzw, sl));
+            }
+            const uint32_t s = __shfl_sync(0xffffffffu, src, sl);
+            if (s != 0xffffffffu) {
+                const char* a0 = hrb + (size_t)s * PXB;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const char* at = a0 + (t & 1) * PXB + (t >> 1) * (size_t)hr_rs;
+                    if (HR32) { tap[it][2 * t] = t_ldg128(at); tap[it][2 * t + 1] = t_ldg128(at + 16); }
+                    else tap[it][t] = t_ldg128(at);
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < (HR32 ? 8 : 4); ++t) tap[it][t] = make_uint4(0u, 0u, 0u, 0u);
+                wq[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < NB; ++it) {
+            uint32_t o[4];
+            if (HR32) {
+                const float wt[4] = {wq[it].x, wq[it].y, wq[it].z, wq[it].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {                       // channels 2e, 2e + 1 of this lane's eight
+                    float vx = 0.f, vy = 0.f;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const float* f = reinterpret_cast<const float*>(&tap[it][2 * t + (e >> 1)]);
+                        vx = fmaf(f[2 * (e & 1)], wt[t], vx);
+                        vy = fmaf(f[2 * (e & 1) + 1], wt[t], vy);
+                    }
+                    o[e] = pack_h2_sat(vx, vy);
+                }
+            } else {
+                const uint32_t wa = __float_as_uint(wq[it].x), wb = __float_as_uint(wq[it].y);
+                const uint16_t w0 = (uint16_t)(wa & 0xffffu), w1 = (uint16_t)(wa >> 16), w2 = (uint16_t)(wb & 0xffffu), w3 = (uint16_t)(wb >> 16);
+                const uint32_t* t0 = reinterpret_cast<const uint32_t*>(&tap[it][0]);
+                const uint32_t* t1 = reinterpret_cast<const uint32_t*>(&tap[it][1]);
+                const uint32_t* t2 = reinterpret_cast<const uint32_t*>(&tap[it][2]);
+                const uint32_t* t3 = reinterpret_cast<const uint32_t*>(&tap[it][3]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float vx = 0.f, vy = 0.f;
+                    t_fhfma(vx, (uint16_t)(t0[e] & 0xffffu), w0); t_fhfma(vy, (uint16_t)(t0[e] >> 16), w0);
+                    t_fhfma(vx, (uint16_t)(t1[e] & 0xffffu), w1); t_fhfma(vy, (uint16_t)(t1[e] >> 16), w1);
+                    t_fhfma(vx, (uint16_t)(t2[e] & 0xffffu), w2); t_fhfma(vy, (uint16_t)(t2[e] >> 16), w2);
+                    t_fhfma(vx, (uint16_t)(t3[e] & 0xffffu), w3); t_fhfma(vy, (uint16_t)(t3[e] >> 16), w3);
+                    o[e] = pack_h2_sat(vx, vy);
+                }
+            }
+            const int q = (pass * NB + it) * 4 + (lane >> 3);
+            if (q < nval) dst[(base + q) * 8 + l8] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
 template <int K, int NCP>
-__global__ void __launch_bounds__(TTHREADS, 1) creff_tc_kernel(CreffMmaParams p, const uint4* __restrict__ rec) {
+__global__ void __launch_bounds__(TTHREADS, 1) creff_tc_kernel(CreffMmaParams p, const uint4* __restrict__ rec, const char* __restrict__ warped) {
     using Cf = TCfg<K>;
     extern __shared__ __align__(1024) uint8_t tsm_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tsm_raw) + 1023) & ~(uintptr_t)1023);
@@ -959,7 +1093,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) creff_tc_kernel(CreffMmaParams p,
 
     if (tid == 0) {
         for (int i = 0; i < TNB; ++i) {
-            tbar_init(sm.gfull + i, TG_WARPS * TARRIVALS); tbar_init(sm.ddone + i, TD_WARPS * TARRIVALS); tbar_init(sm.lrfree + i, TC_WARPS * TARRIVALS);
+            tbar_init(sm.gfull + i, TG_WARPS * TARRIVALS + 1);   /* + the bulk-copy issuer's expect_tx arrival */ tbar_init(sm.ddone + i, TD_WARPS * TARRIVALS); tbar_init(sm.lrfree + i, TC_WARPS * TARRIVALS);
             tbar_init(sm.sfull + i, 1); tbar_init(sm.pfull + i, TC_WARPS * TARRIVALS); tbar_init(sm.ofull + i, 1);
             tbar_init(sm.afull + i, TC_WARPS * TARRIVALS); tbar_init(sm.lfull + i, 1); tbar_init(sm.ofree + i, TC_WARPS * TARRIVALS);
         }
@@ -991,8 +1125,8 @@ __global__ void __launch_bounds__(TTHREADS, 1) creff_tc_kernel(CreffMmaParams p,
     if (warp >= TS_W0) t_s_role<K>(sm, tmem, S);
     else if (warp >= TE_W0) t_e_role<K, NCP>(p, sm, tmem, n, x0, ya, yb, S);
     else if (warp == TM_WARP) t_m_role<K, NCP>(sm, tmem, S, p.dbg);
-    else if (warp < 4 || warp == TQ_WARP0 || warp == TQ_WARP0 + 1) t_d_role<K>(p, sm, x0, ya, NH, S);
-    else t_g_role<K>(p, sm, rec, n, x0, ya, NH, S);
+    else if (warp < TG_WARP0) t_d_role<K>(p, sm, x0, ya, NH, S);
+    else t_g_role<K>(p, sm, rec, warped, n, x0, ya, NH, S);
 #ifdef ARSEG_TTRACE
     if (blockIdx.x == TTRACE_CTA && (tid & 31) == 0) { g_ttrace[warp * 16 + 15] += clock64() - t_role; g_ttrace[warp * 16 + 14] += S; }
 #endif
@@ -1006,7 +1140,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) creff_tc_kernel(CreffMmaParams p,
 }
 
 template <int K, int NCP>
-static int creff_tc_launch_n(CreffMmaParams& p, void* ws, size_t ws_bytes, cudaStream_t st) {
+static int creff_tc_launch_n(CreffMmaParams& p, int hr_dtype, int phase, void* ws, size_t ws_bytes, cudaStream_t st) {
     using Cf = TCfg<K>;
     auto kern = creff_tc_kernel<K, NCP>;
     // per device, written once per process: an idempotent attribute, so the unsynchronised flag is a benign race between
@@ -1021,13 +1155,22 @@ static int creff_tc_launch_n(CreffMmaParams& p, void* ws, size_t ws_bytes, cudaS
         ARSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)((Cf::SMEM + 1024) * 100 / (228 * 1024)) + 1));
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
-    ARSEG_REQUIRE(ws && ws_bytes >= creff_tc_workspace_bytes(p.N, p.H, p.W) && ((uintptr_t)ws % 16) == 0,
-                  "creff_tc: needs a 16-byte aligned workspace of %zu bytes (arseg_creff_workspace_bytes)", creff_tc_workspace_bytes(p.N, p.H, p.W));
+    ARSEG_REQUIRE(ws && ws_bytes >= creff_tc_workspace_bytes(p.N, p.H, p.W, K) && ((uintptr_t)ws % 128) == 0,
+                  "creff_tc: needs a 128-byte aligned workspace of %zu bytes (arseg_creff_workspace_bytes)", creff_tc_workspace_bytes(p.N, p.H, p.W, K));
     uint4* rec = reinterpret_cast<uint4*>(ws);
-    {
-        const long long total = (long long)(p.N + 1) * p.H * p.W;
-        creff_tc_rec_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, st>>>(p, rec);
+    char* warped = reinterpret_cast<char*>(ws) + t_rec_bytes(p.H, p.W);
+    if (phase != ARSEG_CREFF_PHASE_MAIN) {
+        // pre-pass: depends on the keyframe feature and the MV fields only (not on the LR feature)
+        creff_tc_rec_kernel<<<(unsigned)ceil_div_ll((long long)p.H * p.W, 256), 256, 0, st>>>(p, rec);
         ARSEG_CHECK_LAUNCH("creff_tc_rec");
+        int TWB = TWB_DEFAULT;
+        { const char* e = getenv("ARSEG_TC_TWB"); if (e && atoi(e) > 0) TWB = atoi(e); }
+        const long long warps = (long long)ceil_div(t_hp<K>(p.H), TWB) * p.N * ceil_div(TWB * t_wp<K>(p.W), 32);
+        ARSEG_REQUIRE((long long)p.N * p.H * p.W < 0xffffffffLL && ceil_div_ll(warps, 8) < 2147483647LL, "creff_tc: too many pixels");
+        if (hr_dtype == ARSEG_F16) creff_tc_warp_kernel<K, false><<<(unsigned)ceil_div_ll(warps, 8), 256, 0, st>>>(p, reinterpret_cast<uint4*>(warped), TWB);
+        else creff_tc_warp_kernel<K, true><<<(unsigned)ceil_div_ll(warps, 8), 256, 0, st>>>(p, reinterpret_cast<uint4*>(warped), TWB);
+        ARSEG_CHECK_LAUNCH("creff_tc_warp");
+        if (phase == ARSEG_CREFF_PHASE_PREPASS) return ARSEG_OK;
     }
     p.ncols = ceil_div(p.W, TSW);
     { const char* d = getenv("ARSEG_CREFF_DBG"); p.dbg = d ? atoi(d) : 0; }      // -DARSEG_TTRACE builds only
@@ -1042,26 +1185,27 @@ static int creff_tc_launch_n(CreffMmaParams& p, void* ws, size_t ws_bytes, cudaS
     p.nseg = ceil_div(p.H, p.seg_rows);
     const long long blocks = (long long)p.N * p.ncols * p.nseg;
     ARSEG_REQUIRE(blocks > 0 && blocks < 2147483647LL, "creff_tc: grid too large");
-    kern<<<(unsigned)blocks, TTHREADS, Cf::SMEM, st>>>(p, rec);
+    kern<<<(unsigned)blocks, TTHREADS, Cf::SMEM, st>>>(p, rec, warped);
     ARSEG_CHECK_LAUNCH("creff_tc");
     return ARSEG_OK;
 }
 
 template <int K>
-static int creff_tc_launch_k(CreffMmaParams& p, void* ws, size_t ws_bytes, cudaStream_t st) {
-    if (!p.wcls) return creff_tc_launch_n<K, 0>(p, ws, ws_bytes, st);
-    if (p.ncls <= 16) return creff_tc_launch_n<K, 16>(p, ws, ws_bytes, st);
-    return creff_tc_launch_n<K, 32>(p, ws, ws_bytes, st);
+static int creff_tc_launch_k(CreffMmaParams& p, int hr_dtype, int phase, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (!p.wcls) return creff_tc_launch_n<K, 0>(p, hr_dtype, phase, ws, ws_bytes, st);
+    if (p.ncls <= 16) return creff_tc_launch_n<K, 16>(p, hr_dtype, phase, ws, ws_bytes, st);
+    return creff_tc_launch_n<K, 32>(p, hr_dtype, phase, ws, ws_bytes, st);
 }
 
-// hr and lr are f16 NHWC ([.,H,W,64] / [N,h,w,64]); k in {3, 5, 7}; ws = the gather records (creff_tc_workspace_bytes)
-int creff_tc_launch(CreffMmaParams& p, int k, void* ws, size_t ws_bytes, cudaStream_t st) {
+// hr NHWC fp32 or f16 ([.,H,W,64]), lr NHWC f16 ([N,h,w,64]); k in {3, 5, 7}; ws = lr_up gather records + warped keyframe rows
+// (creff_tc_workspace_bytes); phase: ARSEG_CREFF_PHASE_* (pre-pass and attention kernel together or separately)
+int creff_tc_launch(CreffMmaParams& p, int k, int hr_dtype, int phase, void* ws, size_t ws_bytes, cudaStream_t st) {
     if (p.H < 2 || p.W < 2 || p.h < 2 || p.w < 2) ARSEG_UNSUPPORTED("creff_tc: maps must be at least 2x2 (hr %dx%d, lr %dx%d)", p.H, p.W, p.h, p.w);
     ARSEG_REQUIRE((long long)p.H * p.W < (1LL << 31) && (long long)p.h * p.w < (1LL << 31), "creff_tc: map too large");
     switch (k) {
-        case 3: return creff_tc_launch_k<3>(p, ws, ws_bytes, st);
-        case 5: return creff_tc_launch_k<5>(p, ws, ws_bytes, st);
-        case 7: return creff_tc_launch_k<7>(p, ws, ws_bytes, st);
+        case 3: return creff_tc_launch_k<3>(p, hr_dtype, phase, ws, ws_bytes, st);
+        case 5: return creff_tc_launch_k<5>(p, hr_dtype, phase, ws, ws_bytes, st);
+        case 7: return creff_tc_launch_k<7>(p, hr_dtype, phase, ws, ws_bytes, st);
         default: ARSEG_UNSUPPORTED("creff_tc: window k=%d (3, 5, 7)", k);
     }
 }

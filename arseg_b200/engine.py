@@ -67,6 +67,12 @@ class Plan:
         self.conv_flops = 0                # 2*MACs of conv/linear layers as executed
         self.step_flops: List[int] = []    # the same, per launch (0 for launches that are not contractions)
         self.n_launches = 0
+        # steps that depend only on the plan's INPUTS (not on earlier steps): launch() forks them onto a side stream at the start
+        # of the plan and joins right before the step that follows them in the serial order, so a memory-bound pre-pass (the MV
+        # warp of the keyframe feature) overlaps the tensor-core-bound LR branch.  launch_range() / profile() run them in place.
+        self.hoisted: List[int] = []
+        self.overlap = os.environ.get("ARSEG_PLAN_OVERLAP", "1") != "0"
+        self._side: Optional[torch.cuda.Stream] = None
 
     # -- helpers -------------------------------------------------------------------------------
     def dev(self, t: torch.Tensor, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
@@ -81,7 +87,9 @@ class Plan:
         self.keep.append(t)
         return t
 
-    def _add(self, name: str, fn: Callable[[int], int], flops: int = 0) -> None:
+    def _add(self, name: str, fn: Callable[[int], int], flops: int = 0, hoist: bool = False) -> None:
+        if hoist:
+            self.hoisted.append(len(self.steps))
         self.steps.append(fn)
         self.names.append(name)
         self.step_flops.append(int(flops))
@@ -262,11 +270,13 @@ class Plan:
 
     def creff(self, hr: torch.Tensor, lr: torch.Tensor, sd: SD, prefix: str, k: int, *, flow: Optional[torch.Tensor] = None,
               hr_shared=False, lr_layout=L.NHWC, wcls=None, bcls=None, log_softmax=False, want_p=True, want_logits=True,
-              want_argmax=False, name="creff_fused", engine=None, hr_layout=L.NCHW):
+              want_argmax=False, name="creff_fused", engine=None, hr_layout=L.NCHW, hoist_prepass=False):
         """Fused MV-warp + CReFF (+ classifier).  hr NCHW fp32 [1|N,C,H,W]; lr [N,h,w,C] NHWC (or NCHW fp32).
         engine None: exact fp32 SIMT kernel in 'fp32' plans; tensor-core window attention (f16 operands, fp32
         accumulate) in 'tf32'/'f16'/'bf16' plans when C is a multiple of 64 (hr is first converted to NHWC by one transpose
-        launch; C = 64: column-marching engine, C > 64: the two-launch wide engine with a plan-owned workspace)."""
+        launch; C = 64: column-marching engine, or the tcgen05 engine when lr is f16; C > 64: the two-launch wide engine with a
+        plan-owned workspace).  hoist_prepass: hr and flow are INPUTS of the plan (not produced by earlier steps), so the tcgen05
+        engine's MV-warp pre-pass may run on the side stream from the start of the plan."""
         if hr_layout == L.NHWC:         # the keyframe feature already in the internal layout (fp32 [1|N,H,W,C]): no transpose launch
             _, H, W, Cc = hr.shape
         else:
@@ -276,23 +286,23 @@ class Plan:
                       and (wcls is None or wcls.shape[0] <= 32) and min(H, W) >= 2)
             engine = L.CREFF_MMA_F16 if mma_ok else L.CREFF_EXACT_F32
         hr_in_nhwc = hr_layout == L.NHWC
-        # C = 64 with an f16 LR feature (the 'f16' plan): ARSEG_CREFF_TC=1 converts the keyframe feature to f16 NHWC as well and
-        # runs the tcgen05 / TMEM engine (csrc/creff_tc.cu, k <= 7).  Default = the mma.sync march engine: measured faster on
-        # B200 (3.33 vs 4.1 ms per 11 frames, DESIGN.md section 3.1 -- both are bound by their gather / depthwise producer roles)
+        # C = 64 with an f16 LR feature (the 'f16' plan): the tcgen05 / TMEM engine (csrc/creff_tc.cu, k <= 7), 3.15 ms per 11
+        # CamVid frames against 3.34 ms for the mma.sync march engine, and 0.39 ms of that is the MV-warp pre-pass, which this
+        # plan runs on a side stream under the LR branch.  ARSEG_CREFF_TC=0 keeps the march engine (A/B measurements).
         tc = (engine == L.CREFF_MMA_F16 and Cc == 64 and k <= 7 and lr_layout == L.NHWC and lr.dtype == torch.float16
-              and os.environ.get("ARSEG_CREFF_TC", "0") == "1")
-        if engine == L.CREFF_MMA_F16:
-            if hr_in_nhwc and not tc:
-                if hr.dtype != torch.float32:
-                    raise ValueError("creff: an NHWC keyframe feature must be fp32")
-            elif hr_in_nhwc:
-                raise ValueError("creff: the tcgen05 engine takes the keyframe feature as NCHW fp32 (it converts to f16 NHWC itself)")
+              and os.environ.get("ARSEG_CREFF_TC", "1") != "0")
+        if engine in (L.CREFF_MMA_F16, L.CREFF_TCGEN05):
+            if hr_in_nhwc:
+                if hr.dtype != torch.float32 and not (tc and hr.dtype == torch.float16):
+                    raise ValueError("creff: an NHWC keyframe feature must be fp32 (or fp16 for the tcgen05 engine)")
             else:
-                hr_nhwc = self.empty((hr.shape[0], H, W, Cc), torch.float16 if tc else torch.float32)
+                hr_nhwc = self.empty((hr.shape[0], H, W, Cc), torch.float32)
                 fn_t = self.lib.arseg_nchw_to_nhwc
-                targs = (hr.data_ptr(), hr_nhwc.data_ptr(), L.F16 if tc else L.F32, hr.shape[0], Cc, H, W)
-                self._add("hr_nchw_to_nhwc", lambda s: fn_t(*targs, s))
+                targs = (hr.data_ptr(), hr_nhwc.data_ptr(), L.F32, hr.shape[0], Cc, H, W)
+                self._add("hr_nchw_to_nhwc", lambda s: fn_t(*targs, s), hoist=hoist_prepass and tc)
                 hr, hr_layout = hr_nhwc, L.NHWC
+            if tc:
+                engine = L.CREFF_TCGEN05
             name = name + ("_tc" if tc else "_mma")
         elif hr_in_nhwc:
             raise ValueError("creff: the exact fp32 engine takes the keyframe feature as NCHW")
@@ -320,13 +330,21 @@ class Plan:
                         wc.data_ptr() if wc is not None else None, bc.data_ptr() if bc is not None else None, ncls,
                         int(log_softmax), out_p.data_ptr() if out_p is not None else None,
                         out_l.data_ptr() if out_l is not None else None, out_a.data_ptr() if out_a is not None else None,
-                        N, Cc, H, W, k, None, 0, L.F16 if tc else L.F32)
+                        N, Cc, H, W, k, None, 0, dtype_code(hr.dtype), L.CREFF_PHASE_ALL)
         need = int(self.lib.arseg_creff_workspace_bytes(C.byref(a)))
         if need:
             wsb = self.empty((need,), torch.uint8)
             a.workspace, a.workspace_bytes = wsb.data_ptr(), need
         self.keep.append(a)
         fn = self.lib.arseg_creff_fused_fwd
+        if tc:
+            # two calls on the same arguments: the workspace pre-pass (MV warp of the keyframe feature: reads hr + flow only, so it
+            # may run from the start of the plan when those are plan inputs) and the attention kernel
+            pre = L.CreffArgs()
+            C.memmove(C.byref(pre), C.byref(a), C.sizeof(a))
+            pre.phase, a.phase = L.CREFF_PHASE_PREPASS, L.CREFF_PHASE_MAIN
+            self.keep.append(pre)
+            self._add(name + "_prewarp", lambda s, a=pre: fn(C.byref(a), s), hoist=hoist_prepass)
         self._add(name, lambda s, a=a: fn(C.byref(a), s))
         return out_p, out_l, out_a
 
@@ -349,13 +367,37 @@ class Plan:
 
     # -- execution -----------------------------------------------------------------------------
     def launch(self) -> None:
-        """Enqueue every kernel of the plan on the current stream."""
+        """Enqueue every kernel of the plan on the current stream (hoisted steps: on a side stream forked at the start of the
+        plan and joined before the step that consumes them; inside a stream capture this becomes a parallel graph branch)."""
         with torch.cuda.device(self.device):
-            s = torch.cuda.current_stream().cuda_stream
-            for name, fn in zip(self.names, self.steps):
+            main = torch.cuda.current_stream()
+            s = main.cuda_stream
+            hoisted = self.hoisted if self.overlap else []
+            join_at = {}
+            if hoisted:
+                if self._side is None:
+                    self._side = torch.cuda.Stream(priority=0)          # lowest priority: fills what the main branch leaves free
+                fork = torch.cuda.Event()
+                fork.record(main)
+                self._side.wait_event(fork)
+                ss = self._side.cuda_stream
+                for i in hoisted:
+                    rc = self.steps[i](ss)
+                    if rc != L.OK:
+                        L.check(rc, self.names[i])
+                    ev = torch.cuda.Event()
+                    ev.record(self._side)
+                    join_at[i + 1] = ev
+            for i, (name, fn) in enumerate(zip(self.names, self.steps)):
+                if i in join_at:
+                    main.wait_event(join_at[i])
+                if hoisted and i in hoisted:
+                    continue
                 rc = fn(s)
                 if rc != L.OK:
                     L.check(rc, name)
+            if len(self.steps) in join_at:
+                main.wait_event(join_at[len(self.steps)])
 
     def launch_range(self, lo: int, hi: int) -> None:
         with torch.cuda.device(self.device):
@@ -364,6 +406,13 @@ class Plan:
                 rc = fn(s)
                 if rc != L.OK:
                     L.check(rc, name)
+
+    def _capture_stream(self) -> torch.cuda.Stream:
+        # the main branch is captured on a high-priority stream: kernel nodes keep their stream's priority, so the block scheduler
+        # serves the LR-branch kernels first and the hoisted (priority 0) pre-pass takes the SM capacity they leave
+        if getattr(self, "_cap", None) is None:
+            self._cap = torch.cuda.Stream(priority=-1)
+        return self._cap
 
     def capture(self, split_at: Optional[int] = None) -> None:
         """Capture the launch sequence into a CUDA graph (replayed by run()).  split_at = i: two graphs, launches [0, i) and
@@ -380,7 +429,7 @@ class Plan:
                 parts = []
                 for lo, hi in ((0, split_at), (split_at, len(self.steps))):
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
+                    with torch.cuda.graph(g, stream=self._capture_stream()):
                         self.launch_range(lo, hi)
                     parts.append(g)
                 self.parts, self.split_at = parts, split_at
@@ -393,7 +442,7 @@ class Plan:
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=self._capture_stream()):
                 self.launch()
             self.graph = g
 
@@ -492,7 +541,7 @@ def build_psp_phase1(pl: Plan, sd: SD, x_nchw: torch.Tensor, p: str = "", sizes=
         # up_3 produces the LR feature p (the residual of the CReFF kernel): kept fp32 in 16-bit plans -- the march engine gathers
         # it fastest as fp32 (3.33 ms per 11 frames, 4.39 ms from an f16 feature) -- except for the opt-in tcgen05 CReFF engine,
         # whose operands are f16
-        tc_creff = pl.precision == "f16" and os.environ.get("ARSEG_CREFF_TC", "0") == "1"
+        tc_creff = pl.precision == "f16" and os.environ.get("ARSEG_CREFF_TC", "1") != "0"
         t = pl.conv(t, sd[p + u + "conv.0.weight"], sc, sh, pad=1, act=L.ACT_PRELU,
                     slope=float(sd[p + u + "conv.2.weight"].reshape(-1)[0]), name=u + "conv",
                     out_f32=(u == "up_3." and not tc_creff))

@@ -12,6 +12,8 @@ from __future__ import annotations
 
 from typing import Dict, Optional, Sequence
 
+import os
+
 import torch
 
 from . import _lib as L
@@ -61,6 +63,15 @@ def nonkey_step(net, imgs: torch.Tensor, ref_p: torch.Tensor, flow: torch.Tensor
     return preds, logits, fused, lr_p
 
 
+def internal_ref_dtype(arch: str, precision: str, k: int = 7) -> torch.dtype:
+    """dtype of the keyframe feature in the engines' internal NHWC layout: fp16 where the non-keyframe step runs the tcgen05 CReFF
+    engine (f16 plan, C = 64, k <= 7: its MV-warp pre-pass stores fp16 rows anyway and reads an fp16 feature at half the L2
+    footprint), fp32 otherwise."""
+    C_ = ARCH_INFO[arch][0]
+    tc = precision == "f16" and C_ == 64 and k <= 7 and os.environ.get("ARSEG_CREFF_TC", "1") != "0"
+    return torch.float16 if tc else torch.float32
+
+
 class NonKeyEngine:
     """All non-keyframes of a GOP in one captured step.
 
@@ -75,9 +86,9 @@ class NonKeyEngine:
                  mean=ops.CAMVID_MEAN, std=ops.CAMVID_STD, ref_nhwc: Optional[torch.Tensor] = None):
         """uint8_frames: `imgs` is uint8 HWC [N,H,W,3] (decoded frames); ToTensor + Normalize(mean, std)
         (dataset/camvid.py:182-185) are fused into the LR down-scale kernel -- a quarter of the host->device bytes.
-        ref_nhwc: the keyframe feature as an fp32 NHWC [1,Hf,Wf,C] device tensor in the internal layout (e.g. a
-        KeyFrameEngine's `p_nhwc`): the step reads it in place, without the per-GOP NCHW -> NHWC transpose launch.  `ref_p`
-        (the API-layout buffer) is then None."""
+        ref_nhwc: the keyframe feature as an NHWC [1,Hf,Wf,C] device tensor in the internal layout (fp32, or
+        internal_ref_dtype(arch, precision, k); e.g. a KeyFrameEngine's `p_nhwc`): the step reads it in place, without the
+        per-GOP NCHW -> NHWC transpose launch.  `ref_p` (the API-layout buffer) is then None."""
         if arch not in ARCH_INFO:
             raise KeyError(arch)
         self.arch, self.N, self.H, self.W, self.scale, self.k = arch, n_frames, H, W, scale, k
@@ -94,8 +105,9 @@ class NonKeyEngine:
             self.mv = pl.empty((n_frames, H, W, 2), torch.int16)
             self.ref_nhwc = ref_nhwc
             if ref_nhwc is not None:
-                if tuple(ref_nhwc.shape) != (1, self.Hf, self.Wf, C_) or ref_nhwc.dtype != torch.float32 or not ref_nhwc.is_contiguous():
-                    raise ValueError("ref_nhwc must be a contiguous fp32 [1,%d,%d,%d] tensor" % (self.Hf, self.Wf, C_))
+                ok_dt = (torch.float32, internal_ref_dtype(arch, precision, k))
+                if tuple(ref_nhwc.shape) != (1, self.Hf, self.Wf, C_) or ref_nhwc.dtype not in ok_dt or not ref_nhwc.is_contiguous():
+                    raise ValueError("ref_nhwc must be a contiguous [1,%d,%d,%d] tensor of %s" % (self.Hf, self.Wf, C_, " or ".join(map(str, set(ok_dt)))))
                 self.ref_p = None
             else:
                 self.ref_p = pl.empty((1, C_, self.Hf, self.Wf), torch.float32)
@@ -120,7 +132,7 @@ class NonKeyEngine:
                                            hr_shared=True, hr_layout=L.NCHW if ref_nhwc is None else L.NHWC,
                                            lr_layout=L.NHWC, wcls=sd[fin + "weight"], bcls=sd[fin + "bias"],
                                            log_softmax=logsm, want_p=want_p, want_logits=(want_logits or not direct),
-                                           want_argmax=direct)
+                                           want_argmax=direct, hoist_prepass=True)
             self.fused_p, self.logits = out_p, out_l
             if direct:
                 self.preds = out_a
@@ -212,9 +224,10 @@ class KeyFrameEngine:
                 _, p = E.build_semseg_phase1(pl, sd, x, "")
             else:
                 _, _, p = E.build_bisenet_phase1(pl, sd, x, "", aux=False)
-            # the feature in the internal layout: fp32 NHWC for CamVid-PSP in every plan (up_3 writes fp32) -> a NonKeyEngine
-            # built with ref_nhwc=self.p_nhwc reads it in place; api_layout=False then skips the NCHW copy altogether
-            self.p_nhwc = p if p.dtype == torch.float32 else None
+            # the feature in the internal layout: NHWC for CamVid-PSP in every plan (up_3 writes fp32, or fp16 where the f16 plan's
+            # non-keyframe step runs the tcgen05 CReFF engine) -> a NonKeyEngine built with ref_nhwc=self.p_nhwc reads it in place;
+            # api_layout=False then skips the NCHW copy altogether
+            self.p_nhwc = p if p.dtype in (torch.float32, internal_ref_dtype(arch, precision)) and C_ == 64 else None
             self.p = pl.to_nchw(p, name="p_to_nchw", out=out) if (api_layout or self.p_nhwc is None) else None
             if graph:
                 pl.capture()

@@ -271,8 +271,8 @@ def creff_fused(hr, lr, wq, bq, wk, bk, wv, bv, k, flow=None, flow_hw=None, wcls
                 engine=L.CREFF_EXACT_F32, hr_layout=L.NCHW):
     """Fused (MV warp +) CReFF (+ classifier).  hr fp32 NCHW [1|N,C,H,W] (or NHWC [1|N,H,W,C] with hr_layout=NHWC);
     lr NCHW fp32 [N,C,h,w] or NHWC [N,h,w,C].  engine: L.CREFF_EXACT_F32 (fp32 SIMT, NCHW hr) or L.CREFF_MMA_F16
-    (tensor-core window attention, TF32-class error, C = 64 m, NHWC hr and lr; C = 64 with fp16 hr AND fp16 lr runs the
-    tcgen05 / TMEM engine, k <= 7)."""
+    (mma.sync window attention, TF32-class error, C = 64 m, NHWC hr and lr) or L.CREFF_TCGEN05 (tcgen05 / TMEM engine: C = 64,
+    k <= 7, NHWC fp32 or fp16 hr, NHWC fp16 lr; CREFF_MMA_F16 with an fp16 hr is routed to it as well)."""
     _chk_cuda("creff_fused", hr, lr, wq, bq, wk, bk, wv, bv, flow, wcls, bcls)
     _chk_f32("creff_fused (depthwise / classifier weights)", wq, bq, wk, bk, wv, bv, wcls, bcls)
     if hr.dtype not in (torch.float32, torch.float16) or (hr.dtype == torch.float16 and hr_layout != L.NHWC):

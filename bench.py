@@ -285,7 +285,7 @@ def main():
                  torch.empty((n_local, H, W), dtype=torch.uint8).pin_memory())]
         # the keyframe feature is resident in the engine's internal layout (fp32 NHWC, what the keyframe engine produces): the
         # tensor-core CReFF engines read it in place; the exact fp32 plan keeps the API layout (NCHW)
-        ref_buf = None if precision == "fp32" else torch.empty((1, H // STRIDE_P, W // STRIDE_P, C_P), dtype=torch.float32, device=dev)
+        ref_buf = None if precision == "fp32" else torch.empty((1, H // STRIDE_P, W // STRIDE_P, C_P), dtype=ev.internal_ref_dtype(ARCH, precision, K_WIN), device=dev)
         eng = ev.NonKeyEngine(ARCH, sd, n_local, H, W, SCALE, precision, K_WIN, device=dev, want_logits=True,
                               split_keyframe=frame_mode, uint8_frames=True, ref_nhwc=ref_buf)
         eng.set_inputs(fr.to(dev), mv.to(dev), ref_p.to(dev))
@@ -353,7 +353,10 @@ def main():
         r["lr_numel"], r["lr_elem"] = lr.numel() // max(1, r["n_local"]), lr.element_size()
         r["logits_numel"] = eng.logits.numel() // max(1, r["n_local"]) if eng.logits is not None else 0
         r["creff_names"] = [n for n in eng.plan.names if n.startswith("creff")]
-        r["hr_elem"] = 2 if any(n.endswith("_tc") for n in r["creff_names"]) else 4
+        r["tc"] = any(n.endswith("_tc") for n in r["creff_names"])
+        r["hr_elem"] = eng.ref_nhwc.element_size() if eng.ref_nhwc is not None else 4
+        # tcgen05 engine: the MV-warped keyframe rows go through a workspace (written by the pre-pass, read back by the attention kernel)
+        r["ws_bytes"] = int(eng.N * (H + 17) * ((W + 15) // 16 * 16 + 8) * 128) if r["tc"] else 0      # k = 7: 6 + 11 border rows, 8 border columns (creff_tc.cu t_hp / t_wp)
         return eng
 
     sampler = ClockSampler(local_rank)
@@ -406,19 +409,23 @@ def main():
         conv_tflops = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         tr = traffic.get("creff_" + precision) if ARCH == "camvid-psp18" else None
         roof_creff = {"kernel": "%s (MV warp + CReFF + classifier + log-softmax + argmax; %d launch(es) per step)" %
-                                ("creff_tc_kernel [tcgen05]" if r["hr_elem"] == 2 else "creff_march_kernel [mma.sync]" if C_P == 64 else "creff_wide kernels [mma.sync]",
+                                ("creff_tc_warp_kernel + creff_tc_kernel [tcgen05]" if r["tc"] else "creff_march_kernel [mma.sync]" if C_P == 64 else "creff_wide kernels [mma.sync]",
                                  len(r["creff_names"])),
                       "bound": "hbm", "achieved": round(creff_gbs, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(creff_gbs / hbm_peak, 4),
                       "traffic": int(tr * n / N_FRAMES) if tr else None,
                       "traffic_source": "static: profiles/ncu_traffic.json (ncu --set full capture of this command, scaled to this launch's frame count)" if tr else None,
                       "share_of_step": round(creff_ms / t_all, 3) if t_all else None, "ms_per_launch": round(creff_ms, 4),
                       "algorithmic_bytes_per_launch": cbytes,
+                      "workspace_round_trip_bytes": 2 * r["ws_bytes"],
                       "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
                       "achieved_survey_8d_bytes": round(creff_gbs_full, 1), "frac_survey_8d_bytes": round(creff_gbs_full / hbm_peak, 4),
                       "note": "achieved = bytes ONE launch must move / its CUDA-event time: the keyframe feature once (shared by the "
                               "frames of the GOP) + per frame the LR feature (%d B/elem), the int16 MV field, fp32 logits and the u8 class "
                               "map.  achieved_survey_8d_bytes = SURVEY 8(d)'s 434.0 MB/frame figure (counts the keyframe feature per frame "
-                              "and the fused-p write that evaluation.py:193 discards and the engine does not materialise)" % r["lr_elem"]}
+                              "and the fused-p write that evaluation.py:193 discards and the engine does not materialise).  "
+                              "workspace_round_trip_bytes: the tcgen05 engine's pre-pass writes the MV-warped keyframe rows (fp16) to a "
+                              "workspace and the attention kernel reads them back -- real DRAM traffic (it is in `traffic`) that the "
+                              "algorithm does not need, so it earns no credit in `achieved`" % r["lr_elem"]}
         roof_conv = {"kernel": "conv_tc / conv_simt kernels (implicit-GEMM conv launches of phase 1; stem, pyramid 1x1 and linear layers excluded "
                                "from both FLOPs and time)", "bound": "tensor",
                      "achieved": round(conv_tflops, 2), "peak": tc_burst, "unit": "TFLOP/s", "frac": round(conv_tflops / tc_burst, 4),
@@ -452,7 +459,7 @@ def main():
                    "precision": args.precision,
                    "l2": "256 MiB buffer written between timed steps (L2 flush)",
                    "inputs": "uint8 HWC frames (ToTensor + Normalize fused into the LR down-scale kernel), int16 MV fields, keyframe feature "
-                             "resident in the engine's internal layout (fp32 NHWC, as the keyframe engine writes it)",
+                             "resident in the engine's internal layout (NHWC, %s, as the keyframe engine of this plan writes it)" % str(ev.internal_ref_dtype(ARCH, args.precision, K_WIN)).replace("torch.", ""),
                    "outputs": "log-prob maps fp32 + argmax class maps uint8; fused p is not materialised (evaluation.py:193 discards it)"},
         "e2e": {"value": round(main_r["e2e"], 2), "unit": UNIT, "h2d_bytes_per_step": main_r["h2d"],
                 "d2h_bytes_per_step": main_r["d2h"], "ms_per_step": round(main_r["ms_e2e"] / args.steps, 4),

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define ARSEG_ABI_VERSION 5
+#define ARSEG_ABI_VERSION 6
 
 enum { ARSEG_OK = 0, ARSEG_E_BADARG = -1, ARSEG_E_UNSUPPORTED = -2, ARSEG_E_CUDA = -3 };
 enum { ARSEG_F32 = 0, ARSEG_BF16 = 1, ARSEG_F64 = 2, ARSEG_I16 = 3, ARSEG_F16 = 4 };
@@ -36,7 +36,11 @@ enum { ARSEG_NCHW = 0, ARSEG_NHWC = 1 };
 enum { ARSEG_CONV_SIMT_F32 = 1, ARSEG_CONV_TC_TF32 = 2, ARSEG_CONV_TC_BF16 = 3, ARSEG_CONV_TC_F16 = 4 };
 /* CReFF engines: exact fp32 SIMT (any C, NCHW hr), or tensor-core window attention (f16 operands with fp32 accumulate
  * -- TF32-class error; NHWC hr and lr; C = 64: tcgen05 / TMEM for fp16 hr + lr, mma.sync for fp32 hr; C = 128..1024: mma.sync) */
-enum { ARSEG_CREFF_EXACT_F32 = 0, ARSEG_CREFF_MMA_F16 = 1 };
+enum { ARSEG_CREFF_EXACT_F32 = 0, ARSEG_CREFF_MMA_F16 = 1, ARSEG_CREFF_TCGEN05 = 2 };
+/* arseg_creff_args.phase: the tcgen05 engine is a workspace pre-pass (MV warp of the keyframe feature, which depends only on
+ * the keyframe feature and the MV fields) followed by the attention kernel; a caller may issue the two separately so that the
+ * pre-pass overlaps the LR-branch CNN on another stream.  The other engines do nothing in ARSEG_CREFF_PHASE_PREPASS. */
+enum { ARSEG_CREFF_PHASE_ALL = 0, ARSEG_CREFF_PHASE_PREPASS = 1, ARSEG_CREFF_PHASE_MAIN = 2 };
 
 typedef void* arseg_stream_t;
 
@@ -176,9 +180,9 @@ int arseg_pyramid_upsample_concat(const float* stage, const void* feats, void* o
  * ---------------------------------------------------------------------------------------------- */
 typedef struct arseg_creff_args {
     const void* hr;         /* keyframe feature p_HR, NCHW [Nhr,C,H,W] or NHWC [Nhr,H,W,C] (hr_layout), fp32 or (NHWC, C = 64,
-                               ARSEG_CREFF_MMA_F16 only) fp16 (hr_dtype); Nhr = 1 (shared by all N frames) or N */
+                               tcgen05 engine only) fp16 (hr_dtype); Nhr = 1 (shared by all N frames) or N */
     int hr_shared;          /* 1: hr has batch 1 and is broadcast over the N frames */
-    int hr_layout;          /* ARSEG_NCHW (required by ARSEG_CREFF_EXACT_F32) | ARSEG_NHWC (required by ARSEG_CREFF_MMA_F16) */
+    int hr_layout;          /* ARSEG_NCHW (required by ARSEG_CREFF_EXACT_F32) | ARSEG_NHWC (required by the tensor-core engines) */
     int engine;             /* ARSEG_CREFF_*; an engine that does not support the arguments returns ARSEG_E_UNSUPPORTED */
     const void* flow;       /* NULL: hr is already warped (MyAttention.forward semantics).
                                else MV field [N,Hm,Wm,2] at FRAME resolution: ARSEG_I16 quarter-pel
@@ -196,11 +200,17 @@ typedef struct arseg_creff_args {
     void* workspace;        /* device scratch of >= arseg_creff_workspace_bytes(a) bytes, owned by the caller; may be NULL
                                when that function returns 0 (C = 64 and the exact engine need none) */
     size_t workspace_bytes;
-    int hr_dtype;           /* ARSEG_F32 (0) | ARSEG_F16.  With C = 64, fp16 hr + fp16 NHWC lr run the tcgen05 engine (k <= 7) */
+    int hr_dtype;           /* ARSEG_F32 (0) | ARSEG_F16 (tcgen05 engine only; ARSEG_CREFF_MMA_F16 with an fp16 hr is routed to it) */
+    int phase;              /* ARSEG_CREFF_PHASE_* (0 = the whole operator in one call) */
 } arseg_creff_args;
+/* Engines: ARSEG_CREFF_EXACT_F32 -- fp32 SIMT, any C multiple of 16, k in {3,5,7,9}.
+ *          ARSEG_CREFF_MMA_F16   -- mma.sync column-marching engine (C = 64) / two-launch wide engine (C = 128 .. 1024).
+ *          ARSEG_CREFF_TCGEN05   -- tcgen05 / TMEM engine: C = 64, k in {3,5,7}, NHWC fp32 or fp16 hr, NHWC fp16 lr, ncls <= 32;
+ *                                   needs the workspace (MV-warped keyframe rows, ~ N x H x W x 128 bytes). */
 int arseg_creff_fused_fwd(const arseg_creff_args* a, arseg_stream_t stream);
 /* Scratch the call above needs for these arguments (ARSEG_CREFF_MMA_F16 with C = 128, 192, ... 1024: Q, K, V in fp16
- * and the lr_up residual in fp32 pass through it between the two launches of that engine); 0 otherwise. */
+ * and the lr_up residual in fp32 pass through it between the two launches of that engine; ARSEG_CREFF_TCGEN05: the
+ * MV-warped keyframe rows in fp16 + the lr_up gather records); 0 otherwise. */
 size_t arseg_creff_workspace_bytes(const arseg_creff_args* a);
 
 #ifdef __cplusplus

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol(lib_path):
 def test_binding_covers_header(lib_path):
     assert sorted(_lib.EXPORTED_SYMBOLS) == header_symbols()
     lib = _lib.load()
-    assert lib.arseg_abi_version() == _lib.ABI_VERSION == 5
+    assert lib.arseg_abi_version() == _lib.ABI_VERSION == 6
 
 
 def test_error_reporting_without_gpu(lib_path):

@@ -238,20 +238,67 @@ def test_full_shape_engine_matches_oracle(arch, precision):
     torch.cuda.empty_cache()
 
 
-def test_full_shape_tcgen05_creff_matches_oracle(monkeypatch):
-    """BASELINE configs[1] shapes through the opt-in tcgen05 CReFF engine (ARSEG_CREFF_TC=1) of the f16 plan."""
-    monkeypatch.setenv("ARSEG_CREFF_TC", "1")
+@pytest.mark.parametrize("ref_layout", ["nchw", "nhwc"])
+def test_full_shape_tcgen05_creff_matches_oracle(ref_layout):
+    """BASELINE configs[1] shapes through the tcgen05 CReFF engine (the f16 plan's default at C = 64): the MV-warp pre-pass is a
+    hoisted side-stream branch of the captured graph; the keyframe feature is read as fp32, NCHW (API layout, transposed inside
+    the plan) or NHWC in place."""
     arch = "camvid-psp18"
     H, W, stride, C = _FULL[arch]
     sd, imgs, ref_p, mv, preds, logits, fused, lr_p = _full_case(arch)
-    eng = ev.NonKeyEngine(arch, sd, 1, H, W, 0.5, "f16", want_logits=True, want_p=True, device=DEV)
-    assert any(nm.endswith("_tc") for nm in eng.plan.names), eng.plan.names
+    ref_nhwc = torch.empty((1, H, W, C), device=DEV) if ref_layout == "nhwc" else None
+    eng = ev.NonKeyEngine(arch, sd, 1, H, W, 0.5, "f16", want_logits=True, want_p=True, device=DEV, ref_nhwc=ref_nhwc)
+    assert any(nm.endswith("_tc") for nm in eng.plan.names) and any(nm.endswith("_tc_prewarp") for nm in eng.plan.names), eng.plan.names
+    assert eng.plan.hoisted, "the pre-pass must be a hoisted step"
     eng.set_inputs(imgs.to(DEV), torch.from_numpy(mv).unsqueeze(0).to(DEV), ref_p.to(DEV))
     got = eng.step().cpu()
     torch.cuda.synchronize()
     tmax, trms, targ = TOL["f16"]
     assert rel_err(eng.fused_p, fused) < tmax and rms_err(eng.fused_p, fused) < trms
     assert rel_err(eng.logits, logits) < tmax
+    assert float((got.long() != preds).float().mean()) <= targ
+
+
+def test_hoisted_prepass_equals_serial_plan(monkeypatch):
+    """The side-stream fork / join of the pre-pass is a scheduling change only: the same engine with ARSEG_PLAN_OVERLAP=0 (every
+    step in order on one stream) and the eager (uncaptured) plan give bit-identical class maps and logits, run after run."""
+    g = load_golden("camvid_psp18_s05")
+    arch, _, sd, imgs, ref_p, mv, flow, scale = case_setup(g)
+    H, W = imgs.shape[-2:]
+    mvd = torch.from_numpy(mv).unsqueeze(0).to(DEV)
+
+    def run(graph):
+        eng = ev.NonKeyEngine(arch, sd, 1, H, W, scale, "f16", want_logits=True, device=DEV, graph=graph)
+        assert any(nm.endswith("_tc") for nm in eng.plan.names)
+        eng.set_inputs(imgs.to(DEV), mvd, ref_p.to(DEV))
+        outs = []
+        for _ in range(3):
+            outs.append((eng.step().clone(), eng.logits.clone()))
+        torch.cuda.synchronize()
+        for o in outs[1:]:
+            assert torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1])
+        return outs[0]
+    a = run(True)
+    b = run(False)
+    monkeypatch.setenv("ARSEG_PLAN_OVERLAP", "0")
+    c = run(True)
+    for x in (b, c):
+        assert torch.equal(a[0], x[0]) and torch.equal(a[1], x[1])
+
+
+def test_f16_plan_keeps_the_march_engine_selectable(monkeypatch):
+    """ARSEG_CREFF_TC=0: the f16 plan runs the mma.sync march engine (fp32 LR feature p) as in round 1."""
+    monkeypatch.setenv("ARSEG_CREFF_TC", "0")
+    arch = "camvid-psp18"
+    H, W, stride, C = _FULL[arch]
+    sd, imgs, ref_p, mv, preds, logits, fused, lr_p = _full_case(arch)
+    eng = ev.NonKeyEngine(arch, sd, 1, H, W, 0.5, "f16", want_logits=True, want_p=True, device=DEV)
+    assert any(nm.endswith("_mma") for nm in eng.plan.names) and not eng.plan.hoisted, eng.plan.names
+    eng.set_inputs(imgs.to(DEV), torch.from_numpy(mv).unsqueeze(0).to(DEV), ref_p.to(DEV))
+    got = eng.step().cpu()
+    torch.cuda.synchronize()
+    tmax, trms, targ = TOL["f16"]
+    assert rel_err(eng.fused_p, fused) < tmax and rel_err(eng.logits, logits) < tmax
     assert float((got.long() != preds).float().mean()) <= targ
 
 

@@ -600,6 +600,31 @@ def test_creff_tc_row_segments_are_seamless(k, seg_rows, monkeypatch):
         assert rel_err(seg[0][i:i + 1], fused) < MMA_TOL
 
 
+@pytest.mark.parametrize("k", [3, 7])
+def test_creff_tcgen05_engine_fp32_keyframe_feature(k):
+    """engine = CREFF_TCGEN05 by name with an fp32 NHWC keyframe feature (what a keyframe engine hands over): the pre-pass
+    gathers fp32 taps with fp32 weights, so only the stored warped rows are f16."""
+    from arseg_b200 import synth
+    C, ncls, H, W, h, w = 64, 12, 40, 56, 20, 28
+    sd = creff_sd(C)
+    hr, lr = rnd(1, C, H, W, seed=71) * 0.6, _h(rnd(2, C, h, w, seed=72) * 0.4)
+    wcls, bcls = rnd(ncls, C, seed=73) * 0.2, rnd(ncls, seed=74) * 0.1
+    mvs = np.stack([synth.synth_mv_int16(H, W, 80 + i, distance=4 + 6 * i) for i in range(2)])
+    flow64 = torch.from_numpy(mvs.astype(np.float64) / 4.0)
+    out_p, out_l, out_a = ops.creff_fused(ops.nchw_to_nhwc(hr.to(DEV)), ops.nchw_to_nhwc(lr.to(DEV), torch.float16), *creff_args(sd), k,
+                                          flow=torch.from_numpy(mvs).to(DEV), wcls=wcls.to(DEV), bcls=bcls.to(DEV), log_softmax=True,
+                                          want_argmax=True, hr_shared=True, lr_layout=L.NHWC, hr_layout=L.NHWC, engine=L.CREFF_TCGEN05)
+    for i in range(2):
+        fused = O.creff(sd, "fuse_attention.", O.warp_feature(hr, O.resize_flow(flow64[i:i + 1], H, W)), lr[i:i + 1], k)
+        logits = F.log_softmax(F.conv2d(fused, wcls.view(ncls, C, 1, 1), bcls), dim=1)
+        assert rel_err(out_p[i:i + 1], fused) < MMA_TOL, rel_err(out_p[i:i + 1], fused)
+        assert rel_err(out_l[i:i + 1], logits) < MMA_TOL
+        assert torch.equal(out_a[i:i + 1].cpu().long(), out_l[i:i + 1].cpu().argmax(1))
+    with pytest.raises(L.ArsegError):      # the engine asked for by name does not fall back: fp32 LR feature is unsupported
+        ops.creff_fused(ops.nchw_to_nhwc(hr.to(DEV)), ops.nchw_to_nhwc(lr.to(DEV)), *creff_args(sd), k, want_logits=False,
+                        lr_layout=L.NHWC, hr_layout=L.NHWC, engine=L.CREFF_TCGEN05)
+
+
 def test_creff_tc_rejects_k9_and_mixed_dtypes():
     sd = creff_sd(64)
     hr, lr = rnd(1, 64, 16, 16, seed=1), rnd(1, 64, 8, 8, seed=2)

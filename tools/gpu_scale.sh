@@ -1,11 +1,11 @@
 #!/bin/bash
 # N-GPU pass (run under `gpurun --gpus N`): correctness of frame-level sharding (bit-identical to 1 GPU), then bench.py
-# (weak GOP-sharded value + the frame-sharded `strong` block in one run); $2 = workload (default camvid-psp18)
+# (weak GOP-sharded value + the frame-sharded `strong` block in one run); $2 = workload (default camvid-psp18), $3 = nocheck skips the sharding check
 N=${1:-2}
 WL=${2:-camvid-psp18}
 mkdir -p gpurun_out
 T="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
-timeout 300 $T tools/dist_check.py 2>&1 | grep dist_check | tee gpurun_out/dist_check_n${N}.log
+[ "$3" = nocheck ] || timeout 300 $T tools/dist_check.py 2>&1 | grep dist_check | tee gpurun_out/dist_check_n${N}.log
 timeout 600 $T bench.py --gpus $N --steps 10 --warmup 3 --alt-precision none --workload $WL > gpurun_out/bench_n${N}_${WL}.json 2> gpurun_out/bench_n${N}_${WL}.err
 python - $N $WL <<'PY'
 import json, sys

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--H", type=int, default=720)
     ap.add_argument("--W", type=int, default=960)
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--hr32", action="store_true", help="tc engine: fp32 NHWC keyframe feature (engine asked for by name)")
     a = ap.parse_args()
     torch.set_grad_enabled(False)
     dev = "cuda:0"
@@ -41,7 +42,7 @@ def main():
     wcls, bcls = (torch.randn(ncls, C, generator=g) * 0.2).to(dev), (torch.randn(ncls, generator=g) * 0.1).to(dev)
     lr_nhwc = ops.nchw_to_nhwc(lr, torch.float16 if a.engine == "tc" else torch.float32)
     if a.engine == "tc":      # tcgen05 engine: f16 keyframe feature + f16 LR feature
-        hr_in, kw = ops.nchw_to_nhwc(hr, torch.float16), dict(hr_layout=L.NHWC, engine=L.CREFF_MMA_F16)
+        hr_in, kw = ops.nchw_to_nhwc(hr, torch.float32 if a.hr32 else torch.float16), dict(hr_layout=L.NHWC, engine=L.CREFF_TCGEN05)
     elif a.engine == "mma":
         hr_in, kw = ops.nchw_to_nhwc(hr), dict(hr_layout=L.NHWC, engine=L.CREFF_MMA_F16)
     else:

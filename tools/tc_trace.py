@@ -7,7 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from arseg_b200 import _lib as L, ops, synth
 
 TAGS = {1: "gfull/ready", 2: "ddone(G)", 3: "lrfree", 4: "ofull(D)", 5: "sfull(D)", 6: "ddone(M)", 7: "pfull", 8: "afull", 9: "sfull(S)", 10: "ofull(E)", 11: "lfull", 12: "ofree"}
-ROLE = ["K0", "K1", "V0", "V1", "G0", "G1", "Qa", "Qb", "G2", "G3", "G4", "M", "E0", "E1", "E2", "E3", "S0", "S1", "S2", "S3"]
+ROLE = ["K0", "K1", "K2", "V0", "V1", "V2", "Qa", "Qb", "G0", "G1", "G2", "M", "E0", "E1", "E2", "E3", "S0", "S1", "S2", "S3"]
 
 def main():
     torch.set_grad_enabled(False)
