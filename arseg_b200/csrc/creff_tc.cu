@@ -39,10 +39,13 @@ constexpr int TSW = 16;                    // strip width (pixels)
 // two per scheduler -- and the latency-critical chain M -> S -> M -> E has the highest warp ids (the arbiter prefers them):
 //   0 K0  1 K1  2 K2  3 V0 | 4 V1  5 V2  6 Qa  7 Qb | 8 G0  9 G1  10 G2  11 M | 12..15 E | 16..19 S
 constexpr int TTHREADS = 640;
-constexpr int TD_WARPS = 8;                // K0 K1 K2 V0 V1 V2 Qa Qb
-constexpr int TKV_SPLIT = 3;               // column thirds of a K / V row
-constexpr int TQ_WARP0 = 6;                // warps 6, 7: the two column halves of Q
-constexpr int TG_WARP0 = 8, TG_WARPS = 3;  // warps 8, 9, 10
+#ifndef ARSEG_TC_KVSPLIT
+#define ARSEG_TC_KVSPLIT 3
+#endif
+constexpr int TKV_SPLIT = ARSEG_TC_KVSPLIT;    // column parts of a K / V row (3: the layout above; 2: K0 K1 V0 V1 Qa Qb + five G warps -- within 2 %)
+constexpr int TQ_WARP0 = 2 * TKV_SPLIT;        // two Q warps: the column halves
+constexpr int TD_WARPS = TQ_WARP0 + 2;
+constexpr int TG_WARP0 = TD_WARPS, TG_WARPS = 11 - TD_WARPS;
 constexpr int TM_WARP = 11;                // MMA issuer (and TMEM allocator)
 constexpr int TE_W0 = 12, TS_W0 = 16, TC_WARPS = 4;   // epilogue warps 12..15, softmax warps 16..19 (lane quarter = warp % 4)
 constexpr int TG_THREADS = 32 * TG_WARPS;
