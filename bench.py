@@ -407,7 +407,7 @@ def main():
         creff_gbs = cbytes / (creff_ms * 1e-3) / 1e9 if creff_ms > 0 else 0.0
         creff_gbs_full = full / (creff_ms * 1e-3) / 1e9 if creff_ms > 0 else 0.0
         conv_tflops = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
-        tr = traffic.get("creff_" + precision) if ARCH == "camvid-psp18" else None
+        tr = traffic.get("creff_f16" if r["tc"] else "creff_tf32") if ARCH == "camvid-psp18" else None      # tcgen05 kernels / march kernel
         roof_creff = {"kernel": "%s (MV warp + CReFF + classifier + log-softmax + argmax; %d launch(es) per step)" %
                                 ("creff_tc_warp_kernel + creff_tc_kernel [tcgen05]" if r["tc"] else "creff_march_kernel [mma.sync]" if C_P == 64 else "creff_wide kernels [mma.sync]",
                                  len(r["creff_names"])),

@@ -87,14 +87,22 @@ def main():
     if os.path.exists(os.path.join(OUT, "creff_sweep.md")):
         shutil.copy(os.path.join(OUT, "creff_sweep.md"), os.path.join(PROF, tag + "_creff_sweep.md"))
     launches(tag)
-    creff(tag, "conv_halo_f16.ncu-rep", "conv_halo", "-k regex:conv_tc_halo_kernel -s 20 -c 1 python bench.py --steps 1 --warmup 1 (one 3x3 layer of the f16 plan)")
-    tr = creff(tag, "creff_march_f16.ncu-rep", "creff")
-    if tr:
-        tp = os.path.join(PROF, "ncu_traffic.json")
-        cur = json.load(open(tp)) if os.path.exists(tp) else {}
-        cur.update({"creff_f16": tr, "creff_tf32": tr, "source": "%s_creff_ncu.txt (dram__bytes_read.sum + dram__bytes_write.sum, one launch = 11 frames; "
-                    "the tf32 plan launches the same kernel instantiation: LR p is fp32 in both)" % tag})
-        json.dump(cur, open(tp, "w"), indent=1)
+    for f in ("configs.md",):
+        if os.path.exists(os.path.join(OUT, f)):
+            shutil.copy(os.path.join(OUT, f), os.path.join(PROF, "%s_%s" % (tag, f)))
+    creff(tag, "conv_halo_f16.ncu-rep", "conv_halo", "-k regex:conv_tc_halo_kernel.*256 -s 14 -c 1 python bench.py --steps 1 --warmup 1 (one 3x3 layer of the f16 plan)")
+    tp = os.path.join(PROF, "ncu_traffic.json")
+    cur = json.load(open(tp)) if os.path.exists(tp) else {}
+    tc = creff(tag, "creff_tc_f16.ncu-rep", "creff_tc", "-k regex:creff_tc_kernel -c 1 python bench.py --steps 1 --warmup 1 (f16 plan: 11 frames per launch)")
+    tw = creff(tag, "creff_tc_warp_f16.ncu-rep", "creff_tc_warp", "-k regex:creff_tc_warp_kernel -c 1 python bench.py --steps 1 --warmup 1 (f16 plan: the MV-warp pre-pass of 11 frames)")
+    tm = creff(tag, "creff_march_tf32.ncu-rep", "creff_march", "-k regex:creff_march -c 1 python bench.py --precision tf32 --steps 1 --warmup 1 (tf32 plan: 11 frames per launch)")
+    if tc and tw:
+        cur.update({"creff_f16": tc + tw, "creff_f16_parts": {"creff_tc_kernel": tc, "creff_tc_warp_kernel": tw},
+                    "source_f16": "%s_creff_tc_ncu.txt + %s_creff_tc_warp_ncu.txt (dram__bytes_read.sum + dram__bytes_write.sum, one launch each = 11 frames)" % (tag, tag)})
+    if tm:
+        cur.update({"creff_tf32": tm, "source_tf32": "%s_creff_march_ncu.txt (march engine, fp32 LR feature, one launch = 11 frames)" % tag})
+    cur.pop("source", None)
+    json.dump(cur, open(tp, "w"), indent=1)
     print("profiles written for", tag)
 
 
