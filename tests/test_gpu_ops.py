@@ -625,6 +625,63 @@ def test_creff_tcgen05_engine_fp32_keyframe_feature(k):
                         lr_layout=L.NHWC, hr_layout=L.NHWC, engine=L.CREFF_TCGEN05)
 
 
+def _tc_args(hr, lr, sd, k, out_p, flow=None):
+    """arseg_creff_args for the tcgen05 engine, built by hand: the C ABI exactly as a non-Python caller sees it."""
+    import ctypes as C
+    ws = [sd["fuse_attention." + n].reshape(-1).float().to(DEV).contiguous() for n in
+          ("lr_query_conv.weight", "lr_query_conv.bias", "hr_key_conv.weight", "hr_key_conv.bias", "hr_value_conv.weight", "hr_value_conv.bias")]
+    N, h, w, Cc = lr.shape
+    _, H, W, _ = hr.shape
+    a = L.CreffArgs(hr.data_ptr(), 1, L.NHWC, L.CREFF_TCGEN05, flow.data_ptr() if flow is not None else None, L.I16 if flow is not None else 0,
+                    H if flow is not None else 0, W if flow is not None else 0, lr.data_ptr(), L.NHWC, L.F16, h, w, *[t.data_ptr() for t in ws],
+                    None, None, 0, 0, out_p.data_ptr(), None, None, N, Cc, H, W, k, None, 0, ops.dtype_code(hr.dtype), L.CREFF_PHASE_ALL)
+    return a, ws
+
+
+def test_creff_tcgen05_phases_and_workspace_contract():
+    """C ABI v6: PHASE_PREPASS followed by PHASE_MAIN on the same arguments equals PHASE_ALL bit for bit; a missing or short
+    workspace is refused with a message (no silent fallback), and the other engines treat PHASE_PREPASS as a no-op."""
+    import ctypes as C
+    from arseg_b200 import synth
+    Cc, H, W, h, w, k, N = 64, 40, 56, 20, 28, 7, 2
+    sd = creff_sd(Cc)
+    lib = L.load()
+    hr = ops.nchw_to_nhwc((rnd(1, Cc, H, W, seed=91) * 0.6).to(DEV), torch.float16)
+    lr = ops.nchw_to_nhwc((rnd(N, Cc, h, w, seed=92) * 0.4).to(DEV), torch.float16)
+    mv = torch.from_numpy(np.stack([synth.synth_mv_int16(H, W, 93 + i, distance=3 + 4 * i) for i in range(N)])).to(DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    outs = []
+    for phases in ((L.CREFF_PHASE_ALL,), (L.CREFF_PHASE_PREPASS, L.CREFF_PHASE_MAIN)):
+        out_p = torch.zeros((N, Cc, H, W), device=DEV)
+        a, keep = _tc_args(hr, lr, sd, k, out_p, mv)
+        need = int(lib.arseg_creff_workspace_bytes(C.byref(a)))
+        assert need >= N * H * W * 128
+        wsb = torch.empty(need, dtype=torch.uint8, device=DEV)
+        a.workspace, a.workspace_bytes = wsb.data_ptr(), need
+        for ph in phases:
+            a.phase = ph
+            L.check(lib.arseg_creff_fused_fwd(C.byref(a), st), "creff")
+        torch.cuda.synchronize()
+        outs.append(out_p)
+    assert torch.equal(outs[0], outs[1]) and float(outs[0].abs().max()) > 0
+    # workspace contract
+    out_p = torch.zeros((N, Cc, H, W), device=DEV)
+    a, keep = _tc_args(hr, lr, sd, k, out_p, mv)
+    assert lib.arseg_creff_fused_fwd(C.byref(a), st) != L.OK and b"workspace" in lib.arseg_last_error()
+    a.workspace, a.workspace_bytes = wsb.data_ptr(), 1024
+    assert lib.arseg_creff_fused_fwd(C.byref(a), st) != L.OK
+    a.phase = 7
+    assert lib.arseg_creff_fused_fwd(C.byref(a), st) != L.OK and b"phase" in lib.arseg_last_error()
+    # the march engine has no pre-pass: PHASE_PREPASS returns OK without touching the outputs
+    hr32, lr32 = ops.nchw_to_nhwc((rnd(1, Cc, H, W, seed=91) * 0.6).to(DEV)), ops.nchw_to_nhwc((rnd(N, Cc, h, w, seed=92) * 0.4).to(DEV))
+    out_m = torch.full((N, Cc, H, W), 7.0, device=DEV)
+    a, keep = _tc_args(hr32, lr32, sd, k, out_m, mv)
+    a.engine, a.lr_dtype, a.phase = L.CREFF_MMA_F16, L.F32, L.CREFF_PHASE_PREPASS
+    L.check(lib.arseg_creff_fused_fwd(C.byref(a), st), "creff")
+    torch.cuda.synchronize()
+    assert float(out_m.min()) == 7.0 and float(out_m.max()) == 7.0
+
+
 def test_creff_tc_rejects_k9_and_mixed_dtypes():
     sd = creff_sd(64)
     hr, lr = rnd(1, 64, 16, 16, seed=1), rnd(1, 64, 8, 8, seed=2)
