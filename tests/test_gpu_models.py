@@ -427,21 +427,30 @@ def test_keyframe_engine_full_shape_feeds_the_nonkey_engine():
     torch.cuda.synchronize()
 
 
-def test_nonkey_engine_reads_the_keyframe_feature_in_nhwc():
-    """ref_nhwc: the keyframe feature in the internal fp32 NHWC layout is read in place -- same class maps and logits as the
-    API-layout (NCHW) engine, one launch less."""
+@pytest.mark.parametrize("precision", ["f16", "tf32"])
+def test_nonkey_engine_reads_the_keyframe_feature_in_nhwc(precision):
+    """ref_nhwc: the keyframe feature in the internal NHWC layout (fp16 where the tcgen05 CReFF engine reads it, fp32 otherwise)
+    is read in place -- same class maps and logits as the API-layout (NCHW) engine, one launch less."""
     g = load_golden("camvid_psp18_s05")
     arch, _, sd, imgs, ref_p, mv, flow, scale = case_setup(g)
     H, W = imgs.shape[-2:]
     mvd = torch.from_numpy(mv).unsqueeze(0).to(DEV)
-    a = ev.NonKeyEngine(arch, sd, 1, H, W, scale, "f16", device=DEV, want_logits=True)
-    buf = torch.empty((1, H, W, ref_p.shape[1]), dtype=torch.float32, device=DEV)
-    b = ev.NonKeyEngine(arch, sd, 1, H, W, scale, "f16", device=DEV, want_logits=True, ref_nhwc=buf)
+    a = ev.NonKeyEngine(arch, sd, 1, H, W, scale, precision, device=DEV, want_logits=True)
+    dt = ev.internal_ref_dtype(arch, precision)
+    assert dt == (torch.float16 if precision == "f16" else torch.float32)
+    buf = torch.empty((1, H, W, ref_p.shape[1]), dtype=dt, device=DEV)
+    b = ev.NonKeyEngine(arch, sd, 1, H, W, scale, precision, device=DEV, want_logits=True, ref_nhwc=buf)
     a.set_inputs(imgs.to(DEV), mvd, ref_p.to(DEV))
     b.set_inputs(imgs.to(DEV), mvd, ref_p.to(DEV))
     assert b.launches_per_step == a.launches_per_step - 1
     pa, pb = a.step().clone(), b.step().clone()
     assert torch.equal(pa, pb) and torch.equal(a.logits, b.logits)
+    if precision == "f16":      # an fp32 internal feature is accepted as well (the pre-pass then gathers fp32 taps)
+        buf32 = torch.empty((1, H, W, ref_p.shape[1]), dtype=torch.float32, device=DEV)
+        c = ev.NonKeyEngine(arch, sd, 1, H, W, scale, precision, device=DEV, want_logits=True, ref_nhwc=buf32)
+        c.set_inputs(imgs.to(DEV), mvd, ref_p.to(DEV))
+        pc = c.step().clone()
+        assert float((pc != pa).float().mean()) < 2e-3 and rel_err(c.logits, a.logits.cpu()) < 3e-3
 
 
 def test_uint8_frame_ingest_engine_matches_float_engine():
