@@ -59,6 +59,9 @@ constexpr int TNB = 4;                     // mbarriers per hand-off (indexed by
 constexpr int TBAR_G = 1;                  // named barrier of the G group
 constexpr int TNCLS = 32;                  // classifier rows staged (>= ncls)
 constexpr int TWB_DEFAULT = 8;             // workspace rows per band of the MV-warp pre-pass
+// 128-thread CTAs: 0.340 ms against 0.358 ms with 256 threads (finer-grained tail); small enough to sit beside a resident conv CTA,
+// which however did not change how much of the pre-pass hides under the LR branch (~0.1 ms either way)
+constexpr int TWARP_THREADS = 128;
 
 template <int K> struct TCfg {
     static constexpr int R = K / 2;
@@ -952,7 +955,7 @@ __global__ void __launch_bounds__(256) creff_tc_rec_kernel(CreffMmaParams p, uin
 // bytes per pixel, fully coalesced 512-byte stores; the 4 x 8 tap loads of a lane are all in flight together).
 // ---------------------------------------------------------------------------------------------
 template <int K, bool HR32>
-__global__ void __launch_bounds__(256) creff_tc_warp_kernel(CreffMmaParams p, uint4* __restrict__ dst, int TWB) {
+__global__ void __launch_bounds__(TWARP_THREADS) creff_tc_warp_kernel(CreffMmaParams p, uint4* __restrict__ dst, int TWB) {
     using Cf = TCfg<K>;
     constexpr int PXB = HR32 ? 256 : 128;          // bytes per source pixel
     constexpr int NB = HR32 ? 2 : 4;               // quads of pixels per pass: 16 tap loads (16 bytes each) per lane in flight
@@ -1169,9 +1172,9 @@ static int creff_tc_launch_n(CreffMmaParams& p, int hr_dtype, int phase, void* w
         int TWB = TWB_DEFAULT;
         { const char* e = getenv("ARSEG_TC_TWB"); if (e && atoi(e) > 0) TWB = atoi(e); }
         const long long warps = (long long)ceil_div(t_hp<K>(p.H), TWB) * p.N * ceil_div(TWB * t_wp<K>(p.W), 32);
-        ARSEG_REQUIRE((long long)p.N * p.H * p.W < 0xffffffffLL && ceil_div_ll(warps, 8) < 2147483647LL, "creff_tc: too many pixels");
-        if (hr_dtype == ARSEG_F16) creff_tc_warp_kernel<K, false><<<(unsigned)ceil_div_ll(warps, 8), 256, 0, st>>>(p, reinterpret_cast<uint4*>(warped), TWB);
-        else creff_tc_warp_kernel<K, true><<<(unsigned)ceil_div_ll(warps, 8), 256, 0, st>>>(p, reinterpret_cast<uint4*>(warped), TWB);
+        ARSEG_REQUIRE((long long)p.N * p.H * p.W < 0xffffffffLL && ceil_div_ll(warps, TWARP_THREADS / 32) < 2147483647LL, "creff_tc: too many pixels");
+        if (hr_dtype == ARSEG_F16) creff_tc_warp_kernel<K, false><<<(unsigned)ceil_div_ll(warps, TWARP_THREADS / 32), TWARP_THREADS, 0, st>>>(p, reinterpret_cast<uint4*>(warped), TWB);
+        else creff_tc_warp_kernel<K, true><<<(unsigned)ceil_div_ll(warps, TWARP_THREADS / 32), TWARP_THREADS, 0, st>>>(p, reinterpret_cast<uint4*>(warped), TWB);
         ARSEG_CHECK_LAUNCH("creff_tc_warp");
         if (phase == ARSEG_CREFF_PHASE_PREPASS) return ARSEG_OK;
     }
