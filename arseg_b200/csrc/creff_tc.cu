@@ -43,8 +43,14 @@ constexpr int TTHREADS = 640;
 #define ARSEG_TC_KVSPLIT 3
 #endif
 constexpr int TKV_SPLIT = ARSEG_TC_KVSPLIT;    // column parts of a K / V row (3: the layout above; 2: K0 K1 V0 V1 Qa Qb + five G warps -- within 2 %)
-constexpr int TQ_WARP0 = 2 * TKV_SPLIT;        // two Q warps: the column halves
-constexpr int TD_WARPS = TQ_WARP0 + 2;
+#ifndef ARSEG_TC_QROWSPLIT
+#define ARSEG_TC_QROWSPLIT 1
+#endif
+constexpr int TQ_RSPLIT = ARSEG_TC_QROWSPLIT;  // Q warps per column half: 1 = four query rows per warp and half-step, 2 = two rows each
+constexpr int TQ_ROWS = 4 / TQ_RSPLIT;
+constexpr int TQ_WARP0 = 2 * TKV_SPLIT;        // Q warps: two column halves x TQ_RSPLIT row groups
+constexpr int TD_WARPS = TQ_WARP0 + 2 * TQ_RSPLIT;
+static_assert(TD_WARPS <= 9, "at least two gather warps");
 constexpr int TG_WARP0 = TD_WARPS, TG_WARPS = 11 - TD_WARPS;
 constexpr int TM_WARP = 11;                // MMA issuer (and TMEM allocator)
 constexpr int TE_W0 = 12, TS_W0 = 16, TC_WARPS = 4;   // epilogue warps 12..15, softmax warps 16..19 (lane quarter = warp % 4)
@@ -457,7 +463,7 @@ __device__ __forceinline__ int t_kv_last_reader(int h) {
 template <int K>
 __device__ __forceinline__ void t_d_role(const CreffMmaParams& p, const TSmem& sm, int x0, int ya, int NH, int S) {
     using Cf = TCfg<K>;
-    const int lane = threadIdx.x & 31, dw = (int)(threadIdx.x >> 5), qhalf = dw - TQ_WARP0;
+    const int lane = threadIdx.x & 31, dw = (int)(threadIdx.x >> 5), qhalf = (dw - TQ_WARP0) & 1, qrow = ((dw - TQ_WARP0) >> 1) * TQ_ROWS;
     const uint32_t lane_sub = (uint32_t)((lane & 3) * 4), lane_chunk = (uint32_t)(lane >> 2);
     if (dw < TQ_WARP0) {
         // ---------------- K (warps 0..2) or V (3..5): columns [c_lo, c_lo + ncol) of four K/V rows per half-step ----------------
@@ -542,17 +548,17 @@ __device__ __forceinline__ void t_d_role(const CreffMmaParams& p, const TSmem& s
             if (h >= Cf::HP) {
                 const int q0 = 4 * (h - Cf::HP), ti = q0 >> 3, qy0 = q0 & 7;
                 if (ti >= 1) tbar_wait<true>(sm.sfull, ti - 1, 5);                      // S = Q K^T of the previous tile has retired: the A tile is free
-                uint32_t ra[6];
+                uint32_t ra[TQ_ROWS + 2];
 #pragma unroll
-                for (int i = 0; i < 6; ++i) ra[i] = lbase + (uint32_t)(((q0 + i) % TLRR) * (TLC * 128));
-                const uint32_t qo = sm.sQ + (uint32_t)(qy0 * TSW * 128);
+                for (int i = 0; i < TQ_ROWS + 2; ++i) ra[i] = lbase + (uint32_t)(((q0 + qrow + i) % TLRR) * (TLC * 128));
+                const uint32_t qo = sm.sQ + (uint32_t)((qy0 + qrow) * TSW * 128);
                 // this warp's column half: output columns [8 qhalf, 8 qhalf + 8) from lr ring columns [8 qhalf, 8 qhalf + 10)
                 const int xlo = 8 * qhalf;
-                float2 win[6][3];
+                float2 win[TQ_ROWS + 2][3];
 #pragma unroll
                 for (int c = 0; c < 2; ++c)
 #pragma unroll
-                    for (int i = 0; i < 6; ++i) win[i][c] = t_h2f(t_lds32(ra[i] + (xlo + c) * 128 + lx[c]));     // (xlo + c) & 7 = c
+                    for (int i = 0; i < TQ_ROWS + 2; ++i) win[i][c] = t_h2f(t_lds32(ra[i] + (xlo + c) * 128 + lx[c]));     // (xlo + c) & 7 = c
 #pragma unroll 1
                 for (int x3 = 0; x3 < TSW / 2; x3 += 3) {
 #pragma unroll
@@ -562,10 +568,10 @@ __device__ __forceinline__ void t_d_role(const CreffMmaParams& p, const TSmem& s
                             const int sa = u, sb = (u + 1) % 3, sc = (u + 2) % 3;
                             const uint32_t lin = (uint32_t)((x + 2) * 128) + (((lane_chunk ^ (uint32_t)((x + 2) & 7)) << 4) + lane_sub);
 #pragma unroll
-                            for (int i = 0; i < 6; ++i) win[i][sc] = t_h2f(t_lds32(ra[i] + lin));
+                            for (int i = 0; i < TQ_ROWS + 2; ++i) win[i][sc] = t_h2f(t_lds32(ra[i] + lin));
                             const uint32_t qst = qo + (uint32_t)(x * 128) + (((lane_chunk ^ (uint32_t)(x & 7)) << 4) + lane_sub);
 #pragma unroll
-                            for (int r = 0; r < 4; ++r) {
+                            for (int r = 0; r < TQ_ROWS; ++r) {
                                 const float2 v = t_dw9(w, win[r], win[r + 1], win[r + 2], sa, sb, sc);
                                 t_sts32(qst + (uint32_t)(r * TSW * 128), pack_h2_sat(v.x, v.y));
                             }
