@@ -702,7 +702,7 @@ __device__ __forceinline__ void t_m_role(const TSmem& sm, uint32_t tmem, int S, 
 __device__ __forceinline__ void t_ld_row(uint32_t ta, uint32_t* s) { t_ld16(ta, s); t_ld8(ta + 16, s + 16); }
 
 template <int K>
-__device__ __forceinline__ void t_s_role(const TSmem& sm, uint32_t tmem, int S) {
+__device__ __forceinline__ void t_s_role(const TSmem& sm, uint32_t tmem, int S, int dbg) {
     using Cf = TCfg<K>;
     constexpr float LOG2E = 1.4426950408889634f;
     static_assert((K + 1) % 2 == 0, "the row loops are unrolled by two");
@@ -751,6 +751,9 @@ __device__ __forceinline__ void t_s_role(const TSmem& sm, uint32_t tmem, int S) 
         tbar_wait(sm.sfull, i, 9);
         if (cw == 0) TEV(1, i, 1);
         t_fence_after();
+#ifdef ARSEG_TTRACE
+        if (dbg & 16) { t_fence_before(); tbar_arrive(sm.pfull, i); continue; }      // timing experiment: no softmax work (results are garbage)
+#endif
         // ---------------- pass 1: the shift of the maximum (the next row's TMEM load is in flight while a row is reduced) ----------------
         uint32_t sa[24], sb[24];
         float d = -INFINITY;
@@ -836,6 +839,13 @@ __device__ __forceinline__ void t_e_role(const CreffMmaParams& p, const TSmem& s
         tbar_arrive(sm.lrfree, i);
         // ---------------- fused = lr_up + O / sum (model/attention.py:207,210) ----------------
         tbar_wait(sm.ofull, i, 10);
+#ifdef ARSEG_TTRACE
+        if (p.dbg & 32) {      // timing experiment: no epilogue work (results are garbage)
+            t_fence_before(); tbar_arrive(sm.ofree, i);
+            if (NCP > 0) { tbar_arrive(sm.afull, i); tbar_wait(sm.lfull, i, 11); }
+            continue;
+        }
+#endif
         if (cw == 0) TEV(2, i, 5);
         t_fence_after();
         const int py = ya + 8 * i + qy;
@@ -1134,7 +1144,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) creff_tc_kernel(CreffMmaParams p,
 #ifdef ARSEG_TTRACE
     const long long t_role = clock64();
 #endif
-    if (warp >= TS_W0) t_s_role<K>(sm, tmem, S);
+    if (warp >= TS_W0) t_s_role<K>(sm, tmem, S, p.dbg);
     else if (warp >= TE_W0) t_e_role<K, NCP>(p, sm, tmem, n, x0, ya, yb, S);
     else if (warp == TM_WARP) t_m_role<K, NCP>(sm, tmem, S, p.dbg);
     else if (warp < TG_WARP0) t_d_role<K>(p, sm, x0, ya, NH, S);
