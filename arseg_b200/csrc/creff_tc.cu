@@ -165,8 +165,7 @@ __device__ __forceinline__ void tev(int role, int tile, int ev) {
 #else
 #define TEV(role, tile, ev)
 #endif
-// SLEEP: producer roles (G, D) back off with nanosleep between polls -- a polling warp takes issue slots from the working
-// ones (35 % of all issued instructions before); the latency-critical roles (M, C) poll without sleeping.
+// (the SLEEP template flag is kept for the call sites: producer and consumer roles now wait the same way)
 template <bool SLEEP = false>
 __device__ __forceinline__ void tbar_wait(uint64_t* bars, int idx, int tag = 0) {
 #ifdef ARSEG_TTRACE
@@ -176,23 +175,22 @@ __device__ __forceinline__ void tbar_wait(uint64_t* bars, int idx, int tag = 0) 
     const uint32_t parity = (uint32_t)((idx / TNB) & 1);
     uint32_t ok;
     // bounded: a protocol bug must trap, not hang the GPU box
+    // try_wait with a suspend-time hint: the thread is parked in hardware until the phase completes or the hint (ns) expires, so a
+    // waiting warp issues one instruction per time-out instead of a poll loop (nanosleep back-off loops were 45 % of all
+    // executed instructions; 2.75 -> 2.72 ms)
 #pragma unroll 1
-    for (int spin = 0; spin < (1 << 20); ++spin) {
+    for (int spin = 0; spin < (1 << 16); ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+            : "=r"(ok) : "r"(addr), "r"(parity), "r"(20000u) : "memory");
         if (ok) {
 #ifdef ARSEG_TTRACE
             if (blockIdx.x == TTRACE_CTA && (threadIdx.x & 31) == 0) g_ttrace[(threadIdx.x >> 5) * 16 + tag] += clock64() - t_in;
 #endif
             return;
         }
-        // a polling warp takes issue slots from the working ones (S / E poll for most of a tile and have the highest
-        // scheduling priority): back off -- a few immediate polls for the short hand-offs, then sleep
-        if (SLEEP) __nanosleep(spin < 4 ? 32 : 128);
-        else if (spin >= 8) __nanosleep(spin < 64 ? 40 : 100);
     }
     tbar_timeout(tag, idx);
 }
