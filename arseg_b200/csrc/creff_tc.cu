@@ -591,21 +591,29 @@ __device__ __forceinline__ void t_d_role(const CreffMmaParams& p, const TSmem& s
 template <int K>
 __device__ __forceinline__ void t_issue_qk(const TSmem& sm, uint32_t tmem, int i) {
     using Cf = TCfg<K>;
-    // key rows [8i + PADR, + NKR) of the ring, TWO rows (N = 48) per MMA: the same instruction shapes for every tile whatever
-    // the ring phase (chunks never straddle the ring end: even row counts), so a pixel's logits do not depend on which tile
-    // of which row segment computes them (bit-exact results across segmentations / frame counts)
+    // key rows [8i + PADR, + NKR) of the ring in as few MMAs as possible: up to TEN rows (N = 240 <= 256) per instruction, cut at
+    // the ring end (row counts are even, so every piece is a multiple of N = 48).  Small-N UMMA is issue-bound (28 MMAs of
+    // N = 48 retire in ~1060 cycles against ~340 of math); ARSEG_TC_QK48 restores the fixed two-row pieces.
     const int b0 = (8 * i + Cf::PADR) % Cf::KVR;
     const uint64_t dq = t_desc(sm.sQ), dk = t_desc(sm.sK);
-    constexpr uint32_t ID = t_idesc(2 * TKP, 0);
-    constexpr uint32_t RING16 = (uint32_t)(Cf::KVR * TROWB) >> 4;
-    uint32_t off = (uint32_t)(b0 * (TROWB >> 4)), td = tmem;
+    uint32_t td = tmem;
+    int row = b0, left = Cf::NKR;
 #pragma unroll 1
-    for (int r = 0; r < Cf::NKR; r += 2) {
+    while (left > 0) {
+#ifdef ARSEG_TC_QK48
+        const int seg = 2;
+#else
+        int seg = min(left, Cf::KVR - row);
+        seg = seg > 10 ? 10 : seg;
+#endif
+        const uint32_t id = t_idesc(seg * TKP, 0);
+        const uint64_t dkr = dk + (uint64_t)((uint32_t)row * (TROWB >> 4));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) t_mma_ss(dq + (uint64_t)(2 * k), dk + off + (uint64_t)(2 * k), td, k != 0, ID);
-        off += 2 * (TROWB >> 4);
-        off = off >= RING16 ? off - RING16 : off;
-        td += 2 * TKP;
+        for (int k = 0; k < 4; ++k) t_mma_ss(dq + (uint64_t)(2 * k), dkr + (uint64_t)(2 * k), td, k != 0, id);
+        td += (uint32_t)(seg * TKP);
+        row += seg;
+        row = row >= Cf::KVR ? row - Cf::KVR : row;
+        left -= seg;
     }
 }
 template <int K>
