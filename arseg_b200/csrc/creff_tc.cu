@@ -287,7 +287,8 @@ struct TSmem {
     uint32_t sK, sV, sQ, sW, sOnes, rings;       // shared-window addresses; rings = hr ring, lr ring, scratch
     uint4* posa;                                 // [2][PMAX] gather records: {w0 | w1 << 16, w2 | w3 << 16 (f16), source pixel | lr << 31, ring offset | swizzle << 28}
     float* s_bc;                                 // [TNCLS]
-    uint64_t *gfull /* index g + 1 */, *ddone, *lrfree, *sfull, *pfull, *ofull, *ofree, *afull, *lfull;
+    uint64_t *gfull /* lr_up rows gathered, index g + 1 */, *hfull /* warped-hr rows landed (bulk copies), index g + 1 */, *ddone, *lrfree, *sfull, *pfull, *ofull,
+             *ofree, *afull, *lfull;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -407,19 +408,20 @@ __device__ __forceinline__ void t_g_role(const CreffMmaParams& p, const TSmem& s
         for (int j = 0; j < TJA; ++j) issue(tap[j], buf, j);
         if (g + 1 < NH) fetch(g + 1);                               // the next step's records: in flight during the gather loop
         if (g >= 2) tbar_wait<true>(sm.ddone, g - 2, 2);            // D half-step g-2 done: the hr / lr rows this step overwrites are read
+        if (gt == 0) {
+            // the step's warped-hr rows: one bulk copy each, completing on their own hand-off barrier -- the K / V warps (the
+            // producers that set the pace) wait for these only, never for the lr_up gather below
+            int h0, nh, l0, nl;
+            t_step_geom<K>(g, h0, nh, l0, nl);
+            const uint32_t bar = s_u32(sm.hfull + ((g + 1) & (TNB - 1)));
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)nh * Cf::HROW_BYTES) : "memory");
+            for (int r = 0; r < nh; ++r)
+                t_bulk_row(sm.rings + (uint32_t)((h0 + r) % THRR) * Cf::HROW_BYTES, wsrc + (size_t)(h0 + r) * wrow, Cf::HROW_BYTES, bar);
+        }
         {
             // lr_up rows double as the residual: E takes the rows of tile i at the start of its step
             const int num = 4 * (g - Cf::HP) + 5 - TLRR - 1;        // last overwritten lr row - 1
             if (num >= 0) { const int im = num >> 3; tbar_wait<true>(sm.lrfree, im < S - 1 ? im : S - 1, 3); }
-        }
-        if (gt == 0) {
-            // the step's warped-hr rows: one bulk copy each, completing on the step's hand-off barrier
-            int h0, nh, l0, nl;
-            t_step_geom<K>(g, h0, nh, l0, nl);
-            const uint32_t bar = s_u32(sm.gfull + ((g + 1) & (TNB - 1)));
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)nh * Cf::HROW_BYTES) : "memory");
-            for (int r = 0; r < nh; ++r)
-                t_bulk_row(sm.rings + (uint32_t)((h0 + r) % THRR) * Cf::HROW_BYTES, wsrc + (size_t)(h0 + r) * wrow, Cf::HROW_BYTES, bar);
         }
 #ifdef ARSEG_TTRACE
         if (!(p.dbg & 4))
@@ -479,7 +481,7 @@ __device__ __forceinline__ void t_d_role(const CreffMmaParams& p, const TSmem& s
         const uint32_t hbase = sm.rings + (uint32_t)(c_lo * 128 + lane * 4);
 #pragma unroll 1
         for (int h = 0; h < NH; ++h) {
-            tbar_wait<true>(sm.gfull, h + 1, 1);
+            tbar_wait<true>(sm.hfull, h + 1, 1);
             {
                 const int jm = t_kv_last_reader<K>(h);
                 if (jm >= 0) tbar_wait<true>(sm.ofull, jm < S - 1 ? jm : S - 1, 4);     // P V of the last tile that read these ring slots has retired
@@ -1105,7 +1107,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) creff_tc_kernel(CreffMmaParams p,
     sm.posa = reinterpret_cast<uint4*>(pRec);
     sm.s_bc = reinterpret_cast<float*>(pRec + Cf::REC_BYTES);
     sm.gfull = reinterpret_cast<uint64_t*>(sm.s_bc + TNCLS);
-    sm.ddone = sm.gfull + TNB; sm.lrfree = sm.ddone + TNB; sm.sfull = sm.lrfree + TNB; sm.pfull = sm.sfull + TNB;
+    sm.hfull = sm.gfull + TNB; sm.ddone = sm.hfull + TNB; sm.lrfree = sm.ddone + TNB; sm.sfull = sm.lrfree + TNB; sm.pfull = sm.sfull + TNB;
     sm.ofull = sm.pfull + TNB; sm.ofree = sm.ofull + TNB; sm.afull = sm.ofree + TNB; sm.lfull = sm.afull + TNB;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm.lfull + TNB);
 
@@ -1121,7 +1123,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) creff_tc_kernel(CreffMmaParams p,
 
     if (tid == 0) {
         for (int i = 0; i < TNB; ++i) {
-            tbar_init(sm.gfull + i, TG_WARPS * TARRIVALS + 1);   /* + the bulk-copy issuer's expect_tx arrival */ tbar_init(sm.ddone + i, TD_WARPS * TARRIVALS); tbar_init(sm.lrfree + i, TC_WARPS * TARRIVALS);
+            tbar_init(sm.gfull + i, TG_WARPS * TARRIVALS); tbar_init(sm.hfull + i, 1);   /* the bulk-copy issuer's expect_tx arrival */ tbar_init(sm.ddone + i, TD_WARPS * TARRIVALS); tbar_init(sm.lrfree + i, TC_WARPS * TARRIVALS);
             tbar_init(sm.sfull + i, 1); tbar_init(sm.pfull + i, TC_WARPS * TARRIVALS); tbar_init(sm.ofull + i, 1);
             tbar_init(sm.afull + i, TC_WARPS * TARRIVALS); tbar_init(sm.lfull + i, 1); tbar_init(sm.ofree + i, TC_WARPS * TARRIVALS);
         }
