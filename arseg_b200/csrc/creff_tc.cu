@@ -481,6 +481,7 @@ __device__ __forceinline__ void t_d_role(const CreffMmaParams& p, const TSmem& s
         const uint32_t hbase = sm.rings + (uint32_t)(c_lo * 128 + lane * 4);
 #pragma unroll 1
         for (int h = 0; h < NH; ++h) {
+            if (h == 0) tbar_wait<true>(sm.hfull, 0, 1);                        // rows 0, 1 (step -1) complete on their own barrier phase
             tbar_wait<true>(sm.hfull, h + 1, 1);
             {
                 const int jm = t_kv_last_reader<K>(h);
