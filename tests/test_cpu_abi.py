@@ -34,6 +34,43 @@ def test_binding_covers_header(lib_path):
     assert lib.arseg_abi_version() == _lib.ABI_VERSION == 6
 
 
+def test_struct_layouts_match_the_header(tmp_path):
+    """The ctypes mirrors of the argument structs must have the C compiler's layout of include/arseg.h (size and the offset of
+    every field): a plain-C probe compiled with gcc prints them."""
+    import subprocess
+    structs = {"arseg_creff_args": _lib.CreffArgs, "arseg_conv_desc": getattr(_lib, "ConvDesc", None)}
+    text = open(os.path.join(ROOT, "include", "arseg.h")).read()
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "arseg.h"', "int main(void) {"]
+    checked = {}
+    for cname, cls in structs.items():
+        if cls is None or ("} %s;" % cname) not in text:
+            continue
+        checked[cname] = cls
+        src.append('printf("%s size %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            cfield = {"inp": "in"}.get(fname, fname)          # `in` is a Python keyword
+            src.append('printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, cfield))
+    src.append("return 0; }")
+    assert "arseg_creff_args" in checked
+    c = tmp_path / "probe.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "probe"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)], text=True).split("\n")
+    seen = 0
+    for line in out:
+        if not line:
+            continue
+        cname, field, val = line.split()
+        cls = checked[cname]
+        if field == "size":
+            assert ctypes.sizeof(cls) == int(val), (cname, ctypes.sizeof(cls), val)
+        else:
+            assert getattr(cls, field).offset == int(val), (cname, field, getattr(cls, field).offset, val)
+        seen += 1
+    assert seen > 40
+
+
 def test_error_reporting_without_gpu(lib_path):
     lib = _lib.load()
     # null pointers are rejected before any CUDA call; message is retrievable
